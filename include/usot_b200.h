@@ -1,0 +1,126 @@
+/*
+ * usot_b200 -- C ABI of the Blackwell-native (sm_100a) USOT forward path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  All `float*` arguments are DEVICE
+ * pointers unless the name says `host_`; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * Work is enqueued on `stream`; no call synchronises unless stated.  Every function returns 0 on success and a
+ * non-zero code on failure, in which case usot_last_error() (thread-local) describes it -- the library never
+ * calls exit() (the reference does, lib/models/prroi_pool/src/prroi_pooling_gpu_impl.cu:20-27).
+ *
+ * Layout conventions
+ *   "nchw" : the reference's layout (contiguous N,C,H,W fp32)       -- images, rois, cls/bbox maps, loss scalars
+ *   "nhwc" : contiguous N,H,W,C fp32 -- every 256-channel feature map that crosses the boundary (zf, xf, memory
+ *            features).  The Python host exposes them as NCHW-shaped tensors with channels-last strides, which the
+ *            reference's callers accept (lib/tracker/usot_tracker.py:105-106,196-199,258-261).
+ *
+ * Reference interfaces replaced (file:line under /root/reference):
+ *   usot_prroi_pool_forward          <- prroi_pooling_forward_cuda       lib/models/prroi_pool/src/prroi_pooling_gpu.c:22-44
+ *                                       (+ PrRoIPoolingForwardGpu        lib/models/prroi_pool/src/prroi_pooling_gpu_impl.cu:381-402)
+ *   usot_xcorr_depthwise             <- xcorr_depthwise                  lib/models/connect.py:147-157
+ *   usot_groupdw_xcorr               <- GroupDW.forward                  lib/models/connect.py:86-102
+ *   usot_conv2d_nhwc                 <- nn.Conv2d + BatchNorm2d (+ReLU)  lib/models/modules.py:37-58, connect.py:20-53
+ *   usot_engine_template             <- USOT_.template                   lib/models/models.py:173-177
+ *   usot_engine_track                <- USOT_.track                      lib/models/models.py:179-198
+ *   usot_engine_extract_memory_feature <- USOT_.extract_memory_feature   lib/models/models.py:200-206
+ *   usot_engine_backbone_neck        <- feature_extractor + neck         lib/models/models.py:39-40,181-184
+ *   usot_engine_forward_train        <- USOT_.forward                    lib/models/models.py:208-295
+ *   usot_tracker_postprocess         <- USOTTracker.update tensor path   lib/tracker/usot_tracker.py:137-163
+ *   usot_engine_load_tensor/finalize <- load_state_dict contract         lib/utils/train_utils.py:92-128
+ */
+#ifndef USOT_B200_H
+#define USOT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USOT_API __attribute__((visibility("default")))
+
+typedef struct usot_engine usot_engine;
+
+/* precision modes of the dense convolutions */
+enum {
+    USOT_PREC_FP32_SIMT = 0, /* fp32 FMA on CUDA cores: exact reference arithmetic, cross-check path            */
+    USOT_PREC_FP16X3_TC = 1, /* tcgen05 kind::f16, operands split hi+lo fp16, 3 MMAs: fp32-equivalent (default) */
+    USOT_PREC_FP16_TC = 2    /* tcgen05 kind::f16 single pass, fp32 accumulate: fast mode (BASELINE config 3)    */
+};
+
+USOT_API const char* usot_last_error(void);
+USOT_API int usot_abi_version(void);
+/* Process-wide performance knobs (never change results): "groupdw_strips" = 2 | 3. */
+USOT_API int usot_set_tunable(const char* name, int value);
+
+/* Measurement hooks.  Launches of this library's kernels are always counted per kernel family; with on=1 every launch is
+ * additionally bracketed by CUDA events on its own stream so that usot_profile_read can report the family's device time.
+ * usot_profile_read synchronises the device; out[4] = {launches, ms, algorithmic FLOPs, algorithmic bytes} since reset. */
+USOT_API int usot_profile_reset(int on);
+USOT_API int usot_profile_family_count(void);
+USOT_API const char* usot_profile_family_name(int family);
+USOT_API int usot_profile_read(int family, double* out);
+
+/* ------------------------------- stand-alone operators ------------------------------------------------ */
+
+/* PrRoIPool forward, reference layout.  features (n_features,C,H,W) nchw; rois (n_rois,5) = [batch_idx,x1,y1,x2,y2];
+ * output (n_rois,C,PH,PW) nchw, fully overwritten. */
+USOT_API int usot_prroi_pool_forward(const float* features, const float* rois, float* output, int n_features, int n_rois,
+                                     int channels, int height, int width, int pooled_height, int pooled_width,
+                                     float spatial_scale, void* stream);
+
+/* Depth-wise cross-correlation, reference layout.  x (bx,C,hx,wx), kernel (bk,C,hk,wk) with bk == bx or bk == 1
+ * (broadcast, the view trick of connect.py:151-156); out (bx,C,hx-hk+1,wx-wk+1). */
+USOT_API int usot_xcorr_depthwise(const float* x, const float* kernel, float* out, int bx, int bk, int channels, int hx, int wx,
+                                  int hk, int wk, void* stream);
+
+/* Fused GroupDW, nhwc.  x11 (nx,F-2,F-2,C), x12 (nx,F-4,F-2,C), x21 (nx,F-2,F-4,C); z11 (nz,5,5,C), z12 (nz,3,5,C),
+ * z21 (nz,5,3,C); weight = the raw 3-vector (softmax is applied inside; read back with one stream sync);
+ * out (n_out,F-6,F-6,C).  Sample n uses x[n / (n_out/nx)] and z[n] (or z[0] when nz == 1). */
+USOT_API int usot_groupdw_xcorr(const float* x11, const float* x12, const float* x21, const float* z11, const float* z12,
+                                const float* z21, const float* weight, float* out, int nx, int nz, int n_out, int channels,
+                                int feat_size, void* stream);
+
+/* Dense conv + per-channel affine (+residual)(+ReLU), nhwc.  weight_kn is (kh*kw*cin, cout) with k = (r*kw+s)*cin + c.
+ * residual may be NULL.  precision is one of USOT_PREC_*. */
+USOT_API int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh, int kw,
+                              int stride, int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift,
+                              const float* residual, int relu, float* out, int precision, void* stream);
+
+USOT_API int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream);
+USOT_API int usot_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, void* stream);
+
+/* ------------------------------- engine ----------------------------------------------------------------- */
+
+USOT_API int usot_engine_create(usot_engine** out, int device, int precision);
+USOT_API int usot_engine_destroy(usot_engine* e);
+/* Stage one state_dict tensor (HOST pointer, fp32, reference shape/order).  Name = reference state_dict key. */
+USOT_API int usot_engine_load_tensor(usot_engine* e, const char* name, const float* host_data, int64_t numel);
+/* Fold BN, repack and upload every staged tensor.  Synchronises the device.  May be called again after reloading. */
+USOT_API int usot_engine_finalize(usot_engine* e);
+/* Bytes of device memory currently owned by the engine (weights + workspace arena). */
+USOT_API int64_t usot_engine_device_bytes(const usot_engine* e);
+
+/* feature_extractor + neck:  x (n,3,size,size) nchw -> xf (n,F,F,256) nhwc, F = ((size-7)/2+1 -> pool -> s2) */
+USOT_API int usot_engine_backbone_neck(usot_engine* e, const float* x, int n, int size, float* xf, void* stream);
+USOT_API int usot_feature_size(int image_size);
+
+/* USOT_.template.  z (n,3,size,size) nchw.  template_bbox (n,4) in feature coords or NULL (pr_pool=False: centre crop
+ * [4:-4]).  zf (n,7,7,256) nhwc out.  x_ori (n,F,F,256) nhwc out, may be NULL. */
+USOT_API int usot_engine_template(usot_engine* e, const float* z, int n, int size, const float* template_bbox, float* zf,
+                                  float* x_ori, void* stream);
+
+/* USOT_.track.  x (n,3,size,size) nchw; zf (nz,7,7,256) nhwc, nz == n or 1; template_mem (n*nq,7,7,256) nhwc or NULL
+ * (nq = 0: offline only).  Outputs nchw: cls (n,1,R,R), bbox (n,4,R,R), cls_mem (n,1,R,R) [ignored if nq == 0];
+ * xf (n,F,F,256) nhwc, may be NULL.  R = F - 6. */
+USOT_API int usot_engine_track(usot_engine* e, const float* x, int n, int size, const float* zf, int nz, const float* template_mem,
+                               int nq, float* cls, float* bbox, float* cls_mem, float* xf, void* stream);
+
+/* USOT_.extract_memory_feature.  Exactly one of ori_x (n,3,size,size nchw) / xf (n,feat,feat,256 nhwc) is non-NULL.
+ * search_bbox (n,4); out (n,7,7,256) nhwc. */
+USOT_API int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n, int size, const float* xf, int feat,
+                                                const float* search_bbox, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USOT_B200_H */

@@ -1,0 +1,148 @@
+"""GPU parity of the stand-alone operators (through the C ABI) against the oracle / torch-fp32 CPU reference."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import usot_oracle as O
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from usot_b200 import ops as _ops
+    return _ops
+
+
+def _ref_prroi(features, rois, ph, pw, scale):
+    """The reference's own CUDA kernel (compiled unchanged into oracle/_ref) through ctypes."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libprroi_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libprroi_ref.so not built (make -C oracle)")
+    lib = ctypes.CDLL(path)
+    f, r = features.cuda().contiguous(), rois.cuda().contiguous()
+    n, c, h, w = f.shape
+    out = torch.zeros((r.shape[0], c, ph, pw), device="cuda")
+    P = ctypes.c_void_p
+    lib.PrRoIPoolingForwardGpu.argtypes = [P, P, P, P] + [ctypes.c_int] * 5 + [ctypes.c_float, ctypes.c_int]
+    lib.PrRoIPoolingForwardGpu(P(torch.cuda.current_stream().cuda_stream), P(f.data_ptr()), P(r.data_ptr()), P(out.data_ptr()), c, h, w,
+                               ph, pw, ctypes.c_float(scale), out.numel())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+@pytest.mark.parametrize("h,n", [(15, 3), (31, 4), (33, 2)])
+def test_prroi_vs_reference_kernel_and_oracle(ops, h, n):
+    g = torch.Generator().manual_seed(5 + h)
+    feat = torch.randn(n, 256, h, h, generator=g)
+    lo = torch.rand(n, 2, generator=g) * (h / 2) - 1.5  # some boxes start outside the map (usot_tracker.py:349)
+    sz = torch.rand(n, 2, generator=g) * (h / 2) + 0.3
+    rois = torch.cat([torch.arange(n).float().view(-1, 1).flip(0), lo, lo + sz], 1)
+    rois[-1, 3] = rois[-1, 1]  # zero-width roi -> zeros (prroi_pooling_gpu_impl.cu:189-193)
+    ours = ops.prroi_pool2d(feat.cuda(), rois.cuda(), 7, 7, 1.0).cpu()
+    oracle = O.prroi_pool2d(feat, rois, 7, 7, 1.0)
+    ref = _ref_prroi(feat, rois, 7, 7, 1.0)
+    assert rel_err(oracle, ref) <= 5e-6, "oracle restatement drifted from the reference kernel"
+    assert rel_err(ours, ref) <= 5e-6
+    assert float(ours[-1].abs().max()) == 0.0
+
+
+def test_prroi_empty_and_errors(ops):
+    out = ops.prroi_pool2d(torch.zeros(1, 8, 15, 15, device="cuda"), torch.zeros(0, 5, device="cuda"), 7, 7, 1.0)
+    assert tuple(out.shape) == (0, 8, 7, 7)
+    with pytest.raises(NotImplementedError):
+        ops.prroi_pool2d(torch.zeros(1, 8, 15, 15), torch.zeros(1, 5), 7, 7, 1.0)
+
+
+@pytest.mark.parametrize("bx,bk,hx,wx,hk,wk", [(3, 3, 29, 29, 5, 5), (4, 1, 27, 29, 3, 5), (2, 2, 31, 29, 5, 3), (1, 1, 7, 7, 7, 7)])
+def test_xcorr_depthwise(ops, bx, bk, hx, wx, hk, wk):
+    g = torch.Generator().manual_seed(bx * 100 + hx)
+    x, k = torch.randn(bx, 256, hx, wx, generator=g), torch.randn(bk, 256, hk, wk, generator=g)
+    ref = O.xcorr_depthwise(x, k) if bk == bx else O.xcorr_depthwise(x, k)  # view trick broadcasts bk == 1
+    ours = ops.xcorr_depthwise(x.cuda(), k.cuda()).cpu()
+    assert ours.shape == ref.shape
+    assert rel_err(ours, ref) <= 2e-6
+
+
+def _groupdw_ref(xs, zs, w, rep):
+    xs = [t.permute(0, 3, 1, 2).repeat_interleave(rep, 0) for t in xs]
+    zs = [t.permute(0, 3, 1, 2) for t in zs]
+    return O.groupdw(w, zs, xs).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("F_,nx,nz,n_out,strips", [(31, 3, 1, 3, 3), (31, 2, 2, 2, 2), (33, 2, 6, 6, 3), (33, 1, 1, 1, 2), (31, 2, 14, 14, 3)])
+def test_groupdw_fused(ops, F_, nx, nz, n_out, strips):
+    from usot_b200 import _lib
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_strips", strips))
+    g = torch.Generator().manual_seed(F_ + nx)
+    C = 256
+    xs = [torch.randn(nx, F_ - 2, F_ - 2, C, generator=g), torch.randn(nx, F_ - 4, F_ - 2, C, generator=g),
+          torch.randn(nx, F_ - 2, F_ - 4, C, generator=g)]
+    zs = [torch.randn(nz, 5, 5, C, generator=g), torch.randn(nz, 3, 5, C, generator=g), torch.randn(nz, 5, 3, C, generator=g)]
+    w = torch.tensor([0.3, -0.2, 0.9])
+    ref = _groupdw_ref(xs, zs, w, n_out // nx)
+    ours = ops.groupdw_xcorr([t.cuda() for t in xs], [t.cuda() for t in zs], w.cuda(), n_out).cpu()
+    assert ours.shape == ref.shape
+    assert rel_err(ours, ref) <= 3e-6  # pure fp32 FMA, only the summation order differs
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_strips", 3))
+
+
+def test_groupdw_linearity_full_size(ops):
+    """Size-independent property at the BASELINE batch (256 crops): xcorr is linear in the search maps."""
+    torch.manual_seed(0)
+    C, F_, B = 256, 31, 256
+    mk = lambda *s: torch.randn(*s, device="cuda")
+    xa = [mk(B, F_ - 2, F_ - 2, C), mk(B, F_ - 4, F_ - 2, C), mk(B, F_ - 2, F_ - 4, C)]
+    xb = [mk(B, F_ - 2, F_ - 2, C), mk(B, F_ - 4, F_ - 2, C), mk(B, F_ - 2, F_ - 4, C)]
+    zs = [mk(1, 5, 5, C), mk(1, 3, 5, C), mk(1, 5, 3, C)]
+    w = torch.tensor([1.0, 0.5, 1.5], device="cuda")
+    ya, yb = ops.groupdw_xcorr(xa, zs, w, B), ops.groupdw_xcorr(xb, zs, w, B)
+    yab = ops.groupdw_xcorr([a + 2.0 * b for a, b in zip(xa, xb)], zs, w, B)
+    assert rel_err(yab, ya + 2.0 * yb) <= 1e-5
+    # and sample 17 of the batch equals the same sample run alone (no cross-sample leakage)
+    y17 = ops.groupdw_xcorr([t[17:18].contiguous() for t in xa], zs, w, 1)
+    assert torch.equal(y17[0], ya[17])
+
+
+CONV_CASES = [
+    # cin, cout, k, stride, pad, dil, h, w, residual, relu
+    (64, 64, 1, 1, (0, 0), (1, 1), 17, 17, False, True),
+    (64, 256, 1, 1, (0, 0), (1, 1), 9, 11, True, True),
+    (128, 128, 3, 2, (0, 0), (1, 1), 21, 21, False, True),     # layer2.0.conv2
+    (256, 512, 3, 2, (0, 0), (1, 1), 15, 15, False, False),    # layer2.0.downsample
+    (256, 256, 3, 1, (2, 2), (2, 2), 13, 13, False, True),     # layer3.x.conv2 (dilated)
+    (512, 1024, 3, 1, (1, 1), (1, 1), 9, 9, False, False),     # layer3.0.downsample
+    (256, 256, 3, 1, (0, 0), (2, 1), 15, 15, False, True),     # matrix12
+    (256, 256, 3, 1, (0, 0), (1, 2), 7, 7, False, True),       # matrix21 on the template
+    (256, 256, 3, 1, (1, 1), (1, 1), 25, 25, False, True),     # tower
+    (1024, 256, 1, 1, (0, 0), (1, 1), 31, 31, False, False),   # neck
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("precision", ["fp32"])
+def test_conv2d_nhwc(ops, case, precision):
+    cin, cout, k, stride, pad, dil, h, w, use_res, relu = case
+    g = torch.Generator().manual_seed(cin + cout + k)
+    n = 3
+    x = torch.randn(n, cin, h, w, generator=g)
+    wgt = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    ref = F.conv2d(x, wgt, None, stride, pad, dil) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    res = torch.randn_like(ref) if use_res else None
+    if use_res:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    ours = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().cuda(), wgt.cuda(), scale.cuda(), shift.cuda(), stride, pad, dil,
+                           None if res is None else res.permute(0, 2, 3, 1).contiguous().cuda(), relu, precision)
+    ours = ours.permute(0, 3, 1, 2).cpu()
+    assert ours.shape == ref.shape
+    assert rel_err(ours, ref) <= 5e-6

@@ -1,0 +1,58 @@
+"""Host-side mirror of the reference interface: state_dict contract, namespace shadowing, loud CPU failure."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import usot_oracle as O
+from usot_b200 import USOT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_contract_matches_reference_keys():
+    net = USOT()
+    sd = net.state_dict()
+    ref = O.make_state_dict(0)
+    assert len(sd) == 444
+    assert set(sd.keys()) == set(ref.keys())
+    for k in ref:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    net.load_state_dict(ref, strict=True)
+
+
+def test_parameter_groups_addressable_like_train_script():
+    # scripts/train_usot.py:74-121 walks these attributes
+    net = USOT({"mem_size": 3, "pr_pool": True})
+    assert net.mem_size == 3 and net.pr_pool is True
+    for layer in (net.features.features.layer1, net.features.features.layer2, net.features.features.layer3):
+        assert sum(p.numel() for p in layer.parameters()) > 0
+    assert sum(p.numel() for p in net.neck.parameters()) == 1024 * 256 + 2 * 256
+    assert sum(p.numel() for p in net.connect_model.parameters()) > 15e6
+
+
+def test_cpu_model_fails_loudly():
+    net = USOT()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.template(torch.zeros(1, 3, 127, 127), torch.tensor([[3.0, 3.0, 11.0, 11.0]]))
+    net.zf = torch.zeros(1, 256, 7, 7)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.track(torch.zeros(1, 3, 255, 255))
+
+
+def test_ops_reject_cpu_tensors():
+    from usot_b200 import ops
+    with pytest.raises(NotImplementedError):
+        ops.prroi_pool2d(torch.zeros(1, 4, 8, 8), torch.zeros(1, 5), 7, 7, 1.0)
+    with pytest.raises(AssertionError):
+        ops.prroi_pool2d(torch.zeros(1, 4, 8, 8, dtype=torch.float64), torch.zeros(1, 5, dtype=torch.float64), 7, 7, 1.0)
+
+
+def test_namespace_shadowing():
+    """lib.models.models resolves to this repo when it precedes a reference-like tree on PYTHONPATH."""
+    code = "import lib.models.models as m, usot_b200; assert m.USOT is usot_b200.USOT; print('shadow-ok')"
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "shadow-ok" in r.stdout, r.stderr

@@ -1,0 +1,90 @@
+// Shared declarations for the usot_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+
+namespace usot {
+
+// ---- error plumbing: kernels never exit(); launchers return cudaError_t-like ints ----------
+void set_error(const std::string& msg);
+#define USOT_CUDA_OK(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::usot::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+#define USOT_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            ::usot::set_error(std::string("usot_b200: ") + (msg) + " [" #cond "]");             \
+            return 2;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+// ---- activation storage ------------------------------------------------------------------
+// All internal activations are NHWC.  Two storage formats:
+//   F32   : one fp32 plane (SIMT path, bandwidth kernels)
+//   SPLIT : two fp16 planes, value = hi + lo (tcgen05 path; hi = rn_fp16(v), lo = rn_fp16(v - hi))
+struct Act {
+    float* f32 = nullptr;
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    int n = 0, h = 0, w = 0, c = 0;
+    size_t numel() const { return (size_t)n * h * w * c; }
+};
+
+struct ConvGeom {
+    int n, h, w, cin;        // input NHWC
+    int cout, kh, kw;        // filter
+    int stride, ph, pw, dh, dw;
+    int ho, wo;              // output spatial size
+};
+
+inline int conv_out(int in, int k, int stride, int pad, int dil) { return (in + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
+
+// Epilogue of every dense conv: y = acc*scale[c] + shift[c] (+ residual) ; optional ReLU.
+struct Epilogue {
+    const float* scale;     // [cout] folded BN scale (1 if none)
+    const float* shift;     // [cout] folded BN shift + conv bias
+    const float* residual;  // NHWC fp32 [m][cout] or nullptr
+    int relu;
+};
+
+// ---- launchers (kernels_simt.cu) -----------------------------------------------------------
+int launch_stem(const float* x_nchw, int n, int s, const float* w_packed /*[147][64]*/, const float* scale,
+                const float* shift, float* out_nhwc /*[n][ho][ho][64]*/, cudaStream_t st);
+int launch_maxpool3x3s2p1(const float* in, int n, int h, int w, int c, float* out, cudaStream_t st);
+int launch_conv_simt(const float* in, const ConvGeom& g, const float* w_kn /*[kh*kw*cin][cout]*/, const Epilogue& ep,
+                     float* out, cudaStream_t st);
+// Fused GroupDW: out[n] = sum_i sw[i] * xcorr(x_i[n / rep], z_i[zb])  with zb = (nz == n_out ? n : 0)
+struct GroupDWArgs {
+    const float* x11; const float* x12; const float* x21;  // [nx][F-2][F-2][C], [nx][F-4][F-2][C], [nx][F-2][F-4][C]
+    const float* z11; const float* z12; const float* z21;  // [nz][5][5][C], [nz][3][5][C], [nz][5][3][C]
+    const float* dw_weight;                                // [3] raw (softmax applied inside)
+    float* out;                                            // [n_out][R][R][C]
+    int nx, nz, n_out, C, F;                               // R = F - 6
+};
+extern int g_groupdw_strips;
+int launch_groupdw(const GroupDWArgs& a, cudaStream_t st);  // reads dw_weight back (one stream sync)
+int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st);  // softmaxed weights given
+// Single depth-wise xcorr, NCHW (the reference op, connect.py:147-157)
+int launch_xcorr_nchw(const float* x, const float* k, float* out, int nx, int nk, int C, int hx, int wx, int hk, int wk,
+                      cudaStream_t st);
+// Skinny prediction conv 3x3 p1, Cin = C, Cout <= 4, NHWC in -> NCHW out.  mode 0: out = mul*(y+b) ; mode 1: exp(adjust*(y+b)+bias4[co])
+int launch_pred_conv(const float* in, int n, int r, int C, const float* w /*[9][cout][C]*/, const float* b, int cout,
+                     int mode, float mul, const float* adjust, const float* bias4, float* out_nchw, cudaStream_t st);
+int launch_conf_fusion(const float* conf, const float* value, int b, int nq, size_t per_map /*R*R*C*/, float* out,
+                       cudaStream_t st);
+int launch_prroi_nhwc(const float* feat, int n_feat, int h, int w, int c, const float* boxes4, int n_rois, float* out_nhwc,
+                      cudaStream_t st);
+int launch_prroi_nchw(const float* feat, int c, int h, int w, const float* rois5, int n_rois, int ph, int pw, float scale,
+                      float* out, cudaStream_t st);
+int launch_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, cudaStream_t st);
+int launch_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, cudaStream_t st);
+int launch_center_crop_nhwc(const float* in, int n, int h, int w, int c, int l, float* out, cudaStream_t st);
+
+}  // namespace usot

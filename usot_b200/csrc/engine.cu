@@ -1,0 +1,670 @@
+// Engine + C ABI of the usot_b200 library.
+//
+// The engine owns the packed weights (BN folded on the host at finalize()) and a grow-only device arena for
+// activations, and runs the reference's forward graphs as sequences of the kernels in kernels_simt.cu /
+// conv_tc.cu on the caller's stream:
+//   backbone_neck   ResNet_plus2.forward + AdjustLayer      lib/models/modules.py:137-151, connect.py:294-296
+//   template        USOT_.template                          lib/models/models.py:173-177
+//   track           USOT_.track -> box_tower_reg.forward    lib/models/models.py:179-198, connect.py:221-281
+//   extract_memory_feature                                  lib/models/models.py:200-206
+#include "common.cuh"
+#include "../../include/usot_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace usot {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+// ---- optional per-kernel-family profiling (CUDA events on the launching stream) + launch counting ----
+enum { FAM_CONV = 0, FAM_STEM, FAM_POOL, FAM_XCORR, FAM_PRED, FAM_FUSION, FAM_PRROI, FAM_OTHER, FAM_COUNT };
+static const char* kFamNames[FAM_COUNT] = {"conv", "stem", "maxpool", "groupdw_xcorr", "pred_conv", "conf_fusion", "prroi_pool", "other"};
+struct Profiler {
+    bool on = false;
+    long long launches[FAM_COUNT] = {0};
+    double flops[FAM_COUNT] = {0};   // algorithmic FLOPs (dense convs) issued since reset
+    double bytes[FAM_COUNT] = {0};   // algorithmic bytes (bandwidth kernels) issued since reset
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
+};
+static Profiler g_prof;
+struct Scope {
+    int fam; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    Scope(int fam_, cudaStream_t st_, double flops = 0, double bytes = 0) : fam(fam_), st(st_) {
+        g_prof.launches[fam]++;
+        g_prof.flops[fam] += flops;
+        g_prof.bytes[fam] += bytes;
+        if (g_prof.on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~Scope() { if (g_prof.on) { cudaEventRecord(b, st); g_prof.ev.push_back({fam, {a, b}}); } }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Architecture table (restates the reference constructors, lib/models/modules.py:61-135, connect.py:160-219)
+// ---------------------------------------------------------------------------------------------
+struct ConvSpec {
+    std::string name, bn;
+    int cin, cout, k, stride, ph, pw, dh, dw;
+    bool bias, relu;
+};
+
+static std::vector<ConvSpec> build_specs() {
+    std::vector<ConvSpec> v;
+    const std::string bk = "features.features.";
+    auto add = [&](const std::string& name, const std::string& bn, int cin, int cout, int k, int stride, int ph, int pw, int dh,
+                   int dw, bool bias, bool relu) { v.push_back({name, bn, cin, cout, k, stride, ph, pw, dh, dw, bias, relu}); };
+    struct L { const char* name; int planes, blocks, stride, dil; };
+    const L layers[3] = {{"layer1", 64, 3, 1, 1}, {"layer2", 128, 4, 2, 1}, {"layer3", 256, 6, 1, 2}};
+    int inplanes = 64;
+    for (const L& l : layers) {
+        for (int i = 0; i < l.blocks; ++i) {
+            std::string p = bk + l.name + "." + std::to_string(i) + ".";
+            const bool down = i == 0;
+            const int s = down ? l.stride : 1;
+            int pad = 2 - s, dil = l.dil;  // Bottleneck.__init__, modules.py:18-29
+            if (down && dil > 1) { dil /= 2; pad = dil; }
+            if (dil > 1) pad = dil;
+            add(p + "conv1", p + "bn1", inplanes, l.planes, 1, 1, 0, 0, 1, 1, false, true);
+            add(p + "conv2", p + "bn2", l.planes, l.planes, 3, s, pad, pad, dil, dil, false, true);
+            add(p + "conv3", p + "bn3", l.planes, l.planes * 4, 1, 1, 0, 0, 1, 1, false, true /* after the residual add */);
+            if (down) {
+                if (l.stride == 1 && l.dil == 1)  // modules.py:110-115
+                    add(p + "downsample.0", p + "downsample.1", inplanes, l.planes * 4, 1, 1, 0, 0, 1, 1, false, false);
+                else {  // modules.py:116-126 (3x3 shortcut; dilation is not passed to the conv)
+                    const int dpad = l.dil > 1 ? l.dil / 2 : 0;
+                    add(p + "downsample.0", p + "downsample.1", inplanes, l.planes * 4, 3, l.stride, dpad, dpad, 1, 1, false, false);
+                }
+                inplanes = l.planes * 4;
+            }
+        }
+    }
+    add("neck.downsample.0", "neck.downsample.1", 1024, 256, 1, 1, 0, 0, 1, 1, false, false);  // connect.py:287-290
+    for (const char* enc : {"cls_encode", "reg_encode"})
+        for (int m = 0; m < 3; ++m)
+            for (const char* br : {"k", "s"}) {
+                static const char* mn[3] = {"matrix11", "matrix12", "matrix21"};
+                static const int dh[3] = {1, 2, 1}, dw[3] = {1, 1, 2};  // connect.py:20-53
+                std::string p = std::string("connect_model.") + enc + "." + mn[m] + "_" + br + ".";
+                add(p + "0", p + "1", 256, 256, 3, 1, 0, 0, dh[m], dw[m], false, true);
+            }
+    for (const char* g : {"conf_gen", "value_gen"}) {  // connect.py:112-121
+        std::string p = std::string("connect_model.conf_fusion.") + g + ".";
+        add(p + "0", p + "1", 256, 256, 3, 1, 1, 1, 1, 1, true, true);
+    }
+    for (const char* t : {"bbox_tower", "cls_tower", "cls_memory_tower"})  // connect.py:178-209
+        for (int i = 0; i < 4; ++i) {
+            std::string p = std::string("connect_model.") + t + ".";
+            add(p + std::to_string(3 * i), p + std::to_string(3 * i + 1), 256, 256, 3, 1, 1, 1, 1, 1, true, true);
+        }
+    return v;
+}
+
+struct ConvW {
+    ConvSpec s;
+    float* w_kn = nullptr;   // [k*k*cin][cout] fp32 (SIMT path)
+    float* scale = nullptr;  // folded BN
+    float* shift = nullptr;
+};
+
+struct PredW {
+    float* w = nullptr;  // [9][cout][256]
+    float* b = nullptr;
+    int cout = 0;
+};
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    bool plan = false;  // planning pass: count bytes, launch nothing
+    void* alloc(size_t bytes) {
+        size_t a = (off + 255) & ~size_t(255);
+        off = a + bytes;
+        return plan ? reinterpret_cast<void*>(uintptr_t(0x1000) + a) : (void*)(base + a);
+    }
+    float* f(size_t n) { return static_cast<float*>(alloc(n * sizeof(float))); }
+};
+
+}  // namespace usot
+
+using namespace usot;
+
+struct usot_engine {
+    int device = 0;
+    int precision = USOT_PREC_FP32_SIMT;
+    bool finalized = false;
+    std::map<std::string, std::vector<float>> host;
+    std::map<std::string, ConvW> convs;
+    std::vector<void*> owned;  // device allocations holding weights
+    int64_t weight_bytes = 0;
+    float *stem_w = nullptr, *stem_scale = nullptr, *stem_shift = nullptr;
+    PredW bbox_pred, cls_pred, cls_memory_pred;
+    float dw_cls[3] = {0, 0, 0}, dw_reg[3] = {0, 0, 0};  // softmax(GroupDW.weight)
+    float *adjust = nullptr, *bias4 = nullptr;
+    Arena arena;
+    std::mutex mu;  // one forward at a time per engine (DataParallel replicas own separate engines)
+
+    ~usot_engine() {
+        cudaSetDevice(device);
+        for (void* p : owned) cudaFree(p);
+        if (arena.base) cudaFree(arena.base);
+    }
+};
+
+namespace usot {
+
+#define RUN(expr)                        \
+    do {                                 \
+        if (!ar.plan) {                  \
+            int _rc = (expr);            \
+            if (_rc) return _rc;         \
+        }                                \
+    } while (0)
+
+static int upload(usot_engine* e, const std::vector<float>& h, float** out) {
+    void* d = nullptr;
+    USOT_CUDA_OK(cudaMalloc(&d, h.size() * sizeof(float)));
+    USOT_CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    e->owned.push_back(d);
+    e->weight_bytes += (int64_t)h.size() * sizeof(float);
+    *out = static_cast<float*>(d);
+    return 0;
+}
+
+static const std::vector<float>* find(usot_engine* e, const std::string& k, size_t numel) {
+    auto it = e->host.find(k);
+    if (it == e->host.end()) { set_error("usot_b200: missing state_dict tensor '" + k + "'"); return nullptr; }
+    if (it->second.size() != numel) {
+        set_error("usot_b200: tensor '" + k + "' has " + std::to_string(it->second.size()) + " elements, expected " + std::to_string(numel));
+        return nullptr;
+    }
+    return &it->second;
+}
+
+// scale/shift of conv(+bias)+BN folded in double precision (eps = 1e-5, nn.BatchNorm2d default)
+static int fold_bn(usot_engine* e, const std::string& conv, const std::string& bn, int cout, bool bias, std::vector<float>& scale,
+                   std::vector<float>& shift) {
+    scale.assign(cout, 1.f);
+    shift.assign(cout, 0.f);
+    const std::vector<float>* b = nullptr;
+    if (bias && !(b = find(e, conv + ".bias", cout))) return 3;
+    if (bn.empty()) {
+        if (b) shift = *b;
+        return 0;
+    }
+    const auto *g = find(e, bn + ".weight", cout), *be = find(e, bn + ".bias", cout), *mu = find(e, bn + ".running_mean", cout),
+               *var = find(e, bn + ".running_var", cout);
+    if (!g || !be || !mu || !var) return 3;
+    for (int c = 0; c < cout; ++c) {
+        double sc = (double)(*g)[c] / std::sqrt((double)(*var)[c] + 1e-5);
+        double sh = (double)(*be)[c] - (double)(*mu)[c] * sc + (b ? (double)(*b)[c] * sc : 0.0);
+        scale[c] = (float)sc;
+        shift[c] = (float)sh;
+    }
+    return 0;
+}
+
+static int finalize_impl(usot_engine* e) {
+    USOT_CUDA_OK(cudaSetDevice(e->device));
+    for (void* p : e->owned) cudaFree(p);
+    e->owned.clear();
+    e->convs.clear();
+    e->weight_bytes = 0;
+    std::vector<float> scale, shift, packed;
+    {   // stem: OIHW (64,3,7,7) -> [(c*7+kh)*7+kw][co]
+        const auto* w = find(e, "features.features.conv1.weight", 64 * 147);
+        if (!w) return 3;
+        packed.assign(147 * 64, 0.f);
+        for (int co = 0; co < 64; ++co)
+            for (int k = 0; k < 147; ++k) packed[(size_t)k * 64 + co] = (*w)[(size_t)co * 147 + k];
+        if (int rc = fold_bn(e, "features.features.conv1", "features.features.bn1", 64, false, scale, shift)) return rc;
+        if (upload(e, packed, &e->stem_w) || upload(e, scale, &e->stem_scale) || upload(e, shift, &e->stem_shift)) return 1;
+    }
+    for (const ConvSpec& s : build_specs()) {
+        const int K = s.k * s.k * s.cin;
+        const auto* w = find(e, s.name + ".weight", (size_t)s.cout * K);
+        if (!w) return 3;
+        packed.assign((size_t)K * s.cout, 0.f);
+        for (int co = 0; co < s.cout; ++co)
+            for (int c = 0; c < s.cin; ++c)
+                for (int t = 0; t < s.k * s.k; ++t)
+                    packed[((size_t)t * s.cin + c) * s.cout + co] = (*w)[((size_t)co * s.cin + c) * s.k * s.k + t];
+        if (int rc = fold_bn(e, s.name, s.bn, s.cout, s.bias, scale, shift)) return rc;
+        ConvW cw;
+        cw.s = s;
+        if (upload(e, packed, &cw.w_kn) || upload(e, scale, &cw.scale) || upload(e, shift, &cw.shift)) return 1;
+        e->convs[s.name] = cw;
+    }
+    auto pack_pred = [&](const std::string& name, int cout, PredW& pw) -> int {
+        const auto* w = find(e, name + ".weight", (size_t)cout * 256 * 9);
+        const auto* b = find(e, name + ".bias", cout);
+        if (!w || !b) return 3;
+        packed.assign((size_t)9 * cout * 256, 0.f);
+        for (int co = 0; co < cout; ++co)
+            for (int c = 0; c < 256; ++c)
+                for (int t = 0; t < 9; ++t) packed[((size_t)t * cout + co) * 256 + c] = (*w)[((size_t)co * 256 + c) * 9 + t];
+        pw.cout = cout;
+        if (upload(e, packed, &pw.w) || upload(e, *b, &pw.b)) return 1;
+        return 0;
+    };
+    if (int rc = pack_pred("connect_model.bbox_pred", 4, e->bbox_pred)) return rc;
+    if (int rc = pack_pred("connect_model.cls_pred", 1, e->cls_pred)) return rc;
+    if (int rc = pack_pred("connect_model.cls_memory_pred", 1, e->cls_memory_pred)) return rc;
+    auto softmax3 = [&](const std::string& name, float* out) -> int {
+        const auto* w = find(e, name, 3);
+        if (!w) return 3;
+        double m = std::fmax((*w)[0], std::fmax((*w)[1], (*w)[2]));
+        double ex[3], s = 0;
+        for (int i = 0; i < 3; ++i) { ex[i] = std::exp((double)(*w)[i] - m); s += ex[i]; }
+        for (int i = 0; i < 3; ++i) out[i] = (float)(ex[i] / s);
+        return 0;
+    };
+    if (int rc = softmax3("connect_model.cls_dw.weight", e->dw_cls)) return rc;
+    if (int rc = softmax3("connect_model.reg_dw.weight", e->dw_reg)) return rc;
+    const auto* adj = find(e, "connect_model.adjust", 1);
+    const auto* b4 = find(e, "connect_model.bias", 4);
+    if (!adj || !b4) return 3;
+    if (upload(e, *adj, &e->adjust) || upload(e, *b4, &e->bias4)) return 1;
+    USOT_CUDA_OK(cudaDeviceSynchronize());
+    e->finalized = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward graphs
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+    usot_engine* e;
+    Arena& ar;
+    cudaStream_t st;
+};
+
+static int run_conv(Ctx& c, const std::string& name, const float* in, int n, int h, int w, const float* residual, float* out,
+                    int* ho_out = nullptr, int* wo_out = nullptr) {
+    Arena& ar = c.ar;
+    auto it = c.e->convs.find(name);
+    USOT_REQUIRE(it != c.e->convs.end(), "unknown conv layer");
+    const ConvW& cw = it->second;
+    ConvGeom g;
+    g.n = n; g.h = h; g.w = w; g.cin = cw.s.cin; g.cout = cw.s.cout; g.kh = g.kw = cw.s.k;
+    g.stride = cw.s.stride; g.ph = cw.s.ph; g.pw = cw.s.pw; g.dh = cw.s.dh; g.dw = cw.s.dw;
+    g.ho = conv_out(h, g.kh, g.stride, g.ph, g.dh);
+    g.wo = conv_out(w, g.kw, g.stride, g.pw, g.dw);
+    if (ho_out) *ho_out = g.ho;
+    if (wo_out) *wo_out = g.wo;
+    Epilogue ep{cw.scale, cw.shift, residual, cw.s.relu ? 1 : 0};
+    if (!ar.plan) {
+        Scope sc(FAM_CONV, c.st, 2.0 * n * g.ho * g.wo * (double)g.cout * g.kh * g.kw * g.cin);
+        RUN(launch_conv_simt(in, g, cw.w_kn, ep, out, c.st));
+    }
+    return 0;
+}
+
+static inline int conv_hw(int in, int k, int s, int p, int d) { return conv_out(in, k, s, p, d); }
+
+// x (n,3,S,S) nchw -> xf (n,F,F,256) nhwc written to xf_out (arena-allocated if NULL)
+static int backbone_neck(Ctx& c, const float* x, int n, int S, float** xf_out, int* F_out) {
+    Arena& ar = c.ar;
+    usot_engine* e = c.e;
+    const int h1 = (S - 7) / 2 + 1;
+    const int h2 = (h1 + 2 - 3) / 2 + 1;
+    float* a0 = ar.f((size_t)n * h1 * h1 * 64);
+    if (!ar.plan) {
+        Scope sc(FAM_STEM, c.st, 2.0 * n * h1 * h1 * 64.0 * 147);
+        RUN(launch_stem(x, n, S, e->stem_w, e->stem_scale, e->stem_shift, a0, c.st));
+    }
+    float* cur = ar.f((size_t)n * h2 * h2 * 64);
+    if (!ar.plan) {
+        Scope sc(FAM_POOL, c.st, 0, 4.0 * n * 64 * ((double)h1 * h1 + (double)h2 * h2));
+        RUN(launch_maxpool3x3s2p1(a0, n, h1, h1, 64, cur, c.st));
+    }
+    int h = h2;
+    struct L { const char* name; int planes, blocks; };
+    const L layers[3] = {{"layer1", 64, 3}, {"layer2", 128, 4}, {"layer3", 256, 6}};
+    for (const L& l : layers) {
+        for (int i = 0; i < l.blocks; ++i) {
+            const std::string p = std::string("features.features.") + l.name + "." + std::to_string(i) + ".";
+            const float* res = cur;
+            int ho = h, wo = h;
+            if (i == 0) {
+                const ConvSpec& ds = e->convs.at(p + "downsample.0").s;
+                const int hd = conv_hw(h, ds.k, ds.stride, ds.ph, ds.dh);
+                float* r = ar.f((size_t)n * hd * hd * l.planes * 4);
+                if (int rc = run_conv(c, p + "downsample.0", cur, n, h, h, nullptr, r)) return rc;
+                res = r;
+            }
+            float* t1 = ar.f((size_t)n * h * h * l.planes);
+            if (int rc = run_conv(c, p + "conv1", cur, n, h, h, nullptr, t1)) return rc;
+            const ConvSpec& s2 = e->convs.at(p + "conv2").s;
+            ho = wo = conv_hw(h, 3, s2.stride, s2.ph, s2.dh);
+            float* t2 = ar.f((size_t)n * ho * wo * l.planes);
+            if (int rc = run_conv(c, p + "conv2", t1, n, h, h, nullptr, t2)) return rc;
+            float* t3 = ar.f((size_t)n * ho * wo * l.planes * 4);
+            if (int rc = run_conv(c, p + "conv3", t2, n, ho, wo, res, t3)) return rc;
+            cur = t3;
+            h = ho;
+        }
+    }
+    float* xf = *xf_out ? *xf_out : ar.f((size_t)n * h * h * 256);
+    if (int rc = run_conv(c, "neck.downsample.0", cur, n, h, h, nullptr, xf)) return rc;
+    *xf_out = xf;
+    *F_out = h;
+    return 0;
+}
+
+struct Enc3 {
+    float* m[3];
+};
+
+// matrix.forward for one branch: three parallel 3x3 convs on the same input (connect.py:55-74)
+static int encode(Ctx& c, const char* enc, char branch, const float* in, int n, int f, Enc3* out) {
+    Arena& ar = c.ar;
+    static const char* mn[3] = {"matrix11", "matrix12", "matrix21"};
+    static const int dh[3] = {1, 2, 1}, dw[3] = {1, 1, 2};
+    for (int i = 0; i < 3; ++i) {
+        const int ho = f - 2 * dh[i], wo = f - 2 * dw[i];
+        out->m[i] = ar.f((size_t)n * ho * wo * 256);
+        const std::string name = std::string("connect_model.") + enc + "." + mn[i] + "_" + branch + ".0";
+        if (int rc = run_conv(c, name, in, n, f, f, nullptr, out->m[i])) return rc;
+    }
+    return 0;
+}
+
+static int tower(Ctx& c, const char* name, const float* in, int n, int r, float** out) {
+    Arena& ar = c.ar;
+    const float* cur = in;
+    float* o = nullptr;
+    for (int i = 0; i < 4; ++i) {
+        o = ar.f((size_t)n * r * r * 256);
+        if (int rc = run_conv(c, std::string("connect_model.") + name + "." + std::to_string(3 * i), cur, n, r, r, nullptr, o)) return rc;
+        cur = o;
+    }
+    *out = o;
+    return 0;
+}
+
+static int groupdw(Ctx& c, const Enc3& x, int nx, const Enc3& z, int nz, int n_out, int F, const float* w3, float* out) {
+    Arena& ar = c.ar;
+    GroupDWArgs a;
+    a.x11 = x.m[0]; a.x12 = x.m[1]; a.x21 = x.m[2];
+    a.z11 = z.m[0]; a.z12 = z.m[1]; a.z21 = z.m[2];
+    a.dw_weight = nullptr; a.out = out; a.nx = nx; a.nz = nz; a.n_out = n_out; a.C = 256; a.F = F;
+    if (!ar.plan) {
+        // algorithmic bytes: every search map read once per output sample group + output written once
+        const double R = F - 6, per_x = 256.0 * ((F - 2.0) * (F - 2) + 2.0 * (F - 4) * (F - 2));
+        Scope sc(FAM_XCORR, c.st, 0, 4.0 * (nx * per_x + n_out * 256.0 * R * R + nz * 256.0 * 55));
+        RUN(launch_groupdw_w(a, w3[0], w3[1], w3[2], c.st));
+    }
+    return 0;
+}
+
+// box_tower_reg.forward, offline branch (connect.py:224-247). Returns the encoded cls search maps for the memory branch.
+static int head_offline(Ctx& c, const float* xf, int n, int F, const float* zf, int nz, float* cls, float* bbox, Enc3* cls_x) {
+    Arena& ar = c.ar;
+    usot_engine* e = c.e;
+    const int R = F - 6;
+    Enc3 cls_z, reg_z, reg_x;
+    if (int rc = encode(c, "cls_encode", 'k', zf, nz, 7, &cls_z)) return rc;
+    if (int rc = encode(c, "cls_encode", 's', xf, n, F, cls_x)) return rc;
+    if (int rc = encode(c, "reg_encode", 'k', zf, nz, 7, &reg_z)) return rc;
+    if (int rc = encode(c, "reg_encode", 's', xf, n, F, &reg_x)) return rc;
+    float* cls_dw = ar.f((size_t)n * R * R * 256);
+    float* reg_dw = ar.f((size_t)n * R * R * 256);
+    if (int rc = groupdw(c, *cls_x, n, cls_z, nz, n, F, e->dw_cls, cls_dw)) return rc;
+    if (int rc = groupdw(c, reg_x, n, reg_z, nz, n, F, e->dw_reg, reg_dw)) return rc;
+    float *x_reg, *x_cls;
+    if (int rc = tower(c, "bbox_tower", reg_dw, n, R, &x_reg)) return rc;
+    if (!ar.plan) g_prof.launches[FAM_PRED]++;
+    RUN(launch_pred_conv(x_reg, n, R, 256, e->bbox_pred.w, e->bbox_pred.b, 4, 1, 1.f, e->adjust, e->bias4, bbox, c.st));
+    if (int rc = tower(c, "cls_tower", cls_dw, n, R, &x_cls)) return rc;
+    if (!ar.plan) g_prof.launches[FAM_PRED]++;
+    RUN(launch_pred_conv(x_cls, n, R, 256, e->cls_pred.w, e->cls_pred.b, 1, 0, 0.1f, nullptr, nullptr, cls, c.st));
+    return 0;
+}
+
+// box_tower_reg.forward, memory branch (connect.py:248-280). mem: (n*nq,7,7,256) nhwc.
+static int head_memory(Ctx& c, const Enc3& cls_x, int n, int F, const float* mem, int nq, float* cls_mem) {
+    Arena& ar = c.ar;
+    usot_engine* e = c.e;
+    const int R = F - 6;
+    Enc3 mz;
+    if (int rc = encode(c, "cls_encode", 'k', mem, n * nq, 7, &mz)) return rc;
+    const size_t per_map = (size_t)R * R * 256;
+    float* dw = ar.f((size_t)n * nq * per_map);
+    if (int rc = groupdw(c, cls_x, n, mz, n * nq, n * nq, F, e->dw_cls, dw)) return rc;
+    float* conf = ar.f((size_t)n * nq * per_map);
+    float* val = ar.f((size_t)n * nq * per_map);
+    if (int rc = run_conv(c, "connect_model.conf_fusion.conf_gen.0", dw, n * nq, R, R, nullptr, conf)) return rc;
+    if (int rc = run_conv(c, "connect_model.conf_fusion.value_gen.0", dw, n * nq, R, R, nullptr, val)) return rc;
+    float* fused = ar.f((size_t)n * per_map);
+    if (!ar.plan) g_prof.launches[FAM_FUSION]++;
+    RUN(launch_conf_fusion(conf, val, n, nq, per_map, fused, c.st));
+    float* t;
+    if (int rc = tower(c, "cls_memory_tower", fused, n, R, &t)) return rc;
+    if (!ar.plan) g_prof.launches[FAM_PRED]++;
+    RUN(launch_pred_conv(t, n, R, 256, e->cls_memory_pred.w, e->cls_memory_pred.b, 1, 0, 0.1f, nullptr, nullptr, cls_mem, c.st));
+    return 0;
+}
+
+// Two-pass driver: plan (count arena bytes) -> grow arena if needed -> execute.
+template <typename Fn>
+static int with_arena(usot_engine* e, Fn&& body) {
+    USOT_REQUIRE(e && e->finalized, "engine not finalized (load the state_dict and call usot_engine_finalize)");
+    std::lock_guard<std::mutex> lk(e->mu);
+    USOT_CUDA_OK(cudaSetDevice(e->device));
+    Arena& ar = e->arena;
+    ar.plan = true;
+    ar.off = 0;
+    if (int rc = body(ar)) { ar.plan = false; return rc; }
+    const size_t need = ar.off + 256;
+    ar.plan = false;
+    if (need > ar.cap) {
+        USOT_CUDA_OK(cudaDeviceSynchronize());
+        if (ar.base) USOT_CUDA_OK(cudaFree(ar.base));
+        ar.base = nullptr;
+        ar.cap = 0;
+        void* p = nullptr;
+        cudaError_t err = cudaMalloc(&p, need);
+        if (err != cudaSuccess) {
+            set_error("usot_b200: cannot allocate a " + std::to_string(need >> 20) + " MiB activation arena: " + cudaGetErrorString(err));
+            return 1;
+        }
+        ar.base = static_cast<char*>(p);
+        ar.cap = need;
+    }
+    ar.off = 0;
+    return body(ar);
+}
+
+}  // namespace usot
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* usot_last_error(void) { return g_err.c_str(); }
+int usot_abi_version(void) { return 1; }
+
+/* Profiling: kernel launches are always counted; with on=1 every launch is also bracketed by CUDA events on its stream. */
+int usot_profile_reset(int on) {
+    for (auto& e : g_prof.ev) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
+    g_prof.ev.clear();
+    for (int i = 0; i < FAM_COUNT; ++i) { g_prof.launches[i] = 0; g_prof.flops[i] = 0; g_prof.bytes[i] = 0; }
+    g_prof.on = on != 0;
+    return 0;
+}
+int usot_profile_family_count(void) { return FAM_COUNT; }
+const char* usot_profile_family_name(int fam) { return (fam >= 0 && fam < FAM_COUNT) ? kFamNames[fam] : ""; }
+/* Synchronises the device.  out[4] = {launches, milliseconds (0 unless profiling was on), algorithmic FLOPs, algorithmic bytes}. */
+int usot_profile_read(int fam, double* out) {
+    USOT_REQUIRE(fam >= 0 && fam < FAM_COUNT && out, "bad argument");
+    USOT_CUDA_OK(cudaDeviceSynchronize());
+    double ms = 0;
+    for (auto& e : g_prof.ev)
+        if (e.first == fam) { float t = 0; cudaEventElapsedTime(&t, e.second.first, e.second.second); ms += t; }
+    out[0] = (double)g_prof.launches[fam]; out[1] = ms; out[2] = g_prof.flops[fam]; out[3] = g_prof.bytes[fam];
+    return 0;
+}
+
+int usot_set_tunable(const char* name, int value) {
+    USOT_REQUIRE(name, "null name");
+    if (!strcmp(name, "groupdw_strips")) { USOT_REQUIRE(value == 2 || value == 3, "groupdw_strips must be 2 or 3"); g_groupdw_strips = value; return 0; }
+    USOT_REQUIRE(false, "unknown tunable");
+}
+
+int usot_prroi_pool_forward(const float* features, const float* rois, float* output, int n_features, int n_rois, int channels,
+                            int height, int width, int pooled_height, int pooled_width, float spatial_scale, void* stream) {
+    USOT_REQUIRE(n_rois == 0 || (features && rois && output), "null pointer");
+    USOT_REQUIRE(n_features >= 0 && n_rois >= 0 && channels > 0 && height > 0 && width > 0 && pooled_height > 0 && pooled_width > 0,
+                 "bad shape");
+    return launch_prroi_nchw(features, channels, height, width, rois, n_rois, pooled_height, pooled_width, spatial_scale, output,
+                             (cudaStream_t)stream);
+}
+
+int usot_xcorr_depthwise(const float* x, const float* kernel, float* out, int bx, int bk, int channels, int hx, int wx, int hk, int wk,
+                         void* stream) {
+    USOT_REQUIRE(x && kernel && out, "null pointer");
+    return launch_xcorr_nchw(x, kernel, out, bx, bk, channels, hx, wx, hk, wk, (cudaStream_t)stream);
+}
+
+int usot_groupdw_xcorr(const float* x11, const float* x12, const float* x21, const float* z11, const float* z12, const float* z21,
+                       const float* weight, float* out, int nx, int nz, int n_out, int channels, int feat_size, void* stream) {
+    USOT_REQUIRE(x11 && x12 && x21 && z11 && z12 && z21 && weight && out, "null pointer");
+    GroupDWArgs a{x11, x12, x21, z11, z12, z21, weight, out, nx, nz, n_out, channels, feat_size};
+    return launch_groupdw(a, (cudaStream_t)stream);
+}
+
+int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh, int kw, int stride,
+                     int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift, const float* residual,
+                     int relu, float* out, int precision, void* stream) {
+    USOT_REQUIRE(in && weight_kn && scale && shift && out, "null pointer");
+    USOT_REQUIRE(precision == USOT_PREC_FP32_SIMT, "usot_conv2d_nhwc: only USOT_PREC_FP32_SIMT is wired for the stand-alone op");
+    ConvGeom g{n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w, conv_out(h, kh, stride, pad_h, dil_h),
+               conv_out(w, kw, stride, pad_w, dil_w)};
+    USOT_REQUIRE(g.ho > 0 && g.wo > 0, "conv output is empty");
+    Epilogue ep{scale, shift, residual, relu};
+    return launch_conv_simt(in, g, weight_kn, ep, out, (cudaStream_t)stream);
+}
+
+int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream) {
+    return launch_nchw_to_nhwc(in, n, c, h, w, out, (cudaStream_t)stream);
+}
+int usot_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, void* stream) {
+    return launch_nhwc_to_nchw(in, n, h, w, c, out, (cudaStream_t)stream);
+}
+
+int usot_engine_create(usot_engine** out, int device, int precision) {
+    USOT_REQUIRE(out, "null pointer");
+    USOT_REQUIRE(precision >= USOT_PREC_FP32_SIMT && precision <= USOT_PREC_FP16_TC, "unknown precision mode");
+    int count = 0;
+    USOT_CUDA_OK(cudaGetDeviceCount(&count));
+    USOT_REQUIRE(device >= 0 && device < count, "no such CUDA device (usot_b200 has no CPU fallback)");
+    cudaDeviceProp prop;
+    USOT_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    USOT_REQUIRE(prop.major == 10, "usot_b200 is built for sm_100a (Blackwell B200) only");
+    usot_engine* e = new usot_engine();
+    e->device = device;
+    e->precision = precision;
+    *out = e;
+    return 0;
+}
+
+int usot_engine_destroy(usot_engine* e) {
+    delete e;
+    return 0;
+}
+
+int usot_engine_load_tensor(usot_engine* e, const char* name, const float* host_data, int64_t numel) {
+    USOT_REQUIRE(e && name && (host_data || numel == 0) && numel >= 0, "bad argument");
+    e->host[name].assign(host_data, host_data + numel);
+    e->finalized = false;
+    return 0;
+}
+
+int usot_engine_finalize(usot_engine* e) {
+    USOT_REQUIRE(e, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
+    return finalize_impl(e);
+}
+
+int64_t usot_engine_device_bytes(const usot_engine* e) { return e ? e->weight_bytes + (int64_t)e->arena.cap : 0; }
+
+int usot_feature_size(int s) {
+    int h1 = (s - 7) / 2 + 1;          // conv1 7x7/2 p0
+    int h2 = (h1 + 2 - 3) / 2 + 1;     // maxpool 3x3/2 p1
+    return (h2 - 3) / 2 + 1;           // layer2.0 3x3/2 p0 ; layer3 keeps the size
+}
+
+int usot_engine_backbone_neck(usot_engine* e, const float* x, int n, int size, float* xf, void* stream) {
+    USOT_REQUIRE(x && xf && n > 0 && size >= 63, "bad argument");
+    return with_arena(e, [&](Arena& ar) {
+        Ctx c{e, ar, (cudaStream_t)stream};
+        float* o = xf;
+        int F;
+        return backbone_neck(c, x, n, size, &o, &F);
+    });
+}
+
+int usot_engine_template(usot_engine* e, const float* z, int n, int size, const float* template_bbox, float* zf, float* x_ori,
+                         void* stream) {
+    USOT_REQUIRE(z && zf && n > 0 && size >= 63, "bad argument");
+    return with_arena(e, [&](Arena& ar) {
+        Ctx c{e, ar, (cudaStream_t)stream};
+        float* o = x_ori;
+        int F;
+        if (int rc = backbone_neck(c, z, n, size, &o, &F)) return rc;
+        if (!ar.plan) g_prof.launches[FAM_PRROI]++;
+        if (template_bbox) RUN(launch_prroi_nhwc(o, n, F, F, 256, template_bbox, n, zf, c.st));
+        else {
+            USOT_REQUIRE(F - 8 == 7, "pr_pool=False template needs a 127x127 exemplar (15x15 feature)");
+            RUN(launch_center_crop_nhwc(o, n, F, F, 256, 4, zf, c.st));
+        }
+        return 0;
+    });
+}
+
+int usot_engine_track(usot_engine* e, const float* x, int n, int size, const float* zf, int nz, const float* template_mem, int nq,
+                      float* cls, float* bbox, float* cls_mem, float* xf, void* stream) {
+    USOT_REQUIRE(x && zf && cls && bbox && n > 0, "bad argument");
+    USOT_REQUIRE(nz == 1 || nz == n, "template batch must be 1 or equal to the search batch");
+    USOT_REQUIRE(nq >= 0 && (nq == 0 || (template_mem && cls_mem)), "memory branch needs template_mem and cls_mem");
+    USOT_REQUIRE(usot_feature_size(size) >= 9, "search crop too small");
+    return with_arena(e, [&](Arena& ar) {
+        Ctx c{e, ar, (cudaStream_t)stream};
+        float* f = xf;
+        int F;
+        if (int rc = backbone_neck(c, x, n, size, &f, &F)) return rc;
+        Enc3 cls_x;
+        if (int rc = head_offline(c, f, n, F, zf, nz, cls, bbox, &cls_x)) return rc;
+        if (nq > 0)
+            if (int rc = head_memory(c, cls_x, n, F, template_mem, nq, cls_mem)) return rc;
+        return 0;
+    });
+}
+
+int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n, int size, const float* xf, int feat,
+                                       const float* search_bbox, float* out, void* stream) {
+    USOT_REQUIRE((ori_x != nullptr) != (xf != nullptr), "exactly one of ori_x / xf must be given");
+    USOT_REQUIRE(search_bbox && out && n > 0, "bad argument");
+    return with_arena(e, [&](Arena& ar) {
+        Ctx c{e, ar, (cudaStream_t)stream};
+        const float* f = xf;
+        int F = feat;
+        if (ori_x) {
+            float* o = nullptr;
+            if (int rc = backbone_neck(c, ori_x, n, size, &o, &F)) return rc;
+            f = o;
+        }
+        if (!ar.plan) g_prof.launches[FAM_PRROI]++;
+        RUN(launch_prroi_nhwc(f, n, F, F, 256, search_bbox, n, out, c.st));
+        return 0;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+"""Operator-level Python wrappers over the C ABI (same names / argument meaning as the reference ops).
+
+    prroi_pool2d      lib/models/prroi_pool/functional.py:41-84  (forward only)
+    xcorr_depthwise   lib/models/connect.py:147-157
+    groupdw_xcorr     lib/models/connect.py:86-102 (fused, NHWC)
+    conv2d_nhwc       nn.Conv2d + folded BatchNorm2d (+residual)(+ReLU)
+
+torch is used for device memory and the current stream only.
+"""
+import torch
+
+from . import _lib
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            # same contract as the reference op (functional.py:62-63), extended to every op of this package
+            raise NotImplementedError("usot_b200 only supports GPU (cuda) tensors; there is no CPU fallback")
+
+
+def _need_float(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.float32:
+            raise AssertionError("usot_b200 ops only take float32 input, got {}".format(t.dtype))
+
+
+def as_nhwc(t):
+    """Logical-NCHW tensor -> tensor whose memory is contiguous NHWC (no copy if it already is)."""
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def nhwc_view(t_nhwc):
+    """Contiguous NHWC tensor -> logical NCHW view (channels-last strides)."""
+    return t_nhwc.permute(0, 3, 1, 2)
+
+
+def prroi_pool2d(features, rois, pooled_height, pooled_width, spatial_scale):
+    _need_float(features, rois)
+    _need_cuda(features, rois)
+    pooled_height, pooled_width, spatial_scale = int(pooled_height), int(pooled_width), float(spatial_scale)
+    features, rois = features.contiguous(), rois.contiguous()
+    n, c, h, w = features.shape
+    out = torch.empty((rois.shape[0], c, pooled_height, pooled_width), dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        _lib.check(_lib.load().usot_prroi_pool_forward(_lib.ptr(features), _lib.ptr(rois), _lib.ptr(out), n, rois.shape[0], c, h, w,
+                                                       pooled_height, pooled_width, spatial_scale, _stream(features)))
+    return out
+
+
+def xcorr_depthwise(x, kernel):
+    _need_float(x, kernel)
+    _need_cuda(x, kernel)
+    x, kernel = x.contiguous(), kernel.contiguous()
+    bx, c, hx, wx = x.shape
+    bk, ck, hk, wk = kernel.shape
+    assert c == ck, "channel mismatch"
+    out = torch.empty((bx, c, hx - hk + 1, wx - wk + 1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().usot_xcorr_depthwise(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(out), bx, bk, c, hx, wx, hk, wk, _stream(x)))
+    return out
+
+
+def groupdw_xcorr(x, z, weight, n_out=None):
+    """x = [x11, x12, x21], z = [z11, z12, z21] contiguous NHWC tensors; weight (3,) raw.  Returns NHWC (n_out,R,R,C)."""
+    _need_float(*x, *z, weight)
+    _need_cuda(*x, *z, weight)
+    x = [t.contiguous() for t in x]
+    z = [t.contiguous() for t in z]
+    nx, h11, w11, c = x[0].shape
+    f = h11 + 2
+    assert tuple(x[1].shape) == (nx, f - 4, f - 2, c) and tuple(x[2].shape) == (nx, f - 2, f - 4, c), "bad search map shapes"
+    nz = z[0].shape[0]
+    assert tuple(z[0].shape[1:]) == (5, 5, c) and tuple(z[1].shape[1:]) == (3, 5, c) and tuple(z[2].shape[1:]) == (5, 3, c)
+    n_out = n_out or max(nx, nz)
+    out = torch.empty((n_out, f - 6, f - 6, c), dtype=torch.float32, device=x[0].device)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().usot_groupdw_xcorr(*[_lib.ptr(t) for t in x], *[_lib.ptr(t) for t in z], _lib.ptr(weight.contiguous()),
+                                                  _lib.ptr(out), nx, nz, n_out, c, f, _stream(out)))
+    return out
+
+
+def conv2d_nhwc(x, weight_oihw, scale, shift, stride=1, padding=(0, 0), dilation=(1, 1), residual=None, relu=False, precision="fp32"):
+    """x NHWC (n,h,w,cin); weight in the reference's OIHW layout (repacked here); returns NHWC."""
+    _need_float(x, weight_oihw, scale, shift, residual)
+    _need_cuda(x, weight_oihw, scale, shift, residual)
+    n, h, w, cin = x.shape
+    cout, cin2, kh, kw = weight_oihw.shape
+    assert cin == cin2
+    ph, pw = (padding, padding) if isinstance(padding, int) else padding
+    dh, dw = (dilation, dilation) if isinstance(dilation, int) else dilation
+    ho = (h + 2 * ph - dh * (kh - 1) - 1) // stride + 1
+    wo = (w + 2 * pw - dw * (kw - 1) - 1) // stride + 1
+    w_kn = weight_oihw.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
+    out = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().usot_conv2d_nhwc(_lib.ptr(x.contiguous()), n, h, w, cin, _lib.ptr(w_kn), cout, kh, kw, stride, ph, pw, dh, dw,
+                                                _lib.ptr(scale.contiguous()), _lib.ptr(shift.contiguous()),
+                                                _lib.ptr(None if residual is None else residual.contiguous()), int(bool(relu)),
+                                                _lib.ptr(out), _lib.PRECISIONS[precision], _stream(x)))
+    return out
