@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("USOT_B200_PRECISION", "fp32"), choices=["fp32", "fp16x3", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("USOT_B200_PRECISION", "fp16x3"), choices=["fp32", "fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

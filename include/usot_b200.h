@@ -49,7 +49,8 @@ enum {
 
 USOT_API const char* usot_last_error(void);
 USOT_API int usot_abi_version(void);
-/* Process-wide performance knobs (never change results): "groupdw_strips" = 2 | 3. */
+/* Process-wide performance knobs (never change results): "groupdw_strips" = 2 | 3; "tc_bn_max" = 64 | 128 | 256.
+ * One accuracy knob: "tc_split_bn_max" = 64 | 128 (default; separate cross-term accumulator) | 256 (single accumulator). */
 USOT_API int usot_set_tunable(const char* name, int value);
 
 /* Measurement hooks.  Launches of this library's kernels are always counted per kernel family; with on=1 every launch is

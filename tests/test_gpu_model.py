@@ -10,7 +10,15 @@ from helpers import golden, load_weights, rel_err, subsample
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
-PRECISIONS = ["fp32"]
+PRECISIONS = ["fp32", "fp16x3", "fp16"]
+# fp32 / fp16x3 are the parity-graded modes (north-star bar: 1e-3, exact argmax).  "fp16" is the single-pass fast mode
+# (BASELINE config 3): validated against the same oracle with its own, looser, stated tolerance and no argmax claim.
+MODE_TOL = {"fp32": TOL, "fp16x3": TOL, "fp16": {"damp025": 3e-2, "raw": 5e-1}}
+
+
+def tol_for(precision, wname):
+    t = MODE_TOL[precision]
+    return t[wname] if isinstance(t, dict) else t
 
 
 def _net(wname, precision, settings=None):
@@ -30,10 +38,11 @@ def test_config1_pair_forward_vs_golden(wname, precision):
     cls, bbox, cmem, xf = net.track(x.cuda())
     assert cmem is None and xf is None
     assert tuple(net.zf.shape) == (1, 256, 7, 7) and tuple(cls.shape) == (1, 1, 25, 25) and tuple(bbox.shape) == (1, 4, 25, 25)
-    assert rel_err(net.zf, g["c1_zf"]) <= TOL
-    assert rel_err(cls, g["c1_cls"]) <= TOL
-    assert rel_err(bbox, g["c1_bbox"]) <= TOL
-    assert int(cls.flatten().argmax()) == int(np.argmax(g["c1_cls"]))
+    errs = dict(zf=rel_err(net.zf, g["c1_zf"]), cls=rel_err(cls, g["c1_cls"]), bbox=rel_err(bbox, g["c1_bbox"]))
+    print(wname, "c1", precision, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= tol_for(precision, wname), errs
+    if precision != "fp16":
+        assert int(cls.flatten().argmax()) == int(np.argmax(g["c1_cls"]))
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -58,7 +67,9 @@ def test_track_with_memory_vs_golden(wname, tag, S, B, seed, precision):
                 bbox=rel_err(bbox, g[f"{tag}_bbox"]), cls_mem=rel_err(cmem, g[f"{tag}_cls_mem"]),
                 xf=rel_err(subsample(xf), g[f"{tag}_xf_sub"]), feat=rel_err(feat, g[f"{tag}_feat"]))
     print(wname, tag, precision, {k: f"{v:.2e}" for k, v in errs.items()})
-    assert max(errs.values()) <= TOL, errs
+    assert max(errs.values()) <= tol_for(precision, wname), errs
+    if precision == "fp16":
+        return
     ratio = 0.3  # experiments/test/USOT.yaml:7
     mix_ref = ratio * torch.sigmoid(torch.from_numpy(g[f"{tag}_cls"])) + (1 - ratio) * torch.sigmoid(torch.from_numpy(g[f"{tag}_cls_mem"]))
     mix = ratio * torch.sigmoid(cls.cpu()) + (1 - ratio) * torch.sigmoid(cmem.cpu())
@@ -79,7 +90,9 @@ def test_backbone_vs_oracle_fresh_inputs(precision):
         ref = O.backbone_neck(sd, x)
     ours = net.backbone_neck(x.cuda())
     assert tuple(ours.shape) == (3, 256, 31, 31)
-    assert rel_err(ours, ref) <= TOL
+    err = rel_err(ours, ref)
+    print("backbone fresh", precision, f"{err:.2e}")
+    assert err <= tol_for(precision, wname)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -95,8 +108,8 @@ def test_batch_256_independence(precision):
     assert tuple(cls.shape) == (256, 1, 25, 25)
     cls4, bbox4, _, _ = net.track(x1.cuda())
     for i in (0, 1, 2, 3, 100, 255):
-        assert rel_err(cls[i], cls4[i % 4]) <= 1e-6
-        assert rel_err(bbox[i], bbox4[i % 4]) <= 1e-6
+        assert torch.equal(cls[i], cls4[i % 4]), "sample result depends on its position in the batch"
+        assert torch.equal(bbox[i], bbox4[i % 4])
     assert torch.isfinite(cls).all() and torch.isfinite(bbox).all()
 
 

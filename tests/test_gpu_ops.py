@@ -126,8 +126,11 @@ CONV_CASES = [
 ]
 
 
+CONV_TOL = {"fp32": 5e-6, "fp16x3": 3e-5, "fp16": 3e-3}  # fp16x3: tensor-core accumulation truncates, error grows ~3e-9*K
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("precision", ["fp32"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
 def test_conv2d_nhwc(ops, case, precision):
     cin, cout, k, stride, pad, dil, h, w, use_res, relu = case
     g = torch.Generator().manual_seed(cin + cout + k)
@@ -145,4 +148,6 @@ def test_conv2d_nhwc(ops, case, precision):
                            None if res is None else res.permute(0, 2, 3, 1).contiguous().cuda(), relu, precision)
     ours = ours.permute(0, 3, 1, 2).cpu()
     assert ours.shape == ref.shape
-    assert rel_err(ours, ref) <= 5e-6
+    err = rel_err(ours, ref)
+    print(precision, case[:6], f"{err:.2e}")
+    assert err <= CONV_TOL[precision]

@@ -1,0 +1,554 @@
+// Dense convolutions on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
+//
+// Every 1x1 / 3x3 conv of the USOT forward path (lib/models/modules.py:37-58,121-126; connect.py:20-53,112-121,178-209,
+// 287-290) is an implicit GEMM  D[m][n] = sum_k A[m][k] * B[n][k]  with
+//     m = output pixel inside a (BH x BW) spatial patch of one image (<= 128 rows),
+//     n = output channel,  k = (filter tap, input channel).
+// A is never materialised: for each (tap, 64-channel chunk) ONE 4-D TMA box load [64 ch, BW, BH, 1 image] of the NHWC fp16
+// activation tensor lands in shared memory already in the 128-byte-swizzled K-major layout that tcgen05.mma consumes;
+// padding comes from TMA out-of-bounds zero fill (coordinates may be negative), dilation is a coordinate offset, and
+// stride 2 uses four "parity-decimated" views of the same tensor (strides doubled) so that the box stays dense.
+// B (weights, [cout][taps*cin] fp16, K-major) is a 2-D TMA box.  Accumulators live in TMEM (fp32), double buffered so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Persistent CTAs, warp-specialised:
+//     warp 0  TMA producer (one elected lane)      warp 1  MMA issuer (one elected lane)
+//     warp 2  TMEM allocator                        warps 4-7  epilogue (tcgen05.ld -> scale/shift/residual/ReLU -> global)
+//
+// Precision modes
+//   SPLIT (fp16x3, default): activations and weights are stored as value = hi + lo (two fp16 planes); three MMAs
+//       hi*hi + hi*lo + lo*hi accumulate in fp32 in the same TMEM tile.  Per-product relative error ~2^-21, i.e. fp32-class,
+//       which the 1e-3 / exact-argmax parity bar needs (single-pass TF32/fp16 does not meet it on random residual nets,
+//       SURVEY.md App. C).  Weights are pre-scaled by a per-output-channel power of two (folded back in the epilogue scale)
+//       so that both fp16 planes stay in the normal range.
+//   single fp16: only the hi planes are read: 3x fewer MMAs, ~1e-3-class error per layer (fast mode).
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace usot {
+
+// =============================================================================================
+// PTX wrappers
+// =============================================================================================
+static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+static __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+static __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (CUDA error on the host), never as a hung GPU.
+static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("usot_b200 conv_tc: mbarrier wait timed out (block %d, thread %d, bar 0x%x, parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+static __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+static __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+static __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+static __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+static __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+static __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused.
+static __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);   // bits [0,14)  start address >> 4
+    d |= (uint64_t)(1024 >> 4) << 32;         // bits [32,46) stride byte offset >> 4
+    d |= (uint64_t)1 << 46;                   // bits [46,48) descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                   // bits [61,64) SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+static __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+static __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+static __device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+static __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+static __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// =============================================================================================
+// Kernel
+// =============================================================================================
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB per plane per stage
+
+template <int BN, bool SPLIT>
+struct TcCfg {
+    static constexpr int PLANES = SPLIT ? 2 : 1;
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = PLANES * (TC_A_BYTES + B_BYTES);
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;  // barriers, scale/shift staging, alignment slack
+    static constexpr int STAGES_RAW = (SMEM_BUDGET - 2 * BN * 4) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    // Split mode keeps TWO accumulators per tile when TMEM allows it (BN <= 128): `main` receives only the hi*hi products and
+    // `cross` the 2^-11-times smaller hi*lo + lo*hi products.  The tensor core truncates on every accumulate, so the error of
+    // an accumulator grows with the number of MMAs added into it; routing the cross terms elsewhere cuts the adds into `main`
+    // 3x and makes the cross terms' own truncation negligible.  The epilogue adds the two in fp32 (round-to-nearest).
+    static constexpr bool XACC = SPLIT && BN <= 128;
+    static constexpr int ACC_COLS = XACC ? 2 * BN : BN;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double buffered; power of two for BN in {64,128,256}
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 4 + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    using Cfg = TcCfg<BN, SPLIT>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte aligned operand ring (required by the 128B swizzle atoms)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    float* s_scale = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES);
+    float* s_shift = s_scale + BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES,
+                   bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nK = p.taps * p.cin_chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b[0]);
+        tma_prefetch_desc(&p.a[0][0]);
+        if (SPLIT) { tma_prefetch_desc(&p.b[1]); tma_prefetch_desc(&p.a[1][0]); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            const uint32_t a_box_bytes = (uint32_t)p.bw * p.bh * TC_BK * 2;
+            const uint32_t tx = Cfg::PLANES * (a_box_bytes + Cfg::B_BYTES);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nb = tile % p.n_tiles_n;
+                int mt = tile / p.n_tiles_n;
+                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+                const int th = mt % p.tiles_h;
+                const int img = mt / p.tiles_h;
+                const int h0 = th * p.bh, w0 = tw * p.bw;
+                for (int ks = 0; ks < nK; ++ks) {
+                    const int tap = ks / p.cin_chunks, cc = ks - tap * p.cin_chunks;
+                    const int kh = tap / p.kw, kwi = tap - kh * p.kw;
+                    int offh = kh * p.dh - p.ph, offw = kwi * p.dw - p.pw, par = 0;
+                    if (p.stride == 2) {
+                        const int py = offh & 1, px = offw & 1;
+                        par = py * 2 + px;
+                        offh = (offh - py) >> 1;
+                        offw = (offw - px) >> 1;
+                    }
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    mbar_expect_tx(full, tx);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::PLANES * TC_A_BYTES;
+                    tma_load_4d(sa, &p.a[0][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
+                    tma_load_2d(sb, &p.b[0], full, ks * TC_BK, nb * BN);
+                    if (SPLIT) {
+                        tma_load_4d(sa + TC_A_BYTES, &p.a[1][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
+                        tma_load_2d(sb + Cfg::B_BYTES, &p.b[1], full, ks * TC_BK, nb * BN);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(TC_BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * Cfg::ACC_COLS;
+                const uint32_t tmem_x = Cfg::XACC ? tmem_d + BN : tmem_d;
+                for (int ks = 0; ks < nK; ++ks) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::PLANES * TC_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t a_hi = make_smem_desc(sa + k * 32), b_hi = make_smem_desc(sb + k * 32);
+                        umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) ? 1u : 0u);
+                        if (SPLIT) {
+                            const uint64_t a_lo = make_smem_desc(sa + TC_A_BYTES + k * 32), b_lo = make_smem_desc(sb + Cfg::B_BYTES + k * 32);
+                            umma_f16(tmem_x, a_hi, b_lo, idesc, Cfg::XACC ? ((ks | k) ? 1u : 0u) : 1u);
+                            umma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * as);  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int ew = warp - 4;              // TMEM lane quarter == warp % 4
+        const int row = ew * 32 + lane;       // tile row == TMEM lane
+        const int et = threadIdx.x - 128;     // 0..127
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int nb = tile % p.n_tiles_n;
+            int mt = tile / p.n_tiles_n;
+            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th = mt % p.tiles_h;
+            const int img = mt / p.tiles_h;
+            const int hl = row / p.bw, wl = row - hl * p.bw;
+            const int oh = th * p.bh + hl, ow = tw * p.bw + wl;
+            const bool valid = hl < p.bh && oh < p.ho && ow < p.wo;
+            const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
+            const int n0 = nb * BN;
+            // stage this tile's scale/shift (previous tile's readers are past the barrier at the end of the loop body)
+            for (int i = et; i < BN; i += 128) { s_scale[i] = __ldg(p.scale + n0 + i); s_shift[i] = __ldg(p.shift + n0 + i); }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int as = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                if (Cfg::XACC) {
+                    uint32_t x[32];
+                    tmem_ld32(taddr + BN + c0, x);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(x[j]));
+                } else {
+                    tmem_ld_wait();
+                }
+                if (valid) {
+                    float y[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
+                    const size_t off = pix * p.cout + n0 + c0;
+                    if (p.res_hi) {
+                        const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + off);
+                        const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 a = __ldg(rh + q), b = __ldg(rl + q);
+                            const __half2* ah = reinterpret_cast<const __half2*>(&a);
+                            const __half2* bl = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float2 fa = __half22float2(ah[e]), fb = __half22float2(bl[e]);
+                                y[q * 8 + 2 * e] += fa.x + fb.x;
+                                y[q * 8 + 2 * e + 1] += fa.y + fb.y;
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+                    }
+                    if (p.out_hi) {
+                        uint4* oh4 = reinterpret_cast<uint4*>(p.out_hi + off);
+                        uint4* ol4 = reinterpret_cast<uint4*>(p.out_lo + off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 a, b;
+                            __half2* ah = reinterpret_cast<__half2*>(&a);
+                            __half2* bl = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float f0 = y[q * 8 + 2 * e], f1 = y[q * 8 + 2 * e + 1];
+                                const __half2 h = __floats2half2_rn(f0, f1);
+                                const float2 hf = __half22float2(h);
+                                ah[e] = h;
+                                bl[e] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+                            }
+                            oh4[q] = a;
+                            ol4[q] = b;
+                        }
+                    }
+                    if (p.out_f32) {
+                        float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) o[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // scale/shift staging may be overwritten next iteration
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// =============================================================================================
+// Host side: tensor maps, tiling, launch
+// =============================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    USOT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("usot_b200: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return 1;
+    }
+    return 0;
+}
+
+// choose (tiles_w, bw, bh) maximising the fraction of the 128 MMA rows that are real output pixels
+static void choose_tiling(int ho, int wo, int* tiles_w, int* bw, int* bh) {
+    double best = -1;
+    for (int tw = 1; tw <= 8; ++tw) {
+        int w = (wo + tw - 1) / tw;
+        if (w > 128) continue;
+        int h = std::min(128 / w, ho);
+        int th = (ho + h - 1) / h;
+        double eff = (double)ho * wo / ((double)tw * th * 128.0);
+        if (eff > best + 1e-9) { best = eff; *tiles_w = tw; *bw = w; *bh = h; }
+    }
+}
+
+template <int BN, bool SPLIT>
+static int launch_cfg(const TcParams& p, int grid, cudaStream_t st) {
+    using Cfg = TcCfg<BN, SPLIT>;
+    static_assert(Cfg::STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
+    static bool attr = false;
+    if (!attr) {
+        USOT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr = true;
+    }
+    conv_tc_kernel<BN, SPLIT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
+int g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cross-term accumulator (accuracy); 256 trades it for reuse
+
+int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st) {
+    USOT_REQUIRE(g.cin % TC_BK == 0, "conv_tc needs Cin % 64 == 0");
+    USOT_REQUIRE(g.cout % 64 == 0, "conv_tc needs Cout % 64 == 0");
+    USOT_REQUIRE(g.stride == 1 || g.stride == 2, "conv_tc supports stride 1 and 2");
+    USOT_REQUIRE(in.hi && (!split || in.lo), "conv_tc: missing input plane");
+    USOT_REQUIRE(w.hi && (!split || w.lo), "conv_tc: missing weight plane");
+    USOT_REQUIRE(ep.out_hi || ep.out_f32, "conv_tc: no output requested");
+    if ((size_t)g.n * g.ho * g.wo == 0) return 0;
+
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int bn = 64;
+    const int bn_cap = split ? std::min(g_tc_bn_max, g_tc_split_bn_max) : g_tc_bn_max;
+    if (g.cout % 256 == 0 && bn_cap >= 256) bn = 256;
+    else if (g.cout % 128 == 0 && bn_cap >= 128) bn = 128;
+    choose_tiling(g.ho, g.wo, &p.tiles_w, &p.bw, &p.bh);
+    p.tiles_h = (g.ho + p.bh - 1) / p.bh;
+    p.n_img = g.n; p.ho = g.ho; p.wo = g.wo; p.cout = g.cout;
+    p.n_tiles_n = g.cout / bn;
+    p.num_tiles = g.n * p.tiles_h * p.tiles_w * p.n_tiles_n;
+    p.taps = g.kh * g.kw; p.kw = g.kw; p.cin_chunks = g.cin / TC_BK;
+    p.stride = g.stride; p.ph = g.ph; p.pw = g.pw; p.dh = g.dh; p.dw = g.dw;
+    p.scale = w.scale; p.shift = ep.shift;
+    p.res_hi = ep.res_hi; p.res_lo = ep.res_lo;
+    p.out_hi = ep.out_hi; p.out_lo = ep.out_lo; p.out_f32 = ep.out_f32;
+    p.relu = ep.relu;
+    USOT_REQUIRE(!p.res_hi || p.res_lo, "conv_tc: residual needs both planes");
+    USOT_REQUIRE(!p.out_hi || p.out_lo, "conv_tc: split output needs both planes");
+
+    // ---- activation maps: dims {C, W', H', N}, one per (plane, parity) ----
+    const int planes = split ? 2 : 1;
+    const int npar = g.stride == 2 ? 4 : 1;
+    for (int pl = 0; pl < planes; ++pl) {
+        const __half* base = pl == 0 ? in.hi : in.lo;
+        for (int par = 0; par < npar; ++par) {
+            const int py = par >> 1, px = par & 1;
+            cuuint64_t dims[4], strides[3];
+            cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+            const __half* b = base;
+            if (g.stride == 1) {
+                dims[0] = g.cin; dims[1] = g.w; dims[2] = g.h; dims[3] = g.n;
+                strides[0] = (cuuint64_t)g.cin * 2; strides[1] = (cuuint64_t)g.w * g.cin * 2; strides[2] = (cuuint64_t)g.h * g.w * g.cin * 2;
+            } else {
+                if (py >= g.h || px >= g.w) continue;
+                b = base + ((size_t)py * g.w + px) * g.cin;
+                dims[0] = g.cin; dims[1] = (g.w - px + 1) / 2; dims[2] = (g.h - py + 1) / 2; dims[3] = g.n;
+                strides[0] = (cuuint64_t)g.cin * 4; strides[1] = (cuuint64_t)g.w * g.cin * 4; strides[2] = (cuuint64_t)g.h * g.w * g.cin * 2;
+            }
+            if (int rc = encode_map(&p.a[pl][par], b, 4, dims, strides, box)) return rc;
+        }
+        // ---- weight map: dims {K, Cout} ----
+        cuuint64_t wd[2] = {(cuuint64_t)w.K, (cuuint64_t)g.cout}, ws[1] = {(cuuint64_t)w.K * 2};
+        cuuint32_t wb[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+        if (int rc = encode_map(&p.b[pl], pl == 0 ? w.hi : w.lo, 2, wd, ws, wb)) return rc;
+    }
+
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        USOT_CUDA_OK(cudaGetDevice(&dev));
+        USOT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = std::min(p.num_tiles, num_sms);
+    if (split) {
+        if (bn == 256) return launch_cfg<256, true>(p, grid, st);
+        if (bn == 128) return launch_cfg<128, true>(p, grid, st);
+        return launch_cfg<64, true>(p, grid, st);
+    }
+    if (bn == 256) return launch_cfg<256, false>(p, grid, st);
+    if (bn == 128) return launch_cfg<128, false>(p, grid, st);
+    return launch_cfg<64, false>(p, grid, st);
+}
+
+// =============================================================================================
+// fp32 -> split-fp16 conversion (activations) and host-side weight packing
+// =============================================================================================
+__global__ void f32_to_split_kernel(const float4* __restrict__ in, size_t n4, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(in + i);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    uint2 a, b;
+    a.x = *reinterpret_cast<const uint32_t*>(&h0); a.y = *reinterpret_cast<const uint32_t*>(&h1);
+    b.x = *reinterpret_cast<const uint32_t*>(&l0); b.y = *reinterpret_cast<const uint32_t*>(&l1);
+    hi[i] = a;
+    if (lo) lo[i] = b;
+}
+
+int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st) {
+    USOT_REQUIRE(n % 4 == 0, "f32_to_split: element count must be a multiple of 4");
+    if (n == 0) return 0;
+    const size_t n4 = n / 4;
+    f32_to_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in), n4, reinterpret_cast<uint2*>(hi),
+                                                                       reinterpret_cast<uint2*>(lo));
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// w_kn: [K][cout] fp32 (k = tap*cin + c).  Produces [cout][K] fp16 hi/lo planes of w * 2^e[co] and scale_out = scale_in * 2^-e.
+void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,
+                          std::vector<float>& scale_out) {
+    hi.resize((size_t)cout * K);
+    lo.resize((size_t)cout * K);
+    scale_out.resize(cout);
+    for (int co = 0; co < cout; ++co) {
+        float mx = 0.f;
+        for (int k = 0; k < K; ++k) mx = std::max(mx, std::fabs(w_kn[(size_t)k * cout + co]));
+        int e = 0;
+        if (mx > 0.f && std::isfinite(mx)) {
+            int ex;
+            std::frexp(mx, &ex);  // mx = f * 2^ex, f in [0.5, 1)
+            e = 8 - ex;           // scaled max lands in [128, 256): hi and lo planes both far from fp16 under/overflow
+        }
+        const float s = std::ldexp(1.0f, e);
+        for (int k = 0; k < K; ++k) {
+            const float v = w_kn[(size_t)k * cout + co] * s;
+            const __half h = __float2half_rn(v);
+            hi[(size_t)co * K + k] = h;
+            lo[(size_t)co * K + k] = __float2half_rn(v - __half2float(h));
+        }
+        scale_out[co] = scale_in[co] * std::ldexp(1.0f, -e);
+    }
+}
+
+}  // namespace usot

@@ -1,0 +1,55 @@
+// Interface of the tcgen05 implicit-GEMM convolution (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <vector>
+
+namespace usot {
+
+struct TcParams {
+    CUtensorMap a[2][4];  // activation maps [plane hi/lo][stride-2 parity]
+    CUtensorMap b[2];     // weight maps [plane]
+    int n_img, ho, wo, cout;
+    int bw, bh, tiles_w, tiles_h;  // spatial patch of one M tile (bw*bh <= 128 rows)
+    int n_tiles_n, num_tiles;
+    int taps, kw, cin_chunks;
+    int stride, ph, pw, dh, dw;
+    const float* scale;
+    const float* shift;
+    const __half* res_hi;
+    const __half* res_lo;
+    __half* out_hi;
+    __half* out_lo;
+    float* out_f32;
+    int relu;
+};
+
+struct TcTensor {  // NHWC fp16 planes of one activation tensor (lo may be null in single-fp16 mode)
+    const __half* hi;
+    const __half* lo;
+};
+
+struct TcWeights {  // [cout][K] K-major fp16 planes of w * 2^e[co]; scale already multiplied by 2^-e[co]
+    const __half* hi;
+    const __half* lo;
+    const float* scale;
+    int K;
+};
+
+struct TcEpilogue {
+    const float* shift;
+    const __half* res_hi;
+    const __half* res_lo;
+    __half* out_hi;
+    __half* out_lo;
+    float* out_f32;
+    int relu;
+};
+
+extern int g_tc_bn_max, g_tc_split_bn_max;
+int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st);
+int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
+void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,
+                          std::vector<float>& scale_out);
+
+}  // namespace usot

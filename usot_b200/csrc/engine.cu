@@ -8,6 +8,7 @@
 //   track           USOT_.track -> box_tower_reg.forward    lib/models/models.py:179-198, connect.py:221-281
 //   extract_memory_feature                                  lib/models/models.py:200-206
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "../../include/usot_b200.h"
 
 #include <cmath>
@@ -110,6 +111,19 @@ struct ConvW {
     float* w_kn = nullptr;   // [k*k*cin][cout] fp32 (SIMT path)
     float* scale = nullptr;  // folded BN
     float* shift = nullptr;
+    // tcgen05 path: [cout][K] fp16 planes of w*2^e, scale_tc = scale*2^-e
+    __half* w_hi = nullptr;
+    __half* w_lo = nullptr;
+    float* scale_tc = nullptr;
+};
+
+// One NHWC activation tensor; may exist as fp32, as split fp16 planes, or both.
+struct T {
+    float* f = nullptr;
+    __half* hi = nullptr;
+    __half* lo = nullptr;
+    int n = 0, h = 0, w = 0, c = 0;
+    size_t numel() const { return (size_t)n * h * w * c; }
 };
 
 struct PredW {
@@ -128,6 +142,7 @@ struct Arena {
         return plan ? reinterpret_cast<void*>(uintptr_t(0x1000) + a) : (void*)(base + a);
     }
     float* f(size_t n) { return static_cast<float*>(alloc(n * sizeof(float))); }
+    __half* h(size_t n) { return static_cast<__half*>(alloc(n * sizeof(__half))); }
 };
 
 }  // namespace usot
@@ -173,6 +188,16 @@ static int upload(usot_engine* e, const std::vector<float>& h, float** out) {
     e->owned.push_back(d);
     e->weight_bytes += (int64_t)h.size() * sizeof(float);
     *out = static_cast<float*>(d);
+    return 0;
+}
+
+static int upload_half(usot_engine* e, const std::vector<__half>& h, __half** out) {
+    void* d = nullptr;
+    USOT_CUDA_OK(cudaMalloc(&d, h.size() * sizeof(__half)));
+    USOT_CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    e->owned.push_back(d);
+    e->weight_bytes += (int64_t)h.size() * sizeof(__half);
+    *out = static_cast<__half*>(d);
     return 0;
 }
 
@@ -238,6 +263,12 @@ static int finalize_impl(usot_engine* e) {
         ConvW cw;
         cw.s = s;
         if (upload(e, packed, &cw.w_kn) || upload(e, scale, &cw.scale) || upload(e, shift, &cw.shift)) return 1;
+        if (e->precision != USOT_PREC_FP32_SIMT) {
+            std::vector<__half> hi, lo;
+            std::vector<float> scale_tc;
+            pack_tc_weights_host(packed.data(), K, s.cout, scale.data(), hi, lo, scale_tc);
+            if (upload_half(e, hi, &cw.w_hi) || upload_half(e, lo, &cw.w_lo) || upload(e, scale_tc, &cw.scale_tc)) return 1;
+        }
         e->convs[s.name] = cw;
     }
     auto pack_pred = [&](const std::string& name, int cout, PredW& pw) -> int {
@@ -282,33 +313,86 @@ struct Ctx {
     usot_engine* e;
     Arena& ar;
     cudaStream_t st;
+    bool tc() const { return e->precision != USOT_PREC_FP32_SIMT; }
+    bool split() const { return e->precision == USOT_PREC_FP16X3_TC; }
 };
 
-static int run_conv(Ctx& c, const std::string& name, const float* in, int n, int h, int w, const float* residual, float* out,
-                    int* ho_out = nullptr, int* wo_out = nullptr) {
+static inline int conv_hw(int in, int k, int s, int p, int d) { return conv_out(in, k, s, p, d); }
+
+// make sure `t` has the fp16 planes the tensor-core path reads (hi always, lo in split mode)
+static int ensure_split(Ctx& c, T& t) {
     Arena& ar = c.ar;
-    auto it = c.e->convs.find(name);
-    USOT_REQUIRE(it != c.e->convs.end(), "unknown conv layer");
-    const ConvW& cw = it->second;
-    ConvGeom g;
-    g.n = n; g.h = h; g.w = w; g.cin = cw.s.cin; g.cout = cw.s.cout; g.kh = g.kw = cw.s.k;
-    g.stride = cw.s.stride; g.ph = cw.s.ph; g.pw = cw.s.pw; g.dh = cw.s.dh; g.dw = cw.s.dw;
-    g.ho = conv_out(h, g.kh, g.stride, g.ph, g.dh);
-    g.wo = conv_out(w, g.kw, g.stride, g.pw, g.dw);
-    if (ho_out) *ho_out = g.ho;
-    if (wo_out) *wo_out = g.wo;
-    Epilogue ep{cw.scale, cw.shift, residual, cw.s.relu ? 1 : 0};
+    if (t.hi) return 0;
+    USOT_REQUIRE(t.f != nullptr, "tensor has no storage");
+    t.hi = ar.h(t.numel());
+    t.lo = c.split() ? ar.h(t.numel()) : nullptr;
     if (!ar.plan) {
-        Scope sc(FAM_CONV, c.st, 2.0 * n * g.ho * g.wo * (double)g.cout * g.kh * g.kw * g.cin);
-        RUN(launch_conv_simt(in, g, cw.w_kn, ep, out, c.st));
+        Scope sc(FAM_OTHER, c.st, 0, (double)t.numel() * (4 + (c.split() ? 4 : 2)));
+        RUN(launch_f32_to_split(t.f, t.numel(), t.hi, t.lo, c.st));
     }
     return 0;
 }
 
-static inline int conv_hw(int in, int k, int s, int p, int d) { return conv_out(in, k, s, p, d); }
+enum { OUT_F32 = 1, OUT_SPLIT = 2 };
 
-// x (n,3,S,S) nchw -> xf (n,F,F,256) nhwc written to xf_out (arena-allocated if NULL)
-static int backbone_neck(Ctx& c, const float* x, int n, int S, float** xf_out, int* F_out) {
+// One dense conv (+folded BN, +residual, +ReLU).  `want` selects the storage of the result (tensor-core mode only; the SIMT
+// path always produces fp32).  `f32_dst` optionally places the fp32 result in caller memory.
+static int run_conv(Ctx& c, const std::string& name, T& in, T* residual, int want, T* out, float* f32_dst = nullptr) {
+    Arena& ar = c.ar;
+    auto it = c.e->convs.find(name);
+    USOT_REQUIRE(it != c.e->convs.end(), "unknown conv layer");
+    const ConvW& cw = it->second;
+    USOT_REQUIRE(in.c == cw.s.cin, "conv input channel mismatch");
+    ConvGeom g;
+    g.n = in.n; g.h = in.h; g.w = in.w; g.cin = cw.s.cin; g.cout = cw.s.cout; g.kh = g.kw = cw.s.k;
+    g.stride = cw.s.stride; g.ph = cw.s.ph; g.pw = cw.s.pw; g.dh = cw.s.dh; g.dw = cw.s.dw;
+    g.ho = conv_out(in.h, g.kh, g.stride, g.ph, g.dh);
+    g.wo = conv_out(in.w, g.kw, g.stride, g.pw, g.dw);
+    USOT_REQUIRE(g.ho > 0 && g.wo > 0, "conv output is empty");
+    T o;
+    o.n = in.n; o.h = g.ho; o.w = g.wo; o.c = g.cout;
+    const double flops = 2.0 * o.n * g.ho * g.wo * (double)g.cout * g.kh * g.kw * g.cin;
+    if (!c.tc()) {
+        o.f = f32_dst ? f32_dst : ar.f(o.numel());
+        USOT_REQUIRE(!residual || residual->f, "SIMT conv needs an fp32 residual");
+        Epilogue ep{cw.scale, cw.shift, residual ? residual->f : nullptr, cw.s.relu ? 1 : 0};
+        if (!ar.plan) {
+            Scope sc(FAM_CONV, c.st, flops);
+            RUN(launch_conv_simt(in.f, g, cw.w_kn, ep, o.f, c.st));
+        }
+    } else {
+        if (int rc = ensure_split(c, in)) return rc;
+        if (residual)
+            if (int rc = ensure_split(c, *residual)) return rc;
+        if (f32_dst) want |= OUT_F32;
+        if (want & OUT_F32) o.f = f32_dst ? f32_dst : ar.f(o.numel());
+        if (want & OUT_SPLIT) {
+            o.hi = ar.h(o.numel());
+            o.lo = c.split() ? ar.h(o.numel()) : nullptr;
+        }
+        // in single-fp16 mode the lo planes do not exist: write into a scratch plane so the kernel has one code path
+        __half* lo_dst = o.lo;
+        if ((want & OUT_SPLIT) && !lo_dst) lo_dst = ar.h(o.numel());
+        const __half* res_lo = residual ? (residual->lo ? residual->lo : nullptr) : nullptr;
+        TcTensor ti{in.hi, in.lo};
+        TcWeights tw{cw.w_hi, cw.w_lo, cw.scale_tc, g.kh * g.kw * g.cin};
+        TcEpilogue ep{cw.shift, residual ? residual->hi : nullptr, res_lo, o.hi, lo_dst, o.f, cw.s.relu ? 1 : 0};
+        if (residual && !res_lo) {  // single-fp16 mode: an all-zero lo plane is not stored; reuse hi with a zeroed scratch instead
+            __half* z = ar.h(o.numel());
+            if (!ar.plan) USOT_CUDA_OK(cudaMemsetAsync(z, 0, o.numel() * sizeof(__half), c.st));
+            ep.res_lo = z;
+        }
+        if (!ar.plan) {
+            Scope sc(FAM_CONV, c.st, flops);
+            RUN(launch_conv_tc(ti, g, tw, ep, c.split(), c.st));
+        }
+    }
+    *out = o;
+    return 0;
+}
+
+// x (n,3,S,S) nchw -> xf (n,F,F,256) nhwc; fp32 copy written to xf_dst if given; split planes kept for the encoders
+static int backbone_neck(Ctx& c, const float* x, int n, int S, float* xf_dst, T* xf_out) {
     Arena& ar = c.ar;
     usot_engine* e = c.e;
     const int h1 = (S - 7) / 2 + 1;
@@ -318,112 +402,112 @@ static int backbone_neck(Ctx& c, const float* x, int n, int S, float** xf_out, i
         Scope sc(FAM_STEM, c.st, 2.0 * n * h1 * h1 * 64.0 * 147);
         RUN(launch_stem(x, n, S, e->stem_w, e->stem_scale, e->stem_shift, a0, c.st));
     }
-    float* cur = ar.f((size_t)n * h2 * h2 * 64);
+    T cur;
+    cur.n = n; cur.h = cur.w = h2; cur.c = 64;
+    cur.f = ar.f(cur.numel());
     if (!ar.plan) {
         Scope sc(FAM_POOL, c.st, 0, 4.0 * n * 64 * ((double)h1 * h1 + (double)h2 * h2));
-        RUN(launch_maxpool3x3s2p1(a0, n, h1, h1, 64, cur, c.st));
+        RUN(launch_maxpool3x3s2p1(a0, n, h1, h1, 64, cur.f, c.st));
     }
-    int h = h2;
-    struct L { const char* name; int planes, blocks; };
-    const L layers[3] = {{"layer1", 64, 3}, {"layer2", 128, 4}, {"layer3", 256, 6}};
+    struct L { const char* name; int blocks; };
+    const L layers[3] = {{"layer1", 3}, {"layer2", 4}, {"layer3", 6}};
     for (const L& l : layers) {
         for (int i = 0; i < l.blocks; ++i) {
             const std::string p = std::string("features.features.") + l.name + "." + std::to_string(i) + ".";
-            const float* res = cur;
-            int ho = h, wo = h;
-            if (i == 0) {
-                const ConvSpec& ds = e->convs.at(p + "downsample.0").s;
-                const int hd = conv_hw(h, ds.k, ds.stride, ds.ph, ds.dh);
-                float* r = ar.f((size_t)n * hd * hd * l.planes * 4);
-                if (int rc = run_conv(c, p + "downsample.0", cur, n, h, h, nullptr, r)) return rc;
-                res = r;
-            }
-            float* t1 = ar.f((size_t)n * h * h * l.planes);
-            if (int rc = run_conv(c, p + "conv1", cur, n, h, h, nullptr, t1)) return rc;
-            const ConvSpec& s2 = e->convs.at(p + "conv2").s;
-            ho = wo = conv_hw(h, 3, s2.stride, s2.ph, s2.dh);
-            float* t2 = ar.f((size_t)n * ho * wo * l.planes);
-            if (int rc = run_conv(c, p + "conv2", t1, n, h, h, nullptr, t2)) return rc;
-            float* t3 = ar.f((size_t)n * ho * wo * l.planes * 4);
-            if (int rc = run_conv(c, p + "conv3", t2, n, ho, wo, res, t3)) return rc;
+            T res, t1, t2, t3;
+            if (i == 0)
+                if (int rc = run_conv(c, p + "downsample.0", cur, nullptr, OUT_SPLIT, &res)) return rc;
+            if (int rc = run_conv(c, p + "conv1", cur, nullptr, OUT_SPLIT, &t1)) return rc;
+            if (i > 0) res = cur;  // identity shortcut (taken after conv1 so fp16 planes materialised for it are shared)
+            if (int rc = run_conv(c, p + "conv2", t1, nullptr, OUT_SPLIT, &t2)) return rc;
+            if (int rc = run_conv(c, p + "conv3", t2, &res, OUT_SPLIT, &t3)) return rc;
             cur = t3;
-            h = ho;
         }
     }
-    float* xf = *xf_out ? *xf_out : ar.f((size_t)n * h * h * 256);
-    if (int rc = run_conv(c, "neck.downsample.0", cur, n, h, h, nullptr, xf)) return rc;
-    *xf_out = xf;
-    *F_out = h;
+    if (int rc = run_conv(c, "neck.downsample.0", cur, nullptr, OUT_F32 | OUT_SPLIT, xf_out, xf_dst)) return rc;
     return 0;
 }
 
 struct Enc3 {
-    float* m[3];
+    T m[3];
 };
 
-// matrix.forward for one branch: three parallel 3x3 convs on the same input (connect.py:55-74)
-static int encode(Ctx& c, const char* enc, char branch, const float* in, int n, int f, Enc3* out) {
-    Arena& ar = c.ar;
+// matrix.forward for one branch: three parallel 3x3 convs on the same input (connect.py:55-74); fp32 results (xcorr input)
+static int encode(Ctx& c, const char* enc, char branch, T& in, Enc3* out) {
     static const char* mn[3] = {"matrix11", "matrix12", "matrix21"};
-    static const int dh[3] = {1, 2, 1}, dw[3] = {1, 1, 2};
     for (int i = 0; i < 3; ++i) {
-        const int ho = f - 2 * dh[i], wo = f - 2 * dw[i];
-        out->m[i] = ar.f((size_t)n * ho * wo * 256);
         const std::string name = std::string("connect_model.") + enc + "." + mn[i] + "_" + branch + ".0";
-        if (int rc = run_conv(c, name, in, n, f, f, nullptr, out->m[i])) return rc;
+        if (int rc = run_conv(c, name, in, nullptr, OUT_F32, &out->m[i])) return rc;
     }
     return 0;
 }
 
-static int tower(Ctx& c, const char* name, const float* in, int n, int r, float** out) {
-    Arena& ar = c.ar;
-    const float* cur = in;
-    float* o = nullptr;
+static int tower(Ctx& c, const char* name, T in, T* out) {
+    T cur = in;
     for (int i = 0; i < 4; ++i) {
-        o = ar.f((size_t)n * r * r * 256);
-        if (int rc = run_conv(c, std::string("connect_model.") + name + "." + std::to_string(3 * i), cur, n, r, r, nullptr, o)) return rc;
+        T o;
+        if (int rc = run_conv(c, std::string("connect_model.") + name + "." + std::to_string(3 * i), cur, nullptr,
+                              i == 3 ? OUT_F32 : OUT_SPLIT, &o))
+            return rc;
         cur = o;
+    }
+    *out = cur;
+    return 0;
+}
+
+static int groupdw(Ctx& c, const Enc3& x, const Enc3& z, int n_out, int F, const float* w3, T* out) {
+    Arena& ar = c.ar;
+    const int nx = x.m[0].n, nz = z.m[0].n, R = F - 6;
+    T o;
+    o.n = n_out; o.h = o.w = R; o.c = 256;
+    o.f = ar.f(o.numel());
+    GroupDWArgs a;
+    a.x11 = x.m[0].f; a.x12 = x.m[1].f; a.x21 = x.m[2].f;
+    a.z11 = z.m[0].f; a.z12 = z.m[1].f; a.z21 = z.m[2].f;
+    a.dw_weight = nullptr; a.out = o.f; a.nx = nx; a.nz = nz; a.n_out = n_out; a.C = 256; a.F = F;
+    if (!ar.plan) {
+        // algorithmic bytes: every search map read once, every output written once, taps once
+        const double per_x = 256.0 * ((F - 2.0) * (F - 2) + 2.0 * (F - 4) * (F - 2));
+        Scope sc(FAM_XCORR, c.st, 0, 4.0 * (nx * per_x + n_out * 256.0 * R * R + nz * 256.0 * 55));
+        RUN(launch_groupdw_w(a, w3[0], w3[1], w3[2], c.st));
     }
     *out = o;
     return 0;
 }
 
-static int groupdw(Ctx& c, const Enc3& x, int nx, const Enc3& z, int nz, int n_out, int F, const float* w3, float* out) {
+static int pred(Ctx& c, const PredW& pw, const T& in, int mode, float* out) {
     Arena& ar = c.ar;
-    GroupDWArgs a;
-    a.x11 = x.m[0]; a.x12 = x.m[1]; a.x21 = x.m[2];
-    a.z11 = z.m[0]; a.z12 = z.m[1]; a.z21 = z.m[2];
-    a.dw_weight = nullptr; a.out = out; a.nx = nx; a.nz = nz; a.n_out = n_out; a.C = 256; a.F = F;
+    usot_engine* e = c.e;
     if (!ar.plan) {
-        // algorithmic bytes: every search map read once per output sample group + output written once
-        const double R = F - 6, per_x = 256.0 * ((F - 2.0) * (F - 2) + 2.0 * (F - 4) * (F - 2));
-        Scope sc(FAM_XCORR, c.st, 0, 4.0 * (nx * per_x + n_out * 256.0 * R * R + nz * 256.0 * 55));
-        RUN(launch_groupdw_w(a, w3[0], w3[1], w3[2], c.st));
+        Scope sc(FAM_PRED, c.st, 2.0 * in.n * in.h * in.w * 256.0 * 9 * pw.cout);
+        RUN(launch_pred_conv(in.f, in.n, in.h, 256, pw.w, pw.b, pw.cout, mode, mode == 0 ? 0.1f : 1.f, e->adjust, e->bias4, out, c.st));
     }
     return 0;
 }
 
+static T wrap_f32(const float* p, int n, int h, int w, int ch) {
+    T t;
+    t.f = const_cast<float*>(p); t.n = n; t.h = h; t.w = w; t.c = ch;
+    return t;
+}
+
 // box_tower_reg.forward, offline branch (connect.py:224-247). Returns the encoded cls search maps for the memory branch.
-static int head_offline(Ctx& c, const float* xf, int n, int F, const float* zf, int nz, float* cls, float* bbox, Enc3* cls_x) {
-    Arena& ar = c.ar;
+static int head_offline(Ctx& c, T& xf, const float* zf, int nz, float* cls, float* bbox, Enc3* cls_x) {
     usot_engine* e = c.e;
-    const int R = F - 6;
+    const int n = xf.n, F = xf.h;
     Enc3 cls_z, reg_z, reg_x;
-    if (int rc = encode(c, "cls_encode", 'k', zf, nz, 7, &cls_z)) return rc;
-    if (int rc = encode(c, "cls_encode", 's', xf, n, F, cls_x)) return rc;
-    if (int rc = encode(c, "reg_encode", 'k', zf, nz, 7, &reg_z)) return rc;
-    if (int rc = encode(c, "reg_encode", 's', xf, n, F, &reg_x)) return rc;
-    float* cls_dw = ar.f((size_t)n * R * R * 256);
-    float* reg_dw = ar.f((size_t)n * R * R * 256);
-    if (int rc = groupdw(c, *cls_x, n, cls_z, nz, n, F, e->dw_cls, cls_dw)) return rc;
-    if (int rc = groupdw(c, reg_x, n, reg_z, nz, n, F, e->dw_reg, reg_dw)) return rc;
-    float *x_reg, *x_cls;
-    if (int rc = tower(c, "bbox_tower", reg_dw, n, R, &x_reg)) return rc;
-    if (!ar.plan) g_prof.launches[FAM_PRED]++;
-    RUN(launch_pred_conv(x_reg, n, R, 256, e->bbox_pred.w, e->bbox_pred.b, 4, 1, 1.f, e->adjust, e->bias4, bbox, c.st));
-    if (int rc = tower(c, "cls_tower", cls_dw, n, R, &x_cls)) return rc;
-    if (!ar.plan) g_prof.launches[FAM_PRED]++;
-    RUN(launch_pred_conv(x_cls, n, R, 256, e->cls_pred.w, e->cls_pred.b, 1, 0, 0.1f, nullptr, nullptr, cls, c.st));
+    T z = wrap_f32(zf, nz, 7, 7, 256);
+    if (int rc = encode(c, "cls_encode", 'k', z, &cls_z)) return rc;
+    if (int rc = encode(c, "cls_encode", 's', xf, cls_x)) return rc;
+    if (int rc = encode(c, "reg_encode", 'k', z, &reg_z)) return rc;
+    if (int rc = encode(c, "reg_encode", 's', xf, &reg_x)) return rc;
+    T cls_dw, reg_dw, x_reg, x_cls;
+    if (int rc = groupdw(c, *cls_x, cls_z, n, F, e->dw_cls, &cls_dw)) return rc;
+    if (int rc = groupdw(c, reg_x, reg_z, n, F, e->dw_reg, &reg_dw)) return rc;
+    if (int rc = tower(c, "bbox_tower", reg_dw, &x_reg)) return rc;
+    if (int rc = pred(c, e->bbox_pred, x_reg, 1, bbox)) return rc;
+    if (int rc = tower(c, "cls_tower", cls_dw, &x_cls)) return rc;
+    if (int rc = pred(c, e->cls_pred, x_cls, 0, cls)) return rc;
     return 0;
 }
 
@@ -433,23 +517,34 @@ static int head_memory(Ctx& c, const Enc3& cls_x, int n, int F, const float* mem
     usot_engine* e = c.e;
     const int R = F - 6;
     Enc3 mz;
-    if (int rc = encode(c, "cls_encode", 'k', mem, n * nq, 7, &mz)) return rc;
+    T m = wrap_f32(mem, n * nq, 7, 7, 256);
+    if (int rc = encode(c, "cls_encode", 'k', m, &mz)) return rc;
+    T dw, conf, val, t;
+    if (int rc = groupdw(c, cls_x, mz, n * nq, F, e->dw_cls, &dw)) return rc;
+    if (int rc = run_conv(c, "connect_model.conf_fusion.conf_gen.0", dw, nullptr, OUT_F32, &conf)) return rc;
+    if (int rc = run_conv(c, "connect_model.conf_fusion.value_gen.0", dw, nullptr, OUT_F32, &val)) return rc;
     const size_t per_map = (size_t)R * R * 256;
-    float* dw = ar.f((size_t)n * nq * per_map);
-    if (int rc = groupdw(c, cls_x, n, mz, n * nq, n * nq, F, e->dw_cls, dw)) return rc;
-    float* conf = ar.f((size_t)n * nq * per_map);
-    float* val = ar.f((size_t)n * nq * per_map);
-    if (int rc = run_conv(c, "connect_model.conf_fusion.conf_gen.0", dw, n * nq, R, R, nullptr, conf)) return rc;
-    if (int rc = run_conv(c, "connect_model.conf_fusion.value_gen.0", dw, n * nq, R, R, nullptr, val)) return rc;
-    float* fused = ar.f((size_t)n * per_map);
-    if (!ar.plan) g_prof.launches[FAM_FUSION]++;
-    RUN(launch_conf_fusion(conf, val, n, nq, per_map, fused, c.st));
-    float* t;
-    if (int rc = tower(c, "cls_memory_tower", fused, n, R, &t)) return rc;
-    if (!ar.plan) g_prof.launches[FAM_PRED]++;
-    RUN(launch_pred_conv(t, n, R, 256, e->cls_memory_pred.w, e->cls_memory_pred.b, 1, 0, 0.1f, nullptr, nullptr, cls_mem, c.st));
+    T fused;
+    fused.n = n; fused.h = fused.w = R; fused.c = 256;
+    fused.f = ar.f(fused.numel());
+    if (!ar.plan) {
+        Scope sc(FAM_FUSION, c.st, 0, 4.0 * per_map * (2.0 * n * nq + n));
+        RUN(launch_conf_fusion(conf.f, val.f, n, nq, per_map, fused.f, c.st));
+    }
+    if (int rc = tower(c, "cls_memory_tower", fused, &t)) return rc;
+    if (int rc = pred(c, e->cls_memory_pred, t, 0, cls_mem)) return rc;
     return 0;
 }
+
+static int prroi(Ctx& c, const T& feat, const float* boxes, int n_rois, float* out) {
+    Arena& ar = c.ar;
+    if (!ar.plan) {
+        Scope sc(FAM_PRROI, c.st);
+        RUN(launch_prroi_nhwc(feat.f, feat.n, feat.h, feat.w, feat.c, boxes, n_rois, out, c.st));
+    }
+    return 0;
+}
+
 
 // Two-pass driver: plan (count arena bytes) -> grow arena if needed -> execute.
 template <typename Fn>
@@ -514,6 +609,8 @@ int usot_profile_read(int fam, double* out) {
 
 int usot_set_tunable(const char* name, int value) {
     USOT_REQUIRE(name, "null name");
+    if (!strcmp(name, "tc_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_bn_max must be 64, 128 or 256"); g_tc_bn_max = value; return 0; }
+    if (!strcmp(name, "tc_split_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_split_bn_max must be 64, 128 or 256"); g_tc_split_bn_max = value; return 0; }
     if (!strcmp(name, "groupdw_strips")) { USOT_REQUIRE(value == 2 || value == 3, "groupdw_strips must be 2 or 3"); g_groupdw_strips = value; return 0; }
     USOT_REQUIRE(false, "unknown tunable");
 }
@@ -544,12 +641,48 @@ int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float*
                      int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift, const float* residual,
                      int relu, float* out, int precision, void* stream) {
     USOT_REQUIRE(in && weight_kn && scale && shift && out, "null pointer");
-    USOT_REQUIRE(precision == USOT_PREC_FP32_SIMT, "usot_conv2d_nhwc: only USOT_PREC_FP32_SIMT is wired for the stand-alone op");
+    USOT_REQUIRE(precision >= USOT_PREC_FP32_SIMT && precision <= USOT_PREC_FP16_TC, "unknown precision mode");
     ConvGeom g{n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w, conv_out(h, kh, stride, pad_h, dil_h),
                conv_out(w, kw, stride, pad_w, dil_w)};
     USOT_REQUIRE(g.ho > 0 && g.wo > 0, "conv output is empty");
-    Epilogue ep{scale, shift, residual, relu};
-    return launch_conv_simt(in, g, weight_kn, ep, out, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == USOT_PREC_FP32_SIMT) {
+        Epilogue ep{scale, shift, residual, relu};
+        return launch_conv_simt(in, g, weight_kn, ep, out, st);
+    }
+    // Tensor-core path of the stand-alone op (test/debug entry: packs the weights on the host and synchronises).
+    const bool split = precision == USOT_PREC_FP16X3_TC;
+    const int K = kh * kw * cin;
+    const size_t n_in = (size_t)n * h * w * cin, n_out = (size_t)n * g.ho * g.wo * cout;
+    std::vector<float> hw((size_t)K * cout), hs(cout), scale_tc;
+    USOT_CUDA_OK(cudaMemcpyAsync(hw.data(), weight_kn, hw.size() * 4, cudaMemcpyDeviceToHost, st));
+    USOT_CUDA_OK(cudaMemcpyAsync(hs.data(), scale, cout * 4, cudaMemcpyDeviceToHost, st));
+    USOT_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<__half> whi, wlo;
+    pack_tc_weights_host(hw.data(), K, cout, hs.data(), whi, wlo, scale_tc);
+    __half *d_whi = nullptr, *d_wlo = nullptr, *d_ihi = nullptr, *d_ilo = nullptr, *d_rhi = nullptr, *d_rlo = nullptr;
+    float* d_scale = nullptr;
+    int rc = 0;
+    auto fail = [&](int code) { rc = code; };
+    do {
+        if (cudaMalloc(&d_whi, whi.size() * 2) || cudaMalloc(&d_wlo, wlo.size() * 2) || cudaMalloc(&d_scale, cout * 4) ||
+            cudaMalloc(&d_ihi, n_in * 2) || cudaMalloc(&d_ilo, n_in * 2)) { set_error("usot_conv2d_nhwc: cudaMalloc failed"); fail(1); break; }
+        cudaMemcpyAsync(d_whi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_wlo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_scale, scale_tc.data(), cout * 4, cudaMemcpyHostToDevice, st);
+        if ((rc = launch_f32_to_split(in, n_in, d_ihi, d_ilo, st))) break;
+        if (residual) {
+            if (cudaMalloc(&d_rhi, n_out * 2) || cudaMalloc(&d_rlo, n_out * 2)) { set_error("usot_conv2d_nhwc: cudaMalloc failed"); fail(1); break; }
+            if ((rc = launch_f32_to_split(residual, n_out, d_rhi, d_rlo, st))) break;
+        }
+        TcTensor ti{d_ihi, split ? d_ilo : nullptr};
+        TcWeights tw{d_whi, split ? d_wlo : nullptr, d_scale, K};
+        TcEpilogue ep{shift, d_rhi, d_rlo, nullptr, nullptr, out, relu};
+        if ((rc = launch_conv_tc(ti, g, tw, ep, split, st))) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("usot_conv2d_nhwc: ") + cudaGetErrorString(cudaGetLastError())); fail(1); }
+    } while (0);
+    cudaFree(d_whi); cudaFree(d_wlo); cudaFree(d_scale); cudaFree(d_ihi); cudaFree(d_ilo); cudaFree(d_rhi); cudaFree(d_rlo);
+    return rc;
 }
 
 int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream) {
@@ -605,9 +738,8 @@ int usot_engine_backbone_neck(usot_engine* e, const float* x, int n, int size, f
     USOT_REQUIRE(x && xf && n > 0 && size >= 63, "bad argument");
     return with_arena(e, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
-        float* o = xf;
-        int F;
-        return backbone_neck(c, x, n, size, &o, &F);
+        T f;
+        return backbone_neck(c, x, n, size, xf, &f);
     });
 }
 
@@ -616,15 +748,11 @@ int usot_engine_template(usot_engine* e, const float* z, int n, int size, const 
     USOT_REQUIRE(z && zf && n > 0 && size >= 63, "bad argument");
     return with_arena(e, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
-        float* o = x_ori;
-        int F;
-        if (int rc = backbone_neck(c, z, n, size, &o, &F)) return rc;
-        if (!ar.plan) g_prof.launches[FAM_PRROI]++;
-        if (template_bbox) RUN(launch_prroi_nhwc(o, n, F, F, 256, template_bbox, n, zf, c.st));
-        else {
-            USOT_REQUIRE(F - 8 == 7, "pr_pool=False template needs a 127x127 exemplar (15x15 feature)");
-            RUN(launch_center_crop_nhwc(o, n, F, F, 256, 4, zf, c.st));
-        }
+        T f;
+        if (int rc = backbone_neck(c, z, n, size, x_ori, &f)) return rc;
+        if (template_bbox) return prroi(c, f, template_bbox, n, zf);
+        USOT_REQUIRE(f.h - 8 == 7, "pr_pool=False template needs a 127x127 exemplar (15x15 feature)");
+        RUN(launch_center_crop_nhwc(f.f, n, f.h, f.w, 256, 4, zf, c.st));
         return 0;
     });
 }
@@ -637,13 +765,12 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
     USOT_REQUIRE(usot_feature_size(size) >= 9, "search crop too small");
     return with_arena(e, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
-        float* f = xf;
-        int F;
-        if (int rc = backbone_neck(c, x, n, size, &f, &F)) return rc;
+        T f;
+        if (int rc = backbone_neck(c, x, n, size, xf, &f)) return rc;
         Enc3 cls_x;
-        if (int rc = head_offline(c, f, n, F, zf, nz, cls, bbox, &cls_x)) return rc;
+        if (int rc = head_offline(c, f, zf, nz, cls, bbox, &cls_x)) return rc;
         if (nq > 0)
-            if (int rc = head_memory(c, cls_x, n, F, template_mem, nq, cls_mem)) return rc;
+            if (int rc = head_memory(c, cls_x, n, f.h, template_mem, nq, cls_mem)) return rc;
         return 0;
     });
 }
@@ -654,16 +781,10 @@ int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n
     USOT_REQUIRE(search_bbox && out && n > 0, "bad argument");
     return with_arena(e, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
-        const float* f = xf;
-        int F = feat;
-        if (ori_x) {
-            float* o = nullptr;
-            if (int rc = backbone_neck(c, ori_x, n, size, &o, &F)) return rc;
-            f = o;
-        }
-        if (!ar.plan) g_prof.launches[FAM_PRROI]++;
-        RUN(launch_prroi_nhwc(f, n, F, F, 256, search_bbox, n, out, c.st));
-        return 0;
+        T f = wrap_f32(xf, n, feat, feat, 256);
+        if (ori_x)
+            if (int rc = backbone_neck(c, ori_x, n, size, nullptr, &f)) return rc;
+        return prroi(c, f, search_bbox, n, out);
     });
 }
 

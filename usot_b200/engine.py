@@ -19,7 +19,7 @@ def feature_size(image_size):
 
 
 class Engine:
-    def __init__(self, device, precision="fp32"):
+    def __init__(self, device, precision="fp16x3"):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("usot_b200.Engine needs a CUDA device; there is no CPU fallback")

@@ -128,7 +128,7 @@ class USOT_(nn.Module):
         self.mem_size = mem_size
         self.pr_pool = pr_pool
         # dense-conv arithmetic: "fp32" (CUDA-core FMA), "fp16x3" (tcgen05, fp32-equivalent), "fp16" (tcgen05 fast mode)
-        self.precision = precision or os.environ.get("USOT_B200_PRECISION", "fp32")
+        self.precision = precision or os.environ.get("USOT_B200_PRECISION", "fp16x3")
         self._engines = {}
         self._engine_keys = {}
         self._lock = threading.Lock()
