@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_model.py -q -m gpu -s > gpurun_out/model_tests.log 2>&1
-grep -oE "(damp025|raw) [a-z0-9]+ fp[0-9x]+ \{[^}]*\}|backbone fresh [a-z0-9]+ [0-9.e-]+|[0-9]+ (passed|failed).*" gpurun_out/model_tests.log
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 6 -o gpurun_out/prof_conv_v1 python tools/conv_cases.py l3_conv3,l3_down,l1_conv3 256 fp16x3 > gpurun_out/ncu_conv.log 2>&1
+tail -3 gpurun_out/ncu_conv.log

@@ -281,6 +281,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
+            const size_t off0 = pix * p.cout + n0;
+            // Residual loads are software-pipelined one 32-column chunk ahead and the first chunk is requested BEFORE waiting
+            // for the accumulator, so their DRAM latency hides behind the MMAs / the previous chunk's math.
+            uint4 rh[4], rl[4];
+            const bool has_res = p.res_hi != nullptr && valid;
+            if (has_res) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0) + q);
+                    rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0) + q);
+                }
+            }
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS;
@@ -288,6 +300,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
+                uint4 ch[4], cl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { ch[q] = rh[q]; cl[q] = rl[q]; }
+                if (has_res && c0 + 32 < BN) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0 + c0 + 32) + q);
+                        rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + c0 + 32) + q);
+                    }
+                }
                 if (Cfg::XACC) {
                     uint32_t x[32];
                     tmem_ld32(taddr + BN + c0, x);
@@ -301,15 +323,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
-                    const size_t off = pix * p.cout + n0 + c0;
-                    if (p.res_hi) {
-                        const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + off);
-                        const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + off);
+                    const size_t off = off0 + c0;
+                    if (has_res) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            uint4 a = __ldg(rh + q), b = __ldg(rl + q);
-                            const __half2* ah = reinterpret_cast<const __half2*>(&a);
-                            const __half2* bl = reinterpret_cast<const __half2*>(&b);
+                            const __half2* ah = reinterpret_cast<const __half2*>(&ch[q]);
+                            const __half2* bl = reinterpret_cast<const __half2*>(&cl[q]);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 float2 fa = __half22float2(ah[e]), fb = __half22float2(bl[e]);
