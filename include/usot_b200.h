@@ -121,6 +121,24 @@ USOT_API int usot_engine_track(usot_engine* e, const float* x, int n, int size, 
 USOT_API int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n, int size, const float* xf, int feat,
                                                 const float* search_bbox, float* out, void* stream);
 
+/* Head part of USOT_.forward (lib/models/models.py:223-295) with eval-mode BN: everything after the three backbone+neck
+ * passes, which the caller runs with usot_engine_template / usot_engine_backbone_neck (so that a multi-GPU caller can overlap
+ * its all-gather of zf with them).  zf (n,7,7,256), xf (n,feat,feat,256), xf_mem (n*m,feat,feat,256) nhwc; m = 0 selects the
+ * naive-Siamese branch (models.py:288-295).  label (n,R,R), reg_target (n,R,R,4), reg_weight (n,R,R), search_bbox (n,4).
+ * losses[3] (device) = {cls_loss, cls_memory_loss (0 if m == 0), reg_loss}.  Optional outputs (may be NULL): backward_map
+ * (n,1,R,R) and pool_box (n*m,4) = the PrPool boxes of the forward-tracked targets. */
+USOT_API int usot_engine_forward_train(usot_engine* e, const float* zf, const float* xf, const float* xf_mem, int n, int m, int feat,
+                                       const float* label, const float* reg_target, const float* reg_weight, const float* search_bbox,
+                                       float cls_ratio, float* losses, float* backward_map, float* pool_box, void* stream);
+
+/* Tensor path of USOTTracker.update for one frame, on the device (no host sync): sigmoid, ratio mix, box decode on the
+ * stride-8 grid, size/ratio penalty, cosine window, argmax.  cls / cls_mem (1,1,R,R), bbox (1,4,R,R) nchw fp32; window (R,R)
+ * float64 (numpy's np.outer(np.hanning, np.hanning)); target_w/h = target size already multiplied by scale_z.
+ * result[8] (device, float64) = {r_max, c_max, x1, y1, x2, y2, penalty[r,c], mixed_score[r,c]}. */
+USOT_API int usot_tracker_postprocess(const float* cls, const float* cls_mem, const float* bbox, const double* window, int score_size,
+                                      int instance_size, double target_w, double target_h, double ratio, double penalty_k,
+                                      double window_influence, double* result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

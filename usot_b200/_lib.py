@@ -21,6 +21,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _F = ctypes.c_float
 _I64 = ctypes.c_int64
+_D = ctypes.c_double
 
 # name -> (restype, argtypes); must list every USOT_API symbol of the header (tests/test_abi.py checks this)
 SIGNATURES = {
@@ -47,6 +48,8 @@ SIGNATURES = {
     "usot_engine_template": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "usot_engine_track": (_I, [_P, _P, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P]),
     "usot_engine_extract_memory_feature": (_I, [_P, _P, _I, _I, _P, _I, _P, _P, _P]),
+    "usot_engine_forward_train": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P]),
+    "usot_tracker_postprocess": (_I, [_P, _P, _P, _P, _I, _I, _D, _D, _D, _D, _D, _P, _P]),
 }
 
 

@@ -60,7 +60,7 @@ int launch_stem(const float* x_nchw, int n, int s, const float* w_packed /*[147]
 int launch_maxpool3x3s2p1(const float* in, int n, int h, int w, int c, float* out, cudaStream_t st);
 int launch_conv_simt(const float* in, const ConvGeom& g, const float* w_kn /*[kh*kw*cin][cout]*/, const Epilogue& ep,
                      float* out, cudaStream_t st);
-// Fused GroupDW: out[n] = sum_i sw[i] * xcorr(x_i[n / rep], z_i[zb])  with zb = (nz == n_out ? n : 0)
+// Fused GroupDW: out[n] = sum_i sw[i] * xcorr(x_i[n / (n_out/nx)], z_i[n / (n_out/nz)])
 struct GroupDWArgs {
     const float* x11; const float* x12; const float* x21;  // [nx][F-2][F-2][C], [nx][F-4][F-2][C], [nx][F-2][F-4][C]
     const float* z11; const float* z12; const float* z21;  // [nz][5][5][C], [nz][3][5][C], [nz][5][3][C]
@@ -85,6 +85,12 @@ int launch_prroi_nchw(const float* feat, int c, int h, int w, const float* rois5
                       float* out, cudaStream_t st);
 int launch_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, cudaStream_t st);
 int launch_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, cudaStream_t st);
+int launch_tracker_post(const float* cls, const float* cls_mem, const float* bbox, const double* window, int R, int instance_size,
+                        double tw, double th, float ratio, double penalty_k, double window_influence, double* result, cudaStream_t st);
+int launch_cycle_glue(const float* off_cls, const float* mem_cls, const float* off_bbox, int n, int R, int search_size, int sf_size,
+                      float ratio, float* pool_box, float* best_score, int* best_idx, cudaStream_t st);
+int launch_bce(const float* pred, const float* label, int count, float* out, cudaStream_t st);
+int launch_iou(const float* bbox, const float* target, const float* weight, int n, int cells, float* out, cudaStream_t st);
 int launch_center_crop_nhwc(const float* in, int n, int h, int w, int c, int l, float* out, cudaStream_t st);
 
 }  // namespace usot

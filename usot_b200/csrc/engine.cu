@@ -512,12 +512,14 @@ static int head_offline(Ctx& c, T& xf, const float* zf, int nz, float* cls, floa
 }
 
 // box_tower_reg.forward, memory branch (connect.py:248-280). mem: (n*nq,7,7,256) nhwc.
-static int head_memory(Ctx& c, const Enc3& cls_x, int n, int F, const float* mem, int nq, float* cls_mem) {
+// `mem_n` distinct kernels serve the n*nq (sample, slot) pairs in order (mem_n == n*nq at inference; in the cycle-memory
+// forward pass one pooled feature per sample is shared by its m memory frames, models.py:240-244).
+static int head_memory(Ctx& c, const Enc3& cls_x, int n, int F, const float* mem, int nq, int mem_n, float* cls_mem) {
     Arena& ar = c.ar;
     usot_engine* e = c.e;
     const int R = F - 6;
     Enc3 mz;
-    T m = wrap_f32(mem, n * nq, 7, 7, 256);
+    T m = wrap_f32(mem, mem_n, 7, 7, 256);
     if (int rc = encode(c, "cls_encode", 'k', m, &mz)) return rc;
     T dw, conf, val, t;
     if (int rc = groupdw(c, cls_x, mz, n * nq, F, e->dw_cls, &dw)) return rc;
@@ -770,7 +772,7 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
         Enc3 cls_x;
         if (int rc = head_offline(c, f, zf, nz, cls, bbox, &cls_x)) return rc;
         if (nq > 0)
-            if (int rc = head_memory(c, cls_x, n, f.h, template_mem, nq, cls_mem)) return rc;
+            if (int rc = head_memory(c, cls_x, n, f.h, template_mem, nq, n * nq, cls_mem)) return rc;
         return 0;
     });
 }
@@ -786,6 +788,56 @@ int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n
             if (int rc = backbone_neck(c, ori_x, n, size, nullptr, &f)) return rc;
         return prroi(c, f, search_bbox, n, out);
     });
+}
+
+int usot_engine_forward_train(usot_engine* e, const float* zf, const float* xf, const float* xf_mem, int n, int m, int feat,
+                              const float* label, const float* reg_target, const float* reg_weight, const float* search_bbox,
+                              float cls_ratio, float* losses, float* backward_map, float* pool_box, void* stream) {
+    USOT_REQUIRE(zf && xf && label && reg_target && reg_weight && losses && n > 0 && m >= 0, "bad argument");
+    USOT_REQUIRE(m == 0 || (xf_mem && search_bbox), "cycle memory needs xf_mem and search_bbox");
+    USOT_REQUIRE(feat >= 9, "feature map too small");
+    return with_arena(e, [&](Arena& ar) {
+        Ctx c{e, ar, (cudaStream_t)stream};
+        const int R = feat - 6, cells = R * R;
+        T xf_t = wrap_f32(xf, n, feat, feat, 256);
+        float* cls1 = ar.f((size_t)n * cells);
+        float* bbox1 = ar.f((size_t)n * 4 * cells);
+        Enc3 cls_x;
+        if (int rc = head_offline(c, xf_t, zf, n, cls1, bbox1, &cls_x)) return rc;                    // models.py:225
+        RUN(launch_iou(bbox1, reg_target, reg_weight, n, cells, losses + 2, c.st));                  // :228
+        RUN(launch_bce(cls1, label, n * cells, losses + 0, c.st));                                   // :230
+        if (m == 0) {
+            if (!ar.plan) USOT_CUDA_OK(cudaMemsetAsync(losses + 1, 0, sizeof(float), c.st));
+            return 0;
+        }
+        T xfm_t = wrap_f32(xf_mem, n * m, feat, feat, 256);
+        float* spf = ar.f((size_t)n * 49 * 256);
+        if (int rc = prroi(c, xf_t, search_bbox, n, spf)) return rc;                                   // :240
+        float* off_cls = ar.f((size_t)n * m * cells);
+        float* off_bbox = ar.f((size_t)n * m * 4 * cells);
+        Enc3 fwd_x;
+        if (int rc = head_offline(c, xfm_t, zf, n, off_cls, off_bbox, &fwd_x)) return rc;             // :253 (zf shared by the m frames)
+        float* mem_cls = ar.f((size_t)n * m * cells);
+        if (int rc = head_memory(c, fwd_x, n * m, feat, spf, 1, n, mem_cls)) return rc;               // :256-259
+        float* pbox = pool_box ? pool_box : ar.f((size_t)n * m * 4);
+        RUN(launch_cycle_glue(off_cls, mem_cls, off_bbox, n * m, R, 255 + (feat - 31) * 8, R, cls_ratio, pbox, nullptr, nullptr, c.st));  // :265-274
+        float* pooled = ar.f((size_t)n * m * 49 * 256);
+        if (int rc = prroi(c, xfm_t, pbox, n * m, pooled)) return rc;                                  // :277
+        float* back = backward_map ? backward_map : ar.f((size_t)n * cells);
+        if (int rc = head_memory(c, cls_x, n, feat, pooled, m, n * m, back)) return rc;               // :279-281
+        RUN(launch_bce(back, label, n * cells, losses + 1, c.st));                                   // :284
+        return 0;
+    });
+}
+
+int usot_tracker_postprocess(const float* cls, const float* cls_mem, const float* bbox, const double* window, int score_size,
+                             int instance_size, double target_w, double target_h, double ratio, double penalty_k,
+                             double window_influence, double* result, void* stream) {
+    USOT_REQUIRE(cls && cls_mem && bbox && window && result, "null pointer");
+    USOT_REQUIRE(target_w > 0 && target_h > 0, "target size must be positive");
+    g_prof.launches[FAM_OTHER]++;
+    return launch_tracker_post(cls, cls_mem, bbox, window, score_size, instance_size, target_w, target_h, (float)ratio, penalty_k,
+                               window_influence, result, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,202 @@
+// Small latency-bound kernels around the heads:
+//   tracker_post_kernel   tensor path of USOTTracker.update          lib/tracker/usot_tracker.py:137-163
+//   cycle_glue_kernel     forward-track argmax + box gather + PrPool box map   lib/models/models.py:131-162,265-274
+//   bce_kernel            _weighted_BCE / _cls_loss                   lib/models/models.py:42-58
+//   iou_kernel            add_iouloss / _IOULoss                      lib/models/models.py:60-100
+#include "common.cuh"
+#include <cfloat>
+#include <cmath>
+
+namespace usot {
+
+// ---- block-wide argmax (first index wins ties, like numpy.argmax / torch.max on a flat map) -------------------
+template <typename TV>
+static __device__ void block_argmax(TV& v, int& idx) {
+    __shared__ double sv[32];
+    __shared__ int si[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    double dv = (double)v;
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, dv, off);
+        int oi = __shfl_down_sync(0xffffffffu, idx, off);
+        if (ov > dv || (ov == dv && oi < idx)) { dv = ov; idx = oi; }
+    }
+    if (lane == 0) { sv[warp] = dv; si[warp] = idx; }
+    __syncthreads();
+    if (warp == 0) {
+        dv = lane < nw ? sv[lane] : -DBL_MAX;
+        idx = lane < nw ? si[lane] : 0x7fffffff;
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_down_sync(0xffffffffu, dv, off);
+            int oi = __shfl_down_sync(0xffffffffu, idx, off);
+            if (ov > dv || (ov == dv && oi < idx)) { dv = ov; idx = oi; }
+        }
+        if (lane == 0) { sv[0] = dv; si[0] = idx; }
+    }
+    __syncthreads();
+    v = (TV)sv[0];
+    idx = si[0];
+    __syncthreads();
+}
+
+// ---- tracker post-processing: one block, one frame ------------------------------------------------------------
+// Arithmetic types follow the reference: sigmoid / ratio mix in float32 (torch + numpy float32), everything that touches the
+// float64 grids (box decode, penalties, window) in double.
+__global__ void __launch_bounds__(256) tracker_post_kernel(const float* __restrict__ cls, const float* __restrict__ cls_mem,
+                                                           const float* __restrict__ bbox, const double* __restrict__ window, int R,
+                                                           int instance_size, double tw, double th, float ratio, double penalty_k,
+                                                           double window_influence, double* __restrict__ result) {
+    const int cells = R * R;
+    double best = -DBL_MAX;
+    int best_i = 0x7fffffff;
+    const double half = (double)(instance_size / 2);
+    auto change = [](double r) { return fmax(r, 1.0 / r); };
+    auto szf = [](double w, double h) { double pad = (w + h) * 0.5; return sqrt((w + pad) * (h + pad)); };
+    const double sz_t = szf(tw, th);
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        const int r = i / R, c = i % R;
+        const float s0 = 1.f / (1.f + expf(-cls[i])), s1 = 1.f / (1.f + expf(-cls_mem[i]));
+        const float mix = ratio * s0 + (1.f - ratio) * s1;
+        const double gx = (double)(c - R / 2) * 8.0 + half, gy = (double)(r - R / 2) * 8.0 + half;
+        const double x1 = gx - (double)bbox[i], y1 = gy - (double)bbox[cells + i];
+        const double x2 = gx + (double)bbox[2 * cells + i], y2 = gy + (double)bbox[3 * cells + i];
+        const double s_c = change(szf(x2 - x1, y2 - y1) / sz_t);
+        const double r_c = change((tw / th) / ((x2 - x1) / (y2 - y1)));
+        const double pen = exp(-(r_c * s_c - 1.0) * penalty_k);
+        const double ps = pen * (double)mix * (1.0 - window_influence) + window[i] * window_influence;
+        if (ps > best) { best = ps; best_i = i; }
+    }
+    block_argmax(best, best_i);
+    if (threadIdx.x == 0) {
+        const int i = best_i, r = i / R, c = i % R;
+        const float s0 = 1.f / (1.f + expf(-cls[i])), s1 = 1.f / (1.f + expf(-cls_mem[i]));
+        const float mix = ratio * s0 + (1.f - ratio) * s1;
+        const double gx = (double)(c - R / 2) * 8.0 + half, gy = (double)(r - R / 2) * 8.0 + half;
+        const double x1 = gx - (double)bbox[i], y1 = gy - (double)bbox[cells + i];
+        const double x2 = gx + (double)bbox[2 * cells + i], y2 = gy + (double)bbox[3 * cells + i];
+        const double s_c = change(szf(x2 - x1, y2 - y1) / sz_t);
+        const double r_c = change((tw / th) / ((x2 - x1) / (y2 - y1)));
+        result[0] = r; result[1] = c; result[2] = x1; result[3] = y1; result[4] = x2; result[5] = y2;
+        result[6] = exp(-(r_c * s_c - 1.0) * penalty_k);
+        result[7] = (double)mix;
+    }
+}
+
+int launch_tracker_post(const float* cls, const float* cls_mem, const float* bbox, const double* window, int R, int instance_size,
+                        double tw, double th, float ratio, double penalty_k, double window_influence, double* result, cudaStream_t st) {
+    USOT_REQUIRE(R > 0 && R <= 64, "tracker postprocess: bad score size");
+    tracker_post_kernel<<<1, 256, 0, st>>>(cls, cls_mem, bbox, window, R, instance_size, tw, th, ratio, penalty_k, window_influence, result);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- cycle-memory glue: one block per memory sample --------------------------------------------------------------
+// res = r*off_cls + (1-r)*mem_cls ; idx = argmax ; box = grid(idx) -/+ off_bbox[:, idx] ; pool_box = map to PrPool coordinates
+__global__ void __launch_bounds__(256) cycle_glue_kernel(const float* __restrict__ off_cls, const float* __restrict__ mem_cls,
+                                                         const float* __restrict__ off_bbox, int R, int search_size, int sf_size,
+                                                         float ratio, float* __restrict__ pool_box, float* __restrict__ best_score,
+                                                         int* __restrict__ best_idx) {
+    const int s = blockIdx.x, cells = R * R;
+    const float* oc = off_cls + (size_t)s * cells;
+    const float* mc = mem_cls + (size_t)s * cells;
+    float best = -FLT_MAX;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        const float v = ratio * oc[i] + (1.f - ratio) * mc[i];
+        if (v > best) { best = v; bi = i; }
+    }
+    block_argmax(best, bi);
+    if (threadIdx.x == 0) {
+        const int r = bi / R, c = bi % R;
+        const float half = (float)(search_size / 2);
+        const float gx = (float)(c - R / 2) * 8.f + half, gy = (float)(r - R / 2) * 8.f + half;  // models.py:107-117
+        const float* bb = off_bbox + (size_t)s * 4 * cells;
+        float box[4] = {gx - bb[bi], gy - bb[cells + bi], gx + bb[2 * cells + bi], gy + bb[3 * cells + bi]};
+        // image_bbox_to_prpool_bbox, models.py:150-162
+        const double reg_min = (double)(0 - sf_size / 2) * 8.0 + (double)(search_size / 2);
+        const double reg_max = (double)(sf_size - 1 - sf_size / 2) * 8.0 + (double)(search_size / 2);
+        const double gap = (reg_max - reg_min) / (double)(2 * (sf_size / 2));
+        const float lo = (float)(reg_min - 2 * gap), hi = (float)(reg_max + 2 * gap), slope = (float)(1.0 / gap), rmin = (float)reg_min;
+        for (int k = 0; k < 4; ++k) pool_box[(size_t)s * 4 + k] = (fminf(fmaxf(box[k], lo), hi) - rmin) * slope;
+        if (best_score) best_score[s] = best;
+        if (best_idx) best_idx[s] = bi;
+    }
+}
+
+int launch_cycle_glue(const float* off_cls, const float* mem_cls, const float* off_bbox, int n, int R, int search_size, int sf_size,
+                      float ratio, float* pool_box, float* best_score, int* best_idx, cudaStream_t st) {
+    if (n == 0) return 0;
+    cycle_glue_kernel<<<n, 256, 0, st>>>(off_cls, mem_cls, off_bbox, R, search_size, sf_size, ratio, pool_box, best_score, best_idx);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- losses (single block, double accumulation) ---------------------------------------------------------------------
+static __device__ double block_sum(double v) {
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    v = (threadIdx.x < nw) ? sm[threadIdx.x] : 0.0;
+    if (warp == 0)
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) sm[0] = v;
+    __syncthreads();
+    v = sm[0];
+    __syncthreads();
+    return v;
+}
+
+// 0.5 * mean_{label==1} BCEWithLogits(pred,1) + 0.5 * mean_{label==0} BCEWithLogits(pred,0); a class with exactly one member
+// contributes 0 (models.py:43-44 quirk), an empty class contributes NaN (mean of an empty tensor).
+__global__ void __launch_bounds__(1024) bce_kernel(const float* __restrict__ pred, const float* __restrict__ label, int count,
+                                                   float* __restrict__ out) {
+    double sp = 0, sn = 0, cp = 0, cn = 0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const float x = pred[i], y = label[i];
+        const float sl = log1pf(expf(-fabsf(x)));
+        if (y == 1.f) { sp += (double)(fmaxf(-x, 0.f) + sl); cp += 1; }
+        else if (y == 0.f) { sn += (double)(fmaxf(x, 0.f) + sl); cn += 1; }
+    }
+    sp = block_sum(sp); sn = block_sum(sn); cp = block_sum(cp); cn = block_sum(cn);
+    if (threadIdx.x == 0) {
+        const double lp = cp == 1 ? 0.0 : sp / cp, ln = cn == 1 ? 0.0 : sn / cn;
+        *out = (float)(lp * 0.5 + ln * 0.5);
+    }
+}
+
+// bbox_pred (n,4,R,R) nchw ; reg_target (n,R,R,4) ; reg_weight (n,R,R)
+__global__ void __launch_bounds__(1024) iou_kernel(const float* __restrict__ bbox, const float* __restrict__ target,
+                                                   const float* __restrict__ weight, int n, int cells, float* __restrict__ out) {
+    double s = 0, cnt = 0;
+    for (int i = threadIdx.x; i < n * cells; i += blockDim.x) {
+        if (!(weight[i] > 0.f)) continue;
+        const int b = i / cells, c = i % cells;
+        const float* p = bbox + (size_t)b * 4 * cells + c;
+        const float pl = p[0], pt = p[cells], pr = p[2 * cells], pb = p[3 * cells];
+        const float* t = target + (size_t)i * 4;
+        const float tl = t[0], tt = t[1], tr = t[2], tb = t[3];
+        const float ta = (tl + tr) * (tt + tb), pa = (pl + pr) * (pt + pb);
+        const float wi = fminf(pl, tl) + fminf(pr, tr), hi = fminf(pb, tb) + fminf(pt, tt);
+        const float ai = wi * hi, au = ta + pa - ai;
+        s += (double)(-logf((ai + 1.0f) / (au + 1.0f)));
+        cnt += 1;
+    }
+    s = block_sum(s); cnt = block_sum(cnt);
+    if (threadIdx.x == 0) *out = (float)(s / cnt);
+}
+
+int launch_bce(const float* pred, const float* label, int count, float* out, cudaStream_t st) {
+    bce_kernel<<<1, 1024, 0, st>>>(pred, label, count, out);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_iou(const float* bbox, const float* target, const float* weight, int n, int cells, float* out, cudaStream_t st) {
+    iou_kernel<<<1, 1024, 0, st>>>(bbox, target, weight, n, cells, out);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace usot

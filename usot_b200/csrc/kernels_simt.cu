@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(64) groupdw_kernel(GroupDWArgs a, int nstrips,
     const int n = bid / cblocks;
     const int c = cblk * 64 + tid;
     const int rep = a.n_out / a.nx;
-    const int zb = (a.nz == a.n_out) ? n : 0;
+    const int zb = n / (a.n_out / a.nz);  // nz == n_out: own kernel; nz == 1: broadcast; otherwise each kernel serves n_out/nz samples
     const int xb = n / rep;
     const int C = a.C, F = a.F, R = F - 6;
     for (int t = 0; t < 25; ++t) zs[t][tid] = w0 * __ldg(a.z11 + ((size_t)zb * 25 + t) * C + c);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(64) groupdw_kernel(GroupDWArgs a, int nstrips,
 int launch_groupdw(const GroupDWArgs& a, cudaStream_t st) {
     USOT_REQUIRE(a.C % 64 == 0, "groupdw needs C % 64 == 0");
     USOT_REQUIRE(a.nx > 0 && a.n_out % a.nx == 0, "groupdw: n_out must be a multiple of nx");
-    USOT_REQUIRE(a.nz == a.n_out || a.nz == 1, "groupdw: kernel batch must be 1 or n_out");
+    USOT_REQUIRE(a.nz > 0 && a.n_out % a.nz == 0, "groupdw: n_out must be a multiple of the kernel batch");
     USOT_REQUIRE(a.F >= 7, "groupdw: feature size too small");
     float w[3];
     USOT_CUDA_OK(cudaMemcpyAsync(w, a.dw_weight, sizeof(w), cudaMemcpyDeviceToHost, st));
@@ -396,6 +396,7 @@ int launch_groupdw(const GroupDWArgs& a, cudaStream_t st) {
 int g_groupdw_strips = 3;  // tunable (usot_set_tunable("groupdw_strips", 2|3))
 
 int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
+    USOT_REQUIRE(a.nx > 0 && a.nz > 0 && a.n_out % a.nx == 0 && a.n_out % a.nz == 0, "groupdw: n_out must be a multiple of both batches");
     const int R = a.F - 6;
     const int nstrips = (g_groupdw_strips == 2 && R <= 28) ? 2 : (R + 8) / 9;
     const int sw = (R + nstrips - 1) / nstrips;

@@ -121,3 +121,24 @@ class Engine:
                 _lib.check(_lib.load().usot_engine_extract_memory_feature(self._h, None, n, 0, _lib.ptr(xf), xf.shape[1], _lib.ptr(bbox),
                                                                           _lib.ptr(out), _stream(xf)))
         return out
+
+    def forward_train_heads(self, zf, xf, xf_mem, m, label, reg_target, reg_weight, search_bbox, cls_ratio, want_aux=False):
+        """Head part of USOT_.forward (lib/models/models.py:223-295).  zf (n,7,7,256), xf (n,F,F,256), xf_mem (n*m,F,F,256) NHWC.
+        Returns losses (3,) = [cls_loss, cls_memory_loss, reg_loss] on the device (+ backward_map, pool_box if want_aux)."""
+        n, f = xf.shape[0], xf.shape[1]
+        r = f - 6
+        dev = self.device
+        f32 = lambda t: None if t is None else t.to(dev, torch.float32).contiguous()
+        label, reg_target, reg_weight, search_bbox = f32(label), f32(reg_target), f32(reg_weight), f32(search_bbox)
+        assert zf.is_contiguous() and xf.is_contiguous() and tuple(zf.shape) == (n, 7, 7, C_FEAT)
+        assert label.numel() == n * r * r and reg_target.numel() == n * r * r * 4 and reg_weight.numel() == n * r * r
+        if m > 0:
+            assert xf_mem.is_contiguous() and tuple(xf_mem.shape) == (n * m, f, f, C_FEAT) and tuple(search_bbox.shape) == (n, 4)
+        losses = self._empty(3)
+        back = self._empty(n, 1, r, r) if want_aux else None
+        pbox = self._empty(max(n * m, 1), 4) if want_aux else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().usot_engine_forward_train(self._h, _lib.ptr(zf), _lib.ptr(xf), _lib.ptr(xf_mem), n, m, f, _lib.ptr(label),
+                                                             _lib.ptr(reg_target), _lib.ptr(reg_weight), _lib.ptr(search_bbox),
+                                                             float(cls_ratio), _lib.ptr(losses), _lib.ptr(back), _lib.ptr(pbox), _stream(xf)))
+        return (losses, back, pbox) if want_aux else losses

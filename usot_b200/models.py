@@ -190,6 +190,30 @@ class USOT_(nn.Module):
             out = eng.extract_memory_feature(xf=ops.as_nhwc(xf.float()), search_bbox=search_bbox)
         return ops.nhwc_view(out)
 
+    def forward(self, template, search, label=None, reg_target=None, reg_weight=None, template_bbox=None, search_memory=None,
+                search_bbox=None, cls_ratio=0.40, zf_exchange=None):
+        """Training forward of lib/models/models.py:208-295 with eval-mode BN (running statistics; the reference's train()-mode
+        batch statistics are per-replica and shard-size dependent).  Returns the reference's triple
+        (cls_loss, cls_memory_loss or None, reg_loss) as 0-d CUDA tensors (forward only: no autograd graph).
+
+        ``zf_exchange``: optional callable ``zf_local (n,7,7,256) -> (handle_with_wait, zf_rows_for_this_rank)`` used by
+        usot_b200.dist to all-gather the template features across ranks while the search / memory backbones run."""
+        eng = self._engine(search.device)
+        if self.pr_pool and template_bbox is None:
+            raise ValueError("pr_pool=True needs template_bbox")
+        zf, _ = eng.template(template, template_bbox if self.pr_pool else None)
+        pending = zf_exchange(zf) if zf_exchange is not None else None
+        xf = eng.backbone_neck(search)
+        m, xf_mem = 0, None
+        if search_memory is not None:
+            batch, m, cx, hx, wx = search_memory.shape
+            assert batch == search.shape[0]
+            xf_mem = eng.backbone_neck(search_memory.reshape(-1, cx, hx, wx))
+        if pending is not None:
+            zf = pending()
+        losses = eng.forward_train_heads(zf, xf, xf_mem, m, label, reg_target, reg_weight, search_bbox, cls_ratio)
+        return losses[0], (losses[1] if m > 0 else None), losses[2]
+
     def backbone_neck(self, x):
         """feature_extractor + neck (lib/models/models.py:181-184): (N,3,S,S) -> (N,256,F,F)."""
         return ops.nhwc_view(self._engine(x.device).backbone_neck(x))
