@@ -10,6 +10,9 @@ CASES = {  # name: (cin, cout, k, stride, pad, dil, h, residual, relu)
     "l1_conv3": (64, 256, 1, 1, 0, 1, 63, True, True),
     "l3_conv2": (256, 256, 3, 1, 2, 2, 31, False, True),
     "l3_conv1": (1024, 256, 1, 1, 0, 1, 31, False, True),
+    "l3_conv3_nores": (256, 1024, 1, 1, 0, 1, 31, False, True),
+    "l1_conv3_nores": (64, 256, 1, 1, 0, 1, 63, False, True),
+    "tower": (256, 256, 3, 1, 1, 1, 25, False, True),
 }
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 prec = sys.argv[3] if len(sys.argv) > 3 else "fp16x3"

@@ -83,6 +83,15 @@ static __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorM
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+static __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+static __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+static __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 static __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -127,7 +136,9 @@ static __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wa
 // =============================================================================================
 // Kernel
 // =============================================================================================
-constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 256;
+constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_EPI_GROUPS = 2;                          // epilogue warp groups (4 warps each, one per TMEM lane quarter)
+constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;     // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4..: epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB per plane per stage
 
 template <int BN, bool SPLIT>
@@ -135,8 +146,10 @@ struct TcCfg {
     static constexpr int PLANES = SPLIT ? 2 : 1;
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = PLANES * (TC_A_BYTES + B_BYTES);
-    static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;  // barriers, scale/shift staging, alignment slack
-    static constexpr int STAGES_RAW = (SMEM_BUDGET - 2 * BN * 4) / STAGE_BYTES;
+    static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;  // alignment slack + barriers
+    static constexpr bool TMA_OUT = !(SPLIT && BN == 256);  // (the 2-stage 96 KiB ring of that config leaves no room for staging)
+    static constexpr int OUT_STAGE_BYTES = TMA_OUT ? 2 * 2 * TC_BM * 64 : 0;  // 2 buffers x 2 planes x 128 rows x 64 B
+    static constexpr int STAGES_RAW = (SMEM_BUDGET - 2 * BN * 4 - OUT_STAGE_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
     // Split mode keeps TWO accumulators per tile when TMEM allows it (BN <= 128): `main` receives only the hi*hi products and
     // `cross` the 2^-11-times smaller hi*lo + lo*hi products.  The tensor core truncates on every accumulate, so the error of
@@ -145,23 +158,30 @@ struct TcCfg {
     static constexpr bool XACC = SPLIT && BN <= 128;
     static constexpr int ACC_COLS = XACC ? 2 * BN : BN;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double buffered; power of two for BN in {64,128,256}
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 4 + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int BUF_BYTES = 2 * TC_BM * 64;  // one staging buffer: 2 planes x 128 rows x 64 B
+    static constexpr int MISC_BYTES = 2 * BN * 4 + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int smem_bytes(int stages, int nbuf) { return stages * STAGE_BYTES + TC_EPI_GROUPS * nbuf * BUF_BYTES * (TMA_OUT ? 1 : 0) + MISC_BYTES; }
+    // ring depth when every epilogue group rotates 3 staging buffers (TMA-prefetched residual)
+    static constexpr int STAGES_RES = (227 * 1024 - MISC_BYTES - TC_EPI_GROUPS * 3 * BUF_BYTES) / STAGE_BYTES;
 };
 
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, SPLIT>;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = p.stages;
+    constexpr int MAXST = 6;  // barrier slots
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned operand ring (required by the 128B swizzle atoms)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    float* s_scale = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* s_out = smem_gen + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
+    float* s_scale = reinterpret_cast<float*>(s_out + (Cfg::TMA_OUT ? TC_EPI_GROUPS * p.nbuf * Cfg::BUF_BYTES : 0));
     float* s_shift = s_scale + BN;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
-    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES,
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * MAXST, bar_tfull = bar_empty + 8 * MAXST,
                    bar_tempty = bar_tfull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const uint32_t bar_res = bar_tempty + 16;  // [TC_EPI_GROUPS][3] residual chunk landed in staging buffer b of group g
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 4 + 3 * TC_EPI_GROUPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nK = p.taps * p.cin_chunks;
@@ -173,7 +193,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * TC_EPI_GROUPS); }
+        for (int s = 0; s < 3 * TC_EPI_GROUPS; ++s) mbar_init(bar_res + 8 * s, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -261,9 +282,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
-        const int ew = warp - 4;              // TMEM lane quarter == warp % 4
+        // Two groups of 4 warps; warp w reads TMEM lane quarter w % 4; group g owns the 32-column chunks with (chunk % 2 == g)
+        // and one store-staging buffer, so the groups never synchronise with each other inside a tile.
+        const int ew = warp & 3;              // TMEM lane quarter == warp % 4
+        const int eg = (warp - 4) >> 2;       // epilogue group
         const int row = ew * 32 + lane;       // tile row == TMEM lane
-        const int et = threadIdx.x - 128;     // 0..127
+        const int et = (threadIdx.x - 128) & 127;  // 0..127 inside the group
+        const int eall = threadIdx.x - 128;        // 0..255 over both groups
+        const uint32_t s_out_u32 = smem_u32(s_out);
+        uint32_t gc = 0;                      // running chunk counter: selects the store-staging buffer
+        if (eall == 0 && p.tma_store) { tma_prefetch_desc(&p.o[0]); tma_prefetch_desc(&p.o[1]); }
+        if (eall == 32 && p.tma_res) { tma_prefetch_desc(&p.r[0]); tma_prefetch_desc(&p.r[1]); }
+        // TMA-prefetched residual: the group's leader requests chunk j+1 into staging buffer (j+1) % 3 while chunk j is being
+        // processed; that buffer was last used by chunk j-2, whose bulk store has finished reading when wait_group.read 1 returns.
+        auto issue_res = [&](int t, int c0, uint32_t b) {
+            const int nb_ = t % p.n_tiles_n;
+            int mt_ = t / p.n_tiles_n;
+            const int tw_ = mt_ % p.tiles_w; mt_ /= p.tiles_w;
+            const int th_ = mt_ % p.tiles_h;
+            const int img_ = mt_ / p.tiles_h;
+            const uint32_t dst = s_out_u32 + (eg * p.nbuf + b) * Cfg::BUF_BYTES, rb = bar_res + 8 * (eg * 3 + b);
+            mbar_expect_tx(rb, 2u * p.bw * p.bh * 64u);
+            tma_load_4d(dst, &p.r[0], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
+            tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
+        };
+        if (p.tma_res && et == 0 && (int)blockIdx.x < p.num_tiles && eg * 32 < BN) issue_res(blockIdx.x, eg * 32, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int nb = tile % p.n_tiles_n;
@@ -277,37 +320,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
             const int n0 = nb * BN;
             // stage this tile's scale/shift (previous tile's readers are past the barrier at the end of the loop body)
-            for (int i = et; i < BN; i += 128) { s_scale[i] = __ldg(p.scale + n0 + i); s_shift[i] = __ldg(p.shift + n0 + i); }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = eall; i < BN; i += 128 * TC_EPI_GROUPS) { s_scale[i] = __ldg(p.scale + n0 + i); s_shift[i] = __ldg(p.shift + n0 + i); }
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const size_t off0 = pix * p.cout + n0;
+            const int cfirst = eg * 32, cstep = 32 * TC_EPI_GROUPS;
             // Residual loads are software-pipelined one 32-column chunk ahead and the first chunk is requested BEFORE waiting
             // for the accumulator, so their DRAM latency hides behind the MMAs / the previous chunk's math.
             uint4 rh[4], rl[4];
-            const bool has_res = p.res_hi != nullptr && valid;
+            const bool has_res = p.res_hi != nullptr && valid && !p.tma_res;
             if (has_res) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0) + q);
-                    rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0) + q);
+                    rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0 + cfirst) + q);
+                    rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + cfirst) + q);
                 }
             }
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = cfirst; c0 < BN; c0 += cstep) {
+                if (p.tma_res && et == 0) {
+                    int nc0 = c0 + cstep, ntile = tile;
+                    if (nc0 >= BN) { nc0 = cfirst; ntile = tile + gridDim.x; }
+                    if (ntile < p.num_tiles) {
+                        bulk_wait_read<1>();
+                        issue_res(ntile, nc0, (gc + 1) % 3);
+                    }
+                }
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
                 uint4 ch[4], cl[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { ch[q] = rh[q]; cl[q] = rl[q]; }
-                if (has_res && c0 + 32 < BN) {
+                if (has_res && c0 + cstep < BN) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0 + c0 + 32) + q);
-                        rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + c0 + 32) + q);
+                        rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0 + c0 + cstep) + q);
+                        rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + c0 + cstep) + q);
                     }
                 }
                 if (Cfg::XACC) {
@@ -319,7 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 } else {
                     tmem_ld_wait();
                 }
-                if (valid) {
+                if (valid || p.tma_store) {
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
@@ -337,11 +389,67 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             }
                         }
                     }
-                    if (p.relu) {
+                    if (p.relu && !p.tma_res) {  // (with a TMA residual the add + ReLU happen after the chunk has landed, below)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
                     }
-                    if (p.out_hi) {
+                    if (p.tma_store) {
+                        // Stage this 32-column chunk (128 rows x 64 B per plane) in the 64B-swizzled layout of the output tensor
+                        // map and let ONE thread issue the two bulk tensor stores: no per-thread global stores, rows beyond the
+                        // image / patch are clipped by the TMA unit.  Two staging buffers alternate; a buffer is reused only after
+                        // the stores issued from it have finished reading shared memory.
+                        const uint32_t buf = eg * p.nbuf + (p.tma_res ? gc % 3 : 0);
+                        uint8_t* rp = s_out + buf * Cfg::BUF_BYTES + row * 64;
+                        const int sw = (row >> 1) & 3;
+                        if (p.tma_res) {
+                            mbar_wait(bar_res + 8 * (eg * 3 + gc % 3), (gc / 3) & 1);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 a = *reinterpret_cast<const uint4*>(rp + ((q ^ sw) << 4));
+                                const uint4 b = *reinterpret_cast<const uint4*>(rp + TC_BM * 64 + ((q ^ sw) << 4));
+                                const __half2* ah = reinterpret_cast<const __half2*>(&a);
+                                const __half2* bl = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 fa = __half22float2(ah[e]), fb = __half22float2(bl[e]);
+                                    y[q * 8 + 2 * e] += fa.x + fb.x;
+                                    y[q * 8 + 2 * e + 1] += fa.y + fb.y;
+                                }
+                            }
+                            if (p.relu) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+                            }
+                        } else {
+                            if (et == 0) bulk_wait_read<0>();
+                            asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 a, b;
+                            __half2* ah = reinterpret_cast<__half2*>(&a);
+                            __half2* bl = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float f0 = y[q * 8 + 2 * e], f1 = y[q * 8 + 2 * e + 1];
+                                const __half2 h = __floats2half2_rn(f0, f1);
+                                const float2 hf = __half22float2(h);
+                                ah[e] = h;
+                                bl[e] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+                            }
+                            *reinterpret_cast<uint4*>(rp + ((q ^ sw) << 4)) = a;
+                            *reinterpret_cast<uint4*>(rp + TC_BM * 64 + ((q ^ sw) << 4)) = b;
+                        }
+                        fence_proxy_async_smem();
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
+                        if (et == 0) {
+                            const uint32_t src = s_out_u32 + buf * Cfg::BUF_BYTES;
+                            tma_store_4d(&p.o[0], src, n0 + c0, tw * p.bw, th * p.bh, img);
+                            tma_store_4d(&p.o[1], src + TC_BM * 64, n0 + c0, tw * p.bw, th * p.bh, img);
+                            bulk_commit();
+                        }
+                        ++gc;
+                    } else if (p.out_hi) {
                         uint4* oh4 = reinterpret_cast<uint4*>(p.out_hi + off);
                         uint4* ol4 = reinterpret_cast<uint4*>(p.out_lo + off);
 #pragma unroll
@@ -361,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             ol4[q] = b;
                         }
                     }
-                    if (p.out_f32) {
+                    if (p.out_f32 && valid) {
                         float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) o[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
@@ -371,9 +479,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // scale/shift staging may be overwritten next iteration
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");  // scale/shift staging may be overwritten next iteration
         }
     }
+    if (threadIdx.x >= 128 && ((threadIdx.x - 128) & 127) == 0 && p.tma_store) bulk_wait_read<0>();  // staging must outlive the stores' reads
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -400,12 +509,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     USOT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("usot_b200: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -428,20 +537,28 @@ static void choose_tiling(int ho, int wo, int* tiles_w, int* bw, int* bh) {
 }
 
 template <int BN, bool SPLIT>
-static int launch_cfg(const TcParams& p, int grid, cudaStream_t st) {
+static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     using Cfg = TcCfg<BN, SPLIT>;
     static_assert(Cfg::STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
     static bool attr = false;
     if (!attr) {
-        USOT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        USOT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    conv_tc_kernel<BN, SPLIT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p);
+    if (!Cfg::TMA_OUT) { p.tma_store = 0; p.tma_res = 0; }
+    if (p.tma_res && Cfg::STAGES_RES < 2) p.tma_res = 0;
+    p.nbuf = p.tma_res ? 3 : 1;
+    p.stages = p.tma_res ? (Cfg::STAGES_RES < Cfg::STAGES ? Cfg::STAGES_RES : Cfg::STAGES) : Cfg::STAGES;
+    const int smem = Cfg::smem_bytes(p.stages, p.nbuf);
+    USOT_REQUIRE(smem <= 227 * 1024, "conv_tc: shared memory plan exceeds 227 KiB");
+    conv_tc_kernel<BN, SPLIT><<<grid, TC_THREADS, smem, st>>>(p);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
+int g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
+int g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
 int g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cross-term accumulator (accuracy); 256 trades it for reuse
 
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st) {
@@ -498,6 +615,20 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         cuuint64_t wd[2] = {(cuuint64_t)w.K, (cuuint64_t)g.cout}, ws[1] = {(cuuint64_t)w.K * 2};
         cuuint32_t wb[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
         if (int rc = encode_map(&p.b[pl], pl == 0 ? w.hi : w.lo, 2, wd, ws, wb)) return rc;
+    }
+
+    p.tma_store = (g_tc_tma_store && p.out_hi && !(split && bn == 256)) ? 1 : 0;
+    if (p.tma_store) {
+        cuuint64_t od[4] = {(cuuint64_t)g.cout, (cuuint64_t)g.wo, (cuuint64_t)g.ho, (cuuint64_t)g.n};
+        cuuint64_t os[3] = {(cuuint64_t)g.cout * 2, (cuuint64_t)g.wo * g.cout * 2, (cuuint64_t)g.ho * g.wo * g.cout * 2};
+        cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+        if (int rc = encode_map(&p.o[0], p.out_hi, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+        if (int rc = encode_map(&p.o[1], p.out_lo, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+        if (p.res_hi && g_tc_tma_res) {
+            p.tma_res = 1;
+            if (int rc = encode_map(&p.r[0], p.res_hi, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+            if (int rc = encode_map(&p.r[1], p.res_lo, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+        }
     }
 
     static int num_sms = 0;

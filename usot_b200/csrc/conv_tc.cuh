@@ -9,6 +9,12 @@ namespace usot {
 struct TcParams {
     CUtensorMap a[2][4];  // activation maps [plane hi/lo][stride-2 parity]
     CUtensorMap b[2];     // weight maps [plane]
+    CUtensorMap o[2];     // output maps [plane] for the TMA-store epilogue (box {32 ch, bw, bh, 1}, 64B swizzle)
+    CUtensorMap r[2];     // residual maps [plane], same box/swizzle as o[]: the residual chunk is TMA-loaded INTO the staging buffer
+    int tma_res;          // 1: residual arrives by TMA (requires tma_store)
+    int stages;           // operand ring depth used by this launch (<= the config's maximum)
+    int nbuf;             // staging buffers per epilogue group: 1, or 3 when the residual is prefetched by TMA
+    int tma_store;        // 1: split-fp16 outputs leave through smem staging + cp.async.bulk.tensor stores
     int n_img, ho, wo, cout;
     int bw, bh, tiles_w, tiles_h;  // spatial patch of one M tile (bw*bh <= 128 rows)
     int n_tiles_n, num_tiles;
@@ -46,7 +52,7 @@ struct TcEpilogue {
     int relu;
 };
 
-extern int g_tc_bn_max, g_tc_split_bn_max;
+extern int g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res;
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st);
 int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
 void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,

@@ -12,6 +12,7 @@
 #include "../../include/usot_b200.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -612,6 +613,8 @@ int usot_profile_read(int fam, double* out) {
 int usot_set_tunable(const char* name, int value) {
     USOT_REQUIRE(name, "null name");
     if (!strcmp(name, "tc_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_bn_max must be 64, 128 or 256"); g_tc_bn_max = value; return 0; }
+    if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
+    if (!strcmp(name, "tc_tma_store")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_store must be 0 or 1"); g_tc_tma_store = value; return 0; }
     if (!strcmp(name, "tc_split_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_split_bn_max must be 64, 128 or 256"); g_tc_split_bn_max = value; return 0; }
     if (!strcmp(name, "groupdw_strips")) { USOT_REQUIRE(value == 2 || value == 3, "groupdw_strips must be 2 or 3"); g_groupdw_strips = value; return 0; }
     USOT_REQUIRE(false, "unknown tunable");
@@ -662,7 +665,7 @@ int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float*
     USOT_CUDA_OK(cudaStreamSynchronize(st));
     std::vector<__half> whi, wlo;
     pack_tc_weights_host(hw.data(), K, cout, hs.data(), whi, wlo, scale_tc);
-    __half *d_whi = nullptr, *d_wlo = nullptr, *d_ihi = nullptr, *d_ilo = nullptr, *d_rhi = nullptr, *d_rlo = nullptr;
+    __half *d_whi = nullptr, *d_wlo = nullptr, *d_ihi = nullptr, *d_ilo = nullptr, *d_rhi = nullptr, *d_rlo = nullptr, *d_ohi = nullptr, *d_olo = nullptr;
     float* d_scale = nullptr;
     int rc = 0;
     auto fail = [&](int code) { rc = code; };
@@ -680,10 +683,15 @@ int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float*
         TcTensor ti{d_ihi, split ? d_ilo : nullptr};
         TcWeights tw{d_whi, split ? d_wlo : nullptr, d_scale, K};
         TcEpilogue ep{shift, d_rhi, d_rlo, nullptr, nullptr, out, relu};
+        if (const char* dbg = getenv("USOT_DEBUG_SPLIT_OUT")) {  // profiling aid: exercise the split-fp16 output path as the engine does
+            if (cudaMalloc(&d_ohi, n_out * 2) || cudaMalloc(&d_olo, n_out * 2)) { set_error("usot_conv2d_nhwc: cudaMalloc failed"); fail(1); break; }
+            ep.out_hi = d_ohi; ep.out_lo = d_olo;
+            if (dbg[0] == '2') ep.out_f32 = nullptr;  // split output only
+        }
         if ((rc = launch_conv_tc(ti, g, tw, ep, split, st))) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("usot_conv2d_nhwc: ") + cudaGetErrorString(cudaGetLastError())); fail(1); }
     } while (0);
-    cudaFree(d_whi); cudaFree(d_wlo); cudaFree(d_scale); cudaFree(d_ihi); cudaFree(d_ilo); cudaFree(d_rhi); cudaFree(d_rlo);
+    cudaFree(d_whi); cudaFree(d_wlo); cudaFree(d_scale); cudaFree(d_ihi); cudaFree(d_ilo); cudaFree(d_rhi); cudaFree(d_rlo); cudaFree(d_ohi); cudaFree(d_olo);
     return rc;
 }
 
