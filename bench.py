@@ -188,15 +188,36 @@ def main():
     def step_resident():
         net.track(x_dev)
 
-    x_stage = torch.empty_like(x_dev)
+    # End-to-end leg: every step copies ITS 200 MB of crops from pinned host memory and reads its score/box maps back.  The
+    # input copy of step i+1 runs on a copy stream into the other staging buffer while step i computes (what a caller of the
+    # public API does to keep PCIe off the critical path); all copies are inside the timed region.
+    x_stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     out_host = [torch.empty((args.batch, 1, 25, 25)).pin_memory(), torch.empty((args.batch, 4, 25, 25)).pin_memory()]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0, "primed": False}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])  # the compute that last read this buffer is done
+            x_stage[slot].copy_(x_host, non_blocking=True)
+            ready[slot].record(copy_stream)
 
     def step_e2e():
-        x_stage.copy_(x_host, non_blocking=True)
-        cls, bbox, _, _ = net.track(x_stage)
+        cur = state["i"] & 1
+        if not state["primed"]:
+            consumed[0].record(); consumed[1].record()
+            prefetch(cur)
+            state["primed"] = True
+        prefetch(cur ^ 1)  # next step's input, overlapped with this step's compute
+        torch.cuda.current_stream().wait_event(ready[cur])
+        cls, bbox, _, _ = net.track(x_stage[cur])
+        consumed[cur].record()
         out_host[0].copy_(cls, non_blocking=True)
         out_host[1].copy_(bbox, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the maps every step
+        state["i"] += 1
 
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):

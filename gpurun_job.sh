@@ -1,16 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_model.py -q -m gpu -x -k "memory or config1 or independence" 2>&1 | tail -3
-run() {
-  ncu --metrics gpu__time_duration.sum --clock-control none -k regex:conv_tc_kernel --csv --log-file gpurun_out/v_$1.csv env $2 python tools/conv_cases.py $4 256 $3 > /dev/null 2>&1
-  python - <<PY
-import csv
-rows=[r for r in csv.reader(open("gpurun_out/v_$1.csv")) if len(r)>10 and r[0].isdigit()]
-print("$1", "$2", "$3", "$4", [round(float(r[-1])/1e3,1) for r in rows])
-PY
-}
-C=l3_conv3,l3_conv3_nores,l1_conv3,l1_conv3_nores
-run splitout_x3 "USOT_DEBUG_SPLIT_OUT=2" fp16x3 $C
-run splitout_16 "USOT_DEBUG_SPLIT_OUT=2" fp16 $C
+timeout 600 python -m pytest tests/test_gpu_model.py -q -m gpu -x -s -k "memory or config1 or independence or fresh" 2>&1 | grep -oE "(damp025|raw) [a-z0-9]+ fp16x3 \{[^}]*\}|backbone fresh [a-z0-9]+ [0-9.e-]+|[0-9]+ (passed|failed).*|Error.*|error.*" | tail -14
 for prec in fp16x3 fp16; do
 python bench.py --steps 10 --warmup 3 --precision $prec --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_$prec.json
 python - <<PY

@@ -57,6 +57,9 @@ struct Epilogue {
 // ---- launchers (kernels_simt.cu) -----------------------------------------------------------
 int launch_stem(const float* x_nchw, int n, int s, const float* w_packed /*[147][64]*/, const float* scale,
                 const float* shift, float* out_nhwc /*[n][ho][ho][64]*/, cudaStream_t st);
+// tensor-core stem (stem_tc.cu): w_img = packed shared-memory image of the weight tile, see pack_stem_tc_host
+int launch_stem_tc(const float* x_nchw, int n, int s, const void* w_img, const float* scale_tc, const float* shift, float* out_nhwc,
+                   bool split, cudaStream_t st);
 int launch_maxpool3x3s2p1(const float* in, int n, int h, int w, int c, float* out, cudaStream_t st);
 int launch_conv_simt(const float* in, const ConvGeom& g, const float* w_kn /*[kh*kw*cin][cout]*/, const Epilogue& ep,
                      float* out, cudaStream_t st);

@@ -58,4 +58,6 @@ int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaS
 void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,
                           std::vector<float>& scale_out);
 
+void pack_stem_tc_host(const float* w_oihw, const float* scale_in, std::vector<uint8_t>& img, std::vector<float>& scale_out);
+
 }  // namespace usot

@@ -36,6 +36,7 @@ struct Profiler {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
 };
 static Profiler g_prof;
+static int g_stem_tc = 1;  // tunable "stem_tc": 1 = tensor-core stem in the tcgen05 precision modes, 0 = CUDA-core stem
 struct Scope {
     int fam; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     Scope(int fam_, cudaStream_t st_, double flops = 0, double bytes = 0) : fam(fam_), st(st_) {
@@ -159,6 +160,8 @@ struct usot_engine {
     std::vector<void*> owned;  // device allocations holding weights
     int64_t weight_bytes = 0;
     float *stem_w = nullptr, *stem_scale = nullptr, *stem_shift = nullptr;
+    void* stem_tc_img = nullptr;      // tensor-core stem: packed weight tile + scale*2^-e
+    float* stem_tc_scale = nullptr;
     PredW bbox_pred, cls_pred, cls_memory_pred;
     float dw_cls[3] = {0, 0, 0}, dw_reg[3] = {0, 0, 0};  // softmax(GroupDW.weight)
     float *adjust = nullptr, *bias4 = nullptr;
@@ -250,6 +253,16 @@ static int finalize_impl(usot_engine* e) {
             for (int k = 0; k < 147; ++k) packed[(size_t)k * 64 + co] = (*w)[(size_t)co * 147 + k];
         if (int rc = fold_bn(e, "features.features.conv1", "features.features.bn1", 64, false, scale, shift)) return rc;
         if (upload(e, packed, &e->stem_w) || upload(e, scale, &e->stem_scale) || upload(e, shift, &e->stem_shift)) return 1;
+        if (e->precision != USOT_PREC_FP32_SIMT) {
+            std::vector<uint8_t> img;
+            std::vector<float> scale_tc;
+            pack_stem_tc_host(w->data(), scale.data(), img, scale_tc);
+            std::vector<float> as_f(img.size() / 4);
+            memcpy(as_f.data(), img.data(), img.size());
+            float* d = nullptr;
+            if (upload(e, as_f, &d) || upload(e, scale_tc, &e->stem_tc_scale)) return 1;
+            e->stem_tc_img = d;
+        }
     }
     for (const ConvSpec& s : build_specs()) {
         const int K = s.k * s.k * s.cin;
@@ -401,7 +414,8 @@ static int backbone_neck(Ctx& c, const float* x, int n, int S, float* xf_dst, T*
     float* a0 = ar.f((size_t)n * h1 * h1 * 64);
     if (!ar.plan) {
         Scope sc(FAM_STEM, c.st, 2.0 * n * h1 * h1 * 64.0 * 147);
-        RUN(launch_stem(x, n, S, e->stem_w, e->stem_scale, e->stem_shift, a0, c.st));
+        if (c.tc() && g_stem_tc) RUN(launch_stem_tc(x, n, S, e->stem_tc_img, e->stem_tc_scale, e->stem_shift, a0, c.split(), c.st));
+        else RUN(launch_stem(x, n, S, e->stem_w, e->stem_scale, e->stem_shift, a0, c.st));
     }
     T cur;
     cur.n = n; cur.h = cur.w = h2; cur.c = 64;
@@ -613,6 +627,7 @@ int usot_profile_read(int fam, double* out) {
 int usot_set_tunable(const char* name, int value) {
     USOT_REQUIRE(name, "null name");
     if (!strcmp(name, "tc_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_bn_max must be 64, 128 or 256"); g_tc_bn_max = value; return 0; }
+    if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
     if (!strcmp(name, "tc_tma_store")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_store must be 0 or 1"); g_tc_tma_store = value; return 0; }
     if (!strcmp(name, "tc_split_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_split_bn_max must be 64, 128 or 256"); g_tc_split_bn_max = value; return 0; }
