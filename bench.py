@@ -249,6 +249,12 @@ def main():
         conv_tflops = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
         xc_gbs = xc["bytes"] / (xc["ms"] / 1e3) / 1e9 if xc["ms"] > 0 else 0.0
         step_ms_prof = sum(f["ms"] for f in prof.values()) / nprof
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f)
+        mma_per_flop = {"fp32": 0, "fp16x3": 3, "fp16": 1}[args.precision]
         line = {
             "metric": "search_crops_per_sec", "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -258,13 +264,20 @@ def main():
                     "d2h_bytes_per_step": sum(t.numel() * 4 for t in out_host), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "dense conv family (conv_simt / conv_tc), all launches of one step", "bound": "tensor",
-                         "achieved": conv_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": conv_tflops / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] + ", bf16 dense sustained",
+            "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv), all launches of one step" if mma_per_flop else "conv_simt_kernel, all launches of one step",
+                         "bound": "tensor", "achieved": conv_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": conv_tflops / pk["tflops_sustained"],
+                         "traffic": traffic.get("conv_tc_kernel", {}).get("traffic_bytes_per_launch"),
+                         "traffic_note": "dram bytes of the dominant launch (layer3.0.downsample) from profiles/r01_roofline_traffic.json; equals its algorithmic bytes",
+                         "peak_source": pk["source"] + ", bf16 dense sustained",
+                         "achieved_is": "ALGORITHMIC conv FLOPs / summed CUDA-event time of the family's launches (profiled pass of the same step)",
+                         "executed_mma_tflops": conv_tflops * mma_per_flop, "executed_mma_frac": conv_tflops * mma_per_flop / pk["tflops_sustained"],
+                         "mma_per_algorithmic_flop": mma_per_flop,
                          "launches_per_step": conv["launches"] // nprof, "share_of_step": conv["ms"] / nprof / step_ms_prof if step_ms_prof else None,
                          "algorithmic_gflop_per_step": conv["flops"] / nprof / 1e9},
-            "xcorr_roofline": {"kernel": "groupdw_kernel (fused 3-scale depthwise xcorr)", "bound": "hbm", "achieved": xc_gbs, "peak": pk["hbm_gbs"],
-                               "unit": "GB/s", "frac": xc_gbs / pk["hbm_gbs"], "traffic": None, "launches_per_step": xc["launches"] // nprof,
+            "xcorr_roofline": {"kernel": "groupdw_tma_kernel (fused 3-scale depthwise xcorr, TMA ring)", "bound": "hbm", "achieved": xc_gbs, "peak": pk["hbm_gbs"],
+                               "unit": "GB/s", "frac": xc_gbs / pk["hbm_gbs"],
+                               "traffic": traffic.get("groupdw_tma_kernel", {}).get("traffic_bytes_per_launch"), "launches_per_step": xc["launches"] // nprof,
                                "algorithmic_mb_per_launch": xc["bytes"] / max(xc["launches"], 1) / 1e6},
             "backbone_flop_frac": value / world * GFLOP_BACKBONE_NECK * 1e9 / (pk["tflops_sustained"] * 1e12),
             "kernel_ms_per_step": {k: v["ms"] / nprof for k, v in prof.items() if v["launches"]},

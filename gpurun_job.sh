@@ -1,10 +1,7 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_model.py -q -m gpu -x -s -k "memory or config1 or independence or fresh" 2>&1 | grep -oE "(damp025|raw) [a-z0-9]+ fp16x3 \{[^}]*\}|backbone fresh [a-z0-9]+ [0-9.e-]+|[0-9]+ (passed|failed).*|Error.*|error.*" | tail -14
-for prec in fp16x3 fp16; do
-python bench.py --steps 10 --warmup 3 --precision $prec --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_$prec.json
-python - <<PY
-import json
-d=json.load(open("gpurun_out/bench_$prec.json"))
-print("$prec value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "conv TF", round(d["roofline"]["achieved"],1), d["kernel_ms_per_step"], d["clocks"])
-PY
-done
+timeout 600 python -m pytest tests/test_gpu_tunables.py -q -m gpu 2>&1 | tail -4
+USOT_DEBUG_SPLIT_OUT=2 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -o gpurun_out/r01_conv_tc_l3_down python tools/conv_cases.py l3_down 256 fp16x3 > /dev/null 2>&1
+USOT_DEBUG_SPLIT_OUT=2 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 1 -c 1 -o gpurun_out/r01_conv_tc_l3_conv3 python tools/conv_cases.py l3_conv3 256 fp16x3 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:groupdw_tma -s 1 -c 1 -o gpurun_out/r01_groupdw_tma python tools/groupdw_case.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stem_tc -s 2 -c 1 -o gpurun_out/r01_stem_tc python bench.py --steps 1 --warmup 3 --batch 256 --no-cpu-baseline > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep

@@ -77,21 +77,27 @@ def _groupdw_ref(xs, zs, w, rep):
     return O.groupdw(w, zs, xs).permute(0, 2, 3, 1)
 
 
-@pytest.mark.parametrize("F_,nx,nz,n_out,strips", [(31, 3, 1, 3, 3), (31, 2, 2, 2, 2), (33, 2, 6, 6, 3), (33, 1, 1, 1, 2), (31, 2, 14, 14, 3)])
+@pytest.mark.parametrize("F_,nx,nz,n_out,strips", [(31, 3, 1, 3, 3), (31, 2, 2, 2, 2), (33, 2, 6, 6, 3), (33, 1, 1, 1, 2), (31, 2, 14, 14, 3),
+                                                   (31, 6, 2, 6, 0), (31, 3, 1, 3, 0), (33, 2, 6, 6, 0), (31, 2, 14, 14, 0)])
 def test_groupdw_fused(ops, F_, nx, nz, n_out, strips):
+    """strips = 0 selects the TMA-pipelined kernel (default); 2 / 3 the register-staged variants."""
     from usot_b200 import _lib
-    _lib.check(_lib.load().usot_set_tunable(b"groupdw_strips", strips))
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 1 if strips == 0 else 0))
+    if strips:
+        _lib.check(_lib.load().usot_set_tunable(b"groupdw_strips", strips))
     g = torch.Generator().manual_seed(F_ + nx)
     C = 256
     xs = [torch.randn(nx, F_ - 2, F_ - 2, C, generator=g), torch.randn(nx, F_ - 4, F_ - 2, C, generator=g),
           torch.randn(nx, F_ - 2, F_ - 4, C, generator=g)]
     zs = [torch.randn(nz, 5, 5, C, generator=g), torch.randn(nz, 3, 5, C, generator=g), torch.randn(nz, 5, 3, C, generator=g)]
     w = torch.tensor([0.3, -0.2, 0.9])
-    ref = _groupdw_ref(xs, zs, w, n_out // nx)
+    zs_ref = [t.repeat_interleave(n_out // nz, 0) if 1 < nz < n_out else t for t in zs]
+    ref = _groupdw_ref(xs, zs_ref, w, n_out // nx)
     ours = ops.groupdw_xcorr([t.cuda() for t in xs], [t.cuda() for t in zs], w.cuda(), n_out).cpu()
     assert ours.shape == ref.shape
     assert rel_err(ours, ref) <= 3e-6  # pure fp32 FMA, only the summation order differs
     _lib.check(_lib.load().usot_set_tunable(b"groupdw_strips", 3))
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 1))
 
 
 def test_groupdw_linearity_full_size(ops):

@@ -71,7 +71,8 @@ struct GroupDWArgs {
     float* out;                                            // [n_out][R][R][C]
     int nx, nz, n_out, C, F;                               // R = F - 6
 };
-extern int g_groupdw_strips;
+extern int g_groupdw_strips, g_groupdw_tma;
+int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st);  // xcorr_tma.cu
 int launch_groupdw(const GroupDWArgs& a, cudaStream_t st);  // reads dw_weight back (one stream sync)
 int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st);  // softmaxed weights given
 // Single depth-wise xcorr, NCHW (the reference op, connect.py:147-157)

@@ -408,13 +408,13 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box, int swizzle) {
     EncodeTiledFn fn = encode_fn();
     USOT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = fn(m, (CUtensorMapDataType)dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("usot_b200: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
@@ -422,6 +422,12 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
     }
     return 0;
 }
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+    return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box, (int)swizzle);
+}
+
 
 // choose (tiles_w, bw, bh) maximising the fraction of the 128 MMA rows that are real output pixels
 static void choose_tiling(int ho, int wo, int* tiles_w, int* bw, int* bh) {

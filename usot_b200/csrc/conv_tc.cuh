@@ -52,6 +52,9 @@ struct TcEpilogue {
     int relu;
 };
 
+// generic cuTensorMapEncodeTiled wrapper (dtype / swizzle are CUtensorMapDataType / CUtensorMapSwizzle values)
+int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box, int swizzle);
 extern int g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res;
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st);
 int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);

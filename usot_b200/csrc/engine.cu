@@ -627,6 +627,7 @@ int usot_profile_read(int fam, double* out) {
 int usot_set_tunable(const char* name, int value) {
     USOT_REQUIRE(name, "null name");
     if (!strcmp(name, "tc_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_bn_max must be 64, 128 or 256"); g_tc_bn_max = value; return 0; }
+    if (!strcmp(name, "groupdw_tma")) { USOT_REQUIRE(value == 0 || value == 1, "groupdw_tma must be 0 or 1"); g_groupdw_tma = value; return 0; }
     if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
     if (!strcmp(name, "tc_tma_store")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_store must be 0 or 1"); g_tc_tma_store = value; return 0; }

@@ -393,11 +393,13 @@ int launch_groupdw(const GroupDWArgs& a, cudaStream_t st) {
     return launch_groupdw_w(a, e0 / s, e1 / s, e2 / s, st);
 }
 
-int g_groupdw_strips = 3;  // tunable (usot_set_tunable("groupdw_strips", 2|3))
+int g_groupdw_strips = 3;  // tunable (usot_set_tunable("groupdw_strips", 2|3)) of the register-staged variant
+int g_groupdw_tma = 1;     // tunable: 1 = TMA-pipelined kernel (xcorr_tma.cu), 0 = register-staged kernel below
 
 int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
     USOT_REQUIRE(a.nx > 0 && a.nz > 0 && a.n_out % a.nx == 0 && a.n_out % a.nz == 0, "groupdw: n_out must be a multiple of both batches");
     const int R = a.F - 6;
+    if (g_groupdw_tma && (R + 8) / 9 == 3) return launch_groupdw_tma(a, w0, w1, w2, st);
     const int nstrips = (g_groupdw_strips == 2 && R <= 28) ? 2 : (R + 8) / 9;
     const int sw = (R + nstrips - 1) / nstrips;
     const unsigned grid = (unsigned)(a.n_out * (a.C / 64) * nstrips);

@@ -1,0 +1,173 @@
+// Fused GroupDW depth-wise cross-correlation, TMA-pipelined (the bandwidth-bound half of the headline metric).
+//   out[n] = sum_i softmax(w)_i * xcorr(x_i[n / rep_x], z_i[n / rep_z])      lib/models/connect.py:86-102,147-157
+//
+// One CTA = (output sample, 64-channel slab).  A producer warp streams the three encoded search maps row by row through a
+// 4-stage shared-memory ring with 3-D..4-D TMA boxes {64 ch, W, 1 row, 1 sample} (fp32, no swizzle: lanes read consecutive
+// channels, conflict-free), so ~3 rows x 21 KB per CTA are always in flight and every byte of x is fetched from HBM/L2 exactly
+// once per output sample.  Six consumer warps = 3 column strips x 64 channels; each thread keeps its 55 pre-scaled taps and a
+// ring of 5 output rows x 9 columns in registers, accumulates the 5x5 / 5x3 / 3x5 correlations of the current input row, and
+// writes a finished output row (coalesced over channels) every step.
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace usot {
+
+constexpr int GD_STAGES = 4, GD_SW = 9, GD_CONSUMERS = 192;
+
+struct GdwParams {
+    CUtensorMap m11, m12, m21;
+    const float* z11; const float* z12; const float* z21;
+    float* out;
+    int nx, nz, n_out, C, F, nstrips;
+    float w0, w1, w2;
+};
+
+__global__ void __launch_bounds__(GD_CONSUMERS + 32, 2) groupdw_tma_kernel(const __grid_constant__ GdwParams p) {
+    extern __shared__ __align__(128) uint8_t gsm_raw[];
+    const uint32_t base = (smem_u32(gsm_raw) + 127u) & ~127u;
+    uint8_t* sm = gsm_raw + (base - smem_u32(gsm_raw));
+    const int F = p.F, R = F - 6, W11 = F - 2, H11 = F - 2, W12 = F - 2, H12 = F - 4, W21 = F - 4, C = p.C;
+    const int row11 = W11 * 256, row21 = W21 * 256, row12 = W12 * 256;  // bytes of one staged row (64 ch x 4 B per pixel)
+    const int stage_bytes = row11 + row21 + row12;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + GD_STAGES * stage_bytes);
+    const uint32_t bar_full = base + GD_STAGES * stage_bytes, bar_empty = bar_full + 8 * GD_STAGES;
+    (void)bars;
+
+    const int cblocks = C / 64;
+    const int cblk = blockIdx.x % cblocks, n = blockIdx.x / cblocks;
+    const int xb = n / (p.n_out / p.nx), zb = n / (p.n_out / p.nz);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < GD_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, GD_CONSUMERS / 32); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == GD_CONSUMERS / 32) {
+        // ------------------------------- producer -------------------------------
+        if (lane == 0) {
+            tma_prefetch_desc(&p.m11); tma_prefetch_desc(&p.m12); tma_prefetch_desc(&p.m21);
+            for (int t = 0; t < H11; ++t) {
+                const int s = t % GD_STAGES;
+                if (t >= GD_STAGES) mbar_wait(bar_empty + 8 * s, ((t / GD_STAGES) + 1) & 1);
+                const bool has12 = t >= 2 && t - 2 < H12;
+                const uint32_t full = bar_full + 8 * s, dst = base + s * stage_bytes;
+                mbar_expect_tx(full, (uint32_t)(row11 + row21 + (has12 ? row12 : 0)));
+                tma_load_4d(dst, &p.m11, full, cblk * 64, 0, t, xb);
+                tma_load_4d(dst + row11, &p.m21, full, cblk * 64, 0, t, xb);
+                if (has12) tma_load_4d(dst + row11 + row21, &p.m12, full, cblk * 64, 0, t - 2, xb);
+            }
+        }
+        return;
+    }
+
+    // ------------------------------- consumers -------------------------------
+    const int strip = tid >> 6, ch = tid & 63;
+    const int c = cblk * 64 + ch;
+    const int j0 = strip * GD_SW;
+    const int jn = min(GD_SW, R - j0);
+    float z[55];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) z[t] = p.w0 * __ldg(p.z11 + ((size_t)zb * 25 + t) * C + c);
+#pragma unroll
+    for (int t = 0; t < 15; ++t) z[25 + t] = p.w1 * __ldg(p.z12 + ((size_t)zb * 15 + t) * C + c);
+#pragma unroll
+    for (int t = 0; t < 15; ++t) z[40 + t] = p.w2 * __ldg(p.z21 + ((size_t)zb * 15 + t) * C + c);
+    float* out = p.out + (size_t)n * R * R * C + c;
+
+    float acc[5][GD_SW];  // acc[k] = output row t-4+k at step t
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int j = 0; j < GD_SW; ++j) acc[k][j] = 0.f;
+
+    for (int t = 0; t < H11; ++t) {
+        const int s = t % GD_STAGES;
+        mbar_wait(bar_full + 8 * s, (t / GD_STAGES) & 1);
+        const float* xs = reinterpret_cast<const float*>(sm + s * stage_bytes) + ch;
+        {   // 5x5 on x11 row t -> output rows t-u
+            float xr[GD_SW + 4];
+#pragma unroll
+            for (int q = 0; q < GD_SW + 4; ++q) xr[q] = (j0 + q < W11) ? xs[(j0 + q) * 64] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+#pragma unroll
+                for (int v = 0; v < 5; ++v)
+#pragma unroll
+                    for (int j = 0; j < GD_SW; ++j) acc[4 - u][j] = fmaf(xr[j + v], z[u * 5 + v], acc[4 - u][j]);
+        }
+        {   // 5x3 on x21 row t -> output rows t-u
+            const float* x2 = xs + W11 * 64;
+            float xr[GD_SW + 2];
+#pragma unroll
+            for (int q = 0; q < GD_SW + 2; ++q) xr[q] = (j0 + q < W21) ? x2[(j0 + q) * 64] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+#pragma unroll
+                    for (int j = 0; j < GD_SW; ++j) acc[4 - u][j] = fmaf(xr[j + v], z[40 + u * 3 + v], acc[4 - u][j]);
+        }
+        if (t >= 2 && t - 2 < H12) {  // 3x5 on x12 row t-2 -> output rows t-2-u (ring slots 2-u)
+            const float* x3 = xs + (W11 + W21) * 64;
+            float xr[GD_SW + 4];
+#pragma unroll
+            for (int q = 0; q < GD_SW + 4; ++q) xr[q] = (j0 + q < W12) ? x3[(j0 + q) * 64] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+                for (int v = 0; v < 5; ++v)
+#pragma unroll
+                    for (int j = 0; j < GD_SW; ++j) acc[2 - u][j] = fmaf(xr[j + v], z[25 + u * 5 + v], acc[2 - u][j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp is done reading the stage
+        if (t >= 4) {  // output row t-4 is complete
+            float* o = out + ((size_t)(t - 4) * R + j0) * C;
+#pragma unroll
+            for (int j = 0; j < GD_SW; ++j)
+                if (j < jn) o[(size_t)j * C] = acc[0][j];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < GD_SW; ++j) acc[k][j] = acc[k + 1][j];
+#pragma unroll
+        for (int j = 0; j < GD_SW; ++j) acc[4][j] = 0.f;
+    }
+}
+
+int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
+    USOT_REQUIRE(a.C % 64 == 0, "groupdw needs C % 64 == 0");
+    USOT_REQUIRE(a.nx > 0 && a.nz > 0 && a.n_out % a.nx == 0 && a.n_out % a.nz == 0, "groupdw: n_out must be a multiple of both batches");
+    const int F = a.F, R = F - 6;
+    USOT_REQUIRE(R > 0 && (R + GD_SW - 1) / GD_SW == 3, "groupdw_tma supports response sizes 19..27 (search 255 / 271)");
+    if (a.n_out == 0) return 0;
+    GdwParams p;
+    memset(&p, 0, sizeof(p));
+    auto mk = [&](CUtensorMap* m, const float* base, int h, int w) -> int {
+        cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)a.nx};
+        cuuint64_t strides[3] = {(cuuint64_t)a.C * 4, (cuuint64_t)w * a.C * 4, (cuuint64_t)h * w * a.C * 4};
+        cuuint32_t box[4] = {64, (cuuint32_t)w, 1, 1};
+        return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    };
+    if (int rc = mk(&p.m11, a.x11, F - 2, F - 2)) return rc;
+    if (int rc = mk(&p.m12, a.x12, F - 4, F - 2)) return rc;
+    if (int rc = mk(&p.m21, a.x21, F - 2, F - 4)) return rc;
+    p.z11 = a.z11; p.z12 = a.z12; p.z21 = a.z21; p.out = a.out;
+    p.nx = a.nx; p.nz = a.nz; p.n_out = a.n_out; p.C = a.C; p.F = F; p.nstrips = 3;
+    p.w0 = w0; p.w1 = w1; p.w2 = w2;
+    const int smem = GD_STAGES * (3 * F - 8) * 256 + 2 * GD_STAGES * 8 + 128;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        USOT_CUDA_OK(cudaFuncSetAttribute(groupdw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    groupdw_tma_kernel<<<(unsigned)(a.n_out * (a.C / 64)), GD_CONSUMERS + 32, smem, st>>>(p);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace usot
