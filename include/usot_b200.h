@@ -51,7 +51,7 @@ USOT_API const char* usot_last_error(void);
 USOT_API int usot_abi_version(void);
 /* Process-wide performance knobs (never change results): "groupdw_strips" = 2 | 3; "tc_bn_max" = 64 | 128 | 256;
  * "tc_tma_store" = 0 | 1 (TMA-store epilogue), "tc_tma_res" = 0 | 1 (residual loaded by TMA), "stem_tc" = 0 | 1 (tensor-core stem),
- * "groupdw_tma" = 0 | 1 (TMA-pipelined GroupDW).
+ * "groupdw_tma" = 0 | 1 (TMA-pipelined GroupDW), "graph_max_batch" = 0..64 (track() with n <= this replays a CUDA graph).
  * One accuracy knob: "tc_split_bn_max" = 64 | 128 (default; separate cross-term accumulator) | 256 (single accumulator). */
 USOT_API int usot_set_tunable(const char* name, int value);
 

@@ -42,3 +42,25 @@ def test_knob_keeps_results(net, knob, value, exact):
         else:      # different summation order / fp32 CUDA-core stem: rounding-level differences only
             assert float((a - b).abs().max() / b.abs().max()) <= 2e-4
             assert torch.equal(a.flatten(1).argmax(1), b.flatten(1).argmax(1))
+
+
+def test_cuda_graph_replay_matches_eager(net):
+    """track() at small batch replays a captured CUDA graph from the 2nd call on; results must equal the eager path bit for bit,
+    also when inputs / template / memory change between replays."""
+    z, x, tb, sb = O.synth_inputs(92, batch=2)
+    nq = 3
+    net.template(z.cuda(), tb.cuda())
+    mem = net.extract_memory_feature(ori_x=x[:1].repeat(2 * nq, 1, 1, 1).cuda(), search_bbox=sb[:1].repeat(2 * nq, 1).cuda())
+    score = torch.full((2, nq), 0.9).cuda()
+    _set("graph_max_batch", 0)
+    eager = [t.clone() for t in net.track(x.cuda(), mem, score)]
+    x2 = (x * 0.5 + 17.0).cuda()
+    eager2 = [t.clone() for t in net.track(x2, mem, score)]
+    _set("graph_max_batch", 8)
+    for rep in range(4):  # call 1 eager, call 2 captures, calls 3-4 replay
+        out = net.track(x.cuda(), mem, score)
+        for a, b in zip(out, eager):
+            assert torch.equal(a, b), f"replay {rep} differs"
+    out2 = net.track(x2, mem, score)
+    for a, b in zip(out2, eager2):
+        assert torch.equal(a, b)

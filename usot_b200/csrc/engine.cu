@@ -18,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace usot {
@@ -166,10 +167,20 @@ struct usot_engine {
     float dw_cls[3] = {0, 0, 0}, dw_reg[3] = {0, 0, 0};  // softmax(GroupDW.weight)
     float *adjust = nullptr, *bias4 = nullptr;
     Arena arena;
+    // CUDA-graph cache of track() for small batches: key = (n, size, nz, nq); valid while the arena has not moved
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0; int seen = 0; long long launches[8] = {0}; };
+    std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
+    uint64_t arena_gen = 0;
+    cudaStream_t gstream = nullptr;   // graphs are captured and replayed on an engine-owned stream (the caller's may be the
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // legacy default stream, which cannot be captured); ordered by events
     std::mutex mu;  // one forward at a time per engine (DataParallel replicas own separate engines)
 
     ~usot_engine() {
         cudaSetDevice(device);
+        for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        if (gstream) cudaStreamDestroy(gstream);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
         for (void* p : owned) cudaFree(p);
         if (arena.base) cudaFree(arena.base);
     }
@@ -588,10 +599,13 @@ static int with_arena(usot_engine* e, Fn&& body) {
         }
         ar.base = static_cast<char*>(p);
         ar.cap = need;
+        ++e->arena_gen;  // captured graphs hold arena addresses
     }
     ar.off = 0;
     return body(ar);
 }
+
+static int g_graph_max_batch = 8;  // tunable "graph_max_batch": track() with n <= this replays a captured CUDA graph (0 = off)
 
 }  // namespace usot
 
@@ -627,6 +641,7 @@ int usot_profile_read(int fam, double* out) {
 int usot_set_tunable(const char* name, int value) {
     USOT_REQUIRE(name, "null name");
     if (!strcmp(name, "tc_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_bn_max must be 64, 128 or 256"); g_tc_bn_max = value; return 0; }
+    if (!strcmp(name, "graph_max_batch")) { USOT_REQUIRE(value >= 0 && value <= 64, "graph_max_batch must be in [0, 64]"); g_graph_max_batch = value; return 0; }
     if (!strcmp(name, "groupdw_tma")) { USOT_REQUIRE(value == 0 || value == 1, "groupdw_tma must be 0 or 1"); g_groupdw_tma = value; return 0; }
     if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
@@ -789,16 +804,93 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
     USOT_REQUIRE(nz == 1 || nz == n, "template batch must be 1 or equal to the search batch");
     USOT_REQUIRE(nq >= 0 && (nq == 0 || (template_mem && cls_mem)), "memory branch needs template_mem and cls_mem");
     USOT_REQUIRE(usot_feature_size(size) >= 9, "search crop too small");
-    return with_arena(e, [&](Arena& ar) {
-        Ctx c{e, ar, (cudaStream_t)stream};
+    const cudaStream_t caller = (cudaStream_t)stream;
+    cudaStream_t st = caller;
+    const int F = usot_feature_size(size), R = F - 6;
+    const size_t n_x = (size_t)n * 3 * size * size, n_zf = (size_t)nz * 49 * 256, n_mem = (size_t)n * nq * 49 * 256;
+    const size_t n_cls = (size_t)n * R * R, n_xf = (size_t)n * F * F * 256;
+    const bool want_graph = g_graph_max_batch > 0 && n <= g_graph_max_batch && !g_prof.on;
+    // I/O staging inside the arena (allocated first => fixed addresses): lets a captured graph be replayed for any caller pointers
+    struct IO { float *x, *zf, *mem, *cls, *bbox, *cls_mem, *xf; } io{};
+    auto body = [&](Arena& ar, bool staged) -> int {
+        Ctx c{e, ar, st};
+        if (staged) {
+            io.x = ar.f(n_x); io.zf = ar.f(n_zf); io.mem = nq ? ar.f(n_mem) : nullptr;
+            io.cls = ar.f(n_cls); io.bbox = ar.f(4 * n_cls); io.cls_mem = nq ? ar.f(n_cls) : nullptr; io.xf = ar.f(n_xf);
+        }
+        const float* xi = staged ? io.x : x;
+        const float* zi = staged ? io.zf : zf;
+        const float* mi = staged ? io.mem : template_mem;
         T f;
-        if (int rc = backbone_neck(c, x, n, size, xf, &f)) return rc;
+        if (int rc = backbone_neck(c, xi, n, size, staged ? io.xf : xf, &f)) return rc;
         Enc3 cls_x;
-        if (int rc = head_offline(c, f, zf, nz, cls, bbox, &cls_x)) return rc;
+        if (int rc = head_offline(c, f, zi, nz, staged ? io.cls : cls, staged ? io.bbox : bbox, &cls_x)) return rc;
         if (nq > 0)
-            if (int rc = head_memory(c, cls_x, n, f.h, template_mem, nq, n * nq, cls_mem)) return rc;
+            if (int rc = head_memory(c, cls_x, n, f.h, mi, nq, n * nq, staged ? io.cls_mem : cls_mem)) return rc;
         return 0;
-    });
+    };
+    if (!want_graph) return with_arena(e, [&](Arena& ar) { return body(ar, false); });
+
+    usot_engine::GraphEntry* ge = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        ge = &e->graphs[std::make_tuple(n, size, nz, nq)];
+    }
+    if (ge->seen++ == 0)  // first call with this shape runs eagerly (one-time kernel attribute / constant setup must not be captured)
+        return with_arena(e, [&](Arena& ar) { return body(ar, false); });
+    USOT_CUDA_OK(cudaSetDevice(e->device));
+    if (!e->gstream) {
+        USOT_CUDA_OK(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
+        USOT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+        USOT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+    }
+    st = e->gstream;
+    USOT_CUDA_OK(cudaEventRecord(e->ev_in, caller));   // everything the caller enqueued (inputs!) precedes the graph
+    USOT_CUDA_OK(cudaStreamWaitEvent(st, e->ev_in, 0));
+    if (!ge->exec || ge->arena_gen != e->arena_gen) {
+        // (re)capture: the planning pass of with_arena sizes / grows the arena, the execute pass is recorded into the graph
+        if (ge->exec) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; }
+        long long before[FAM_COUNT];
+        for (int i = 0; i < FAM_COUNT; ++i) before[i] = g_prof.launches[i];
+        bool capturing = false;
+        int rc = with_arena(e, [&](Arena& ar) -> int {
+            if (!ar.plan) {
+                if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { set_error("usot_b200: cudaStreamBeginCapture failed"); return 1; }
+                capturing = true;
+            }
+            return body(ar, true);
+        });
+        cudaGraph_t graph = nullptr;
+        if (capturing) {
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc == 0 && ce != cudaSuccess) { set_error(std::string("usot_b200: cudaStreamEndCapture: ") + cudaGetErrorString(ce)); rc = 1; }
+        }
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        cudaError_t ie = cudaGraphInstantiate(&ge->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { ge->exec = nullptr; set_error(std::string("usot_b200: cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return 1; }
+        ge->arena_gen = e->arena_gen;
+        for (int i = 0; i < FAM_COUNT; ++i) { ge->launches[i] = g_prof.launches[i] - before[i]; g_prof.launches[i] = before[i]; }
+    } else {
+        // replay: recompute the (deterministic) staging addresses without launching anything
+        std::lock_guard<std::mutex> lk(e->mu);
+        Arena& ar = e->arena;
+        ar.plan = false; ar.off = 0;
+        io.x = ar.f(n_x); io.zf = ar.f(n_zf); io.mem = nq ? ar.f(n_mem) : nullptr;
+        io.cls = ar.f(n_cls); io.bbox = ar.f(4 * n_cls); io.cls_mem = nq ? ar.f(n_cls) : nullptr; io.xf = ar.f(n_xf);
+    }
+    USOT_CUDA_OK(cudaMemcpyAsync(io.x, x, n_x * 4, cudaMemcpyDeviceToDevice, st));
+    USOT_CUDA_OK(cudaMemcpyAsync(io.zf, zf, n_zf * 4, cudaMemcpyDeviceToDevice, st));
+    if (nq) USOT_CUDA_OK(cudaMemcpyAsync(io.mem, template_mem, n_mem * 4, cudaMemcpyDeviceToDevice, st));
+    USOT_CUDA_OK(cudaGraphLaunch(ge->exec, st));
+    for (int i = 0; i < FAM_COUNT; ++i) g_prof.launches[i] += ge->launches[i];
+    USOT_CUDA_OK(cudaMemcpyAsync(cls, io.cls, n_cls * 4, cudaMemcpyDeviceToDevice, st));
+    USOT_CUDA_OK(cudaMemcpyAsync(bbox, io.bbox, 4 * n_cls * 4, cudaMemcpyDeviceToDevice, st));
+    if (nq) USOT_CUDA_OK(cudaMemcpyAsync(cls_mem, io.cls_mem, n_cls * 4, cudaMemcpyDeviceToDevice, st));
+    if (xf) USOT_CUDA_OK(cudaMemcpyAsync(xf, io.xf, n_xf * 4, cudaMemcpyDeviceToDevice, st));
+    USOT_CUDA_OK(cudaEventRecord(e->ev_out, st));
+    USOT_CUDA_OK(cudaStreamWaitEvent(caller, e->ev_out, 0));  // the caller's stream sees the outputs in order
+    return 0;
 }
 
 int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n, int size, const float* xf, int feat,
