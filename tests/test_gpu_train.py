@@ -87,3 +87,34 @@ def test_tracker_postprocess_vs_numpy_reference(R, S):
         assert (int(out[0]), int(out[1])) == (r, c)
         assert np.allclose(out[2:6], box, rtol=1e-6, atol=1e-6)
         assert abs(out[6] - penalty[r, c]) <= 1e-6 and abs(out[7] - mixed[r, c]) <= 1e-6
+
+
+def test_device_tracker_update_matches_reference_formulae():
+    """usot_b200.tracker_ops.update_device (device queue + fused post-process) against a host restatement of
+    USOTTracker.update (lib/tracker/usot_tracker.py:133-200) driven by the oracle's model outputs."""
+    import types
+    from usot_b200 import tracker_ops
+    sd = load_weights("damp025")
+    net = _net("damp025", "fp16x3")
+    z, x, tb, sb = O.synth_inputs(55, batch=1)
+    net.template(z.cuda(), tb.cuda())
+    f0 = net.extract_memory_feature(ori_x=x.cuda(), search_bbox=sb.cuda())
+    f1 = net.extract_memory_feature(ori_x=torch.flip(x, dims=[3]).cuda(), search_bbox=sb.cuda())
+    q = tracker_ops.MemoryQueue([f0, f1], mem_queue_size=7)
+    p = types.SimpleNamespace(instance_size=255, score_size=25, total_stride=8, ratio=0.3, penalty_k=0.021, window_influence=0.321, lr=0.730)
+    target_pos, target_sz, scale_z = np.array([320.0, 240.0]), np.array([80.0, 60.0]), 0.9
+    window = tracker_ops.cosine_window(25, "cuda")
+    pos, sz, conf, feat = tracker_ops.update_device(net, x.cuda(), target_pos, target_sz * scale_z, window, scale_z, p, q)
+    # reference formulae on the host with the oracle's maps
+    with torch.no_grad():
+        zf = O.template(sd, z, tb)
+        mem, _ = q.select()
+        cls, bbox, cmem, xf = O.track(sd, zf, x, mem.cpu().contiguous(), torch.full((1, 7), 0.9))
+    r, c, pscore, penalty, mixed, box = O.tracker_update(cls, bbox, cmem, target_sz * scale_z, np.outer(np.hanning(25), np.hanning(25)))
+    pw, ph = (box[2] - box[0]) / scale_z, (box[3] - box[1]) / scale_z
+    lr = penalty[r, c] * mixed[r, c] * p.lr
+    ref_pos = target_pos + np.array([(box[0] + box[2]) / 2 - 127, (box[1] + box[3]) / 2 - 127]) / scale_z
+    tsz = target_sz * scale_z / scale_z
+    ref_sz = tsz * (1 - lr) + lr * np.array([pw * lr + (1 - lr) * tsz[0], ph * lr + (1 - lr) * tsz[1]])
+    assert np.allclose(pos, ref_pos, rtol=1e-4, atol=1e-3) and np.allclose(sz, ref_sz, rtol=1e-4, atol=1e-3)
+    assert abs(conf - mixed[r, c]) <= 1e-4 and tuple(feat.shape) == (1, 256, 7, 7)

@@ -28,3 +28,107 @@ def postprocess(cls_score, bbox_pred, cls_memory, window, target_sz_scaled, inst
                                                         float(target_sz_scaled[0]), float(target_sz_scaled[1]), float(ratio), float(penalty_k),
                                                         float(window_influence), _lib.ptr(out), _stream(cls_score)))
     return out
+
+
+class MemoryQueue:
+    """Device-resident memory queue with the reference's sampling rule (lib/tracker/usot_tracker.py:222-256).
+
+    The reference keeps every pooled feature on the HOST (``.cpu()`` each frame, usot_tracker.py:106,123,199) and re-uploads
+    the N_q selected ones every frame (351 KB H2D).  Here the features never leave the GPU: they live in one growing NHWC
+    buffer, the confidences (host scalars the selection rule needs) stay on the host, and ``select()`` gathers the N_q rows
+    with a single index_select on the device.  The selected indices are exactly the reference's, including its documented
+    start/end-index quirk (usot_tracker.py:239-242).
+    """
+
+    def __init__(self, init_features, mem_queue_size=7, capacity=512):
+        """init_features: [feature, flipped_feature], each (1,256,7,7) (any strides) on the device."""
+        f0 = init_features[0]
+        self.device = f0.device
+        self.nq = int(mem_queue_size)
+        self._buf = torch.empty((capacity, 7, 7, f0.shape[1]), dtype=torch.float32, device=self.device)
+        self._n = 0
+        self.confidences = []
+        self._init = [self._append_raw(f) for f in init_features]  # rows 0, 1
+        self._first = self._init[0]  # state['memory_features'] = [memory_feature]
+        self._mem_rows = [self._first]
+        self.confidences = [0.9]
+
+    def _append_raw(self, feat_nchw):
+        if self._n == self._buf.shape[0]:
+            new = torch.empty((2 * self._n,) + tuple(self._buf.shape[1:]), dtype=torch.float32, device=self.device)
+            new[: self._n].copy_(self._buf)
+            self._buf = new
+        self._buf[self._n].copy_(feat_nchw[0].permute(1, 2, 0))
+        self._n += 1
+        return self._n - 1
+
+    def append(self, feature, confidence):
+        """state['memory_features'].append(feat_mem); state['memory_confidences'].append(confidence)."""
+        self._mem_rows.append(self._append_raw(feature))
+        self.confidences.append(float(confidence))
+
+    def selected_rows(self):
+        """Buffer rows of the N_q memory templates and their confidences, in the reference's order."""
+        rows, scores = list(self._init), [0.9, 0.9]
+        mem_rows, conf = self._mem_rows, self.confidences
+        n = len(conf)
+        upd = self.nq - 3
+        if n <= 1:
+            rows += [mem_rows[0]] * (upd + 1)
+            scores += [conf[0]] * (upd + 1)
+        else:
+            gap = (n - 1) / upd
+            for i in range(upd):
+                start = min(int(int(i * gap) * n), n - 1)
+                end = min(int(int((i + 1) * gap) * n), n - 1)
+                if start >= end:
+                    rows.append(mem_rows[start])
+                    scores.append(conf[start])
+                else:
+                    k = int(np.argmax(np.array(conf[start:end]))) + start
+                    rows.append(mem_rows[k])
+                    scores.append(conf[k])
+            rows.append(mem_rows[-1])
+            scores.append(conf[-1])
+        return rows, scores
+
+    def select(self):
+        """(template_mem, score_mem) as USOT.track expects them: (N_q,256,7,7) channels-last view and (1,N_q), both on the device."""
+        rows, scores = self.selected_rows()
+        idx = torch.tensor(rows, dtype=torch.long, device=self.device)
+        mem = self._buf.index_select(0, idx)  # (N_q,7,7,C) contiguous NHWC
+        return mem.permute(0, 3, 1, 2), torch.tensor([scores], dtype=torch.float32, device=self.device)
+
+
+def update_device(net, x_crops, target_pos, target_sz, window, scale_z, p, queue):
+    """Device-side version of USOTTracker.update (lib/tracker/usot_tracker.py:133-200) for one frame.
+
+    Same inputs / outputs as the reference method, except that the memory templates come from a ``MemoryQueue`` (features stay on
+    the GPU) and ``window`` is the float64 CUDA tensor of ``cosine_window``.  One blocking D2H copy per frame (8 doubles)
+    instead of the reference's four; the pooled memory feature is returned on the device.
+    ``target_sz`` is the target size already multiplied by ``scale_z`` (as the reference passes it, usot_tracker.py:258-259).
+    """
+    template_mem, score_mem = queue.select()
+    cls_score, bbox_pred, cls_memory, xf = net.track(x_crops, template_mem=template_mem, score_mem=score_mem)
+    res = postprocess(cls_score, bbox_pred, cls_memory, window, target_sz, instance_size=p.instance_size, ratio=p.ratio,
+                      penalty_k=p.penalty_k, window_influence=p.window_influence).cpu().numpy()
+    x1, y1, x2, y2, penalty, score = res[2], res[3], res[4], res[5], res[6], res[7]
+    # box / size update (usot_tracker.py:165-193)
+    half = p.instance_size // 2
+    dx, dy = ((x1 + x2) / 2 - half) / scale_z, ((y1 + y2) / 2 - half) / scale_z
+    pw, ph = (x2 - x1) / scale_z, (y2 - y1) / scale_z
+    tsz = np.asarray(target_sz, dtype=np.float64) / scale_z
+    lr = penalty * score * p.lr
+    new_pos = np.array([target_pos[0] + dx, target_pos[1] + dy])
+    blended = np.array([pw * lr + (1 - lr) * tsz[0], ph * lr + (1 - lr) * tsz[1]])
+    new_sz = tsz * (1 - lr) + lr * blended
+    # memory feature of the predicted box, PrPool'ed from xf on the device (usot_tracker.py:196-199, pool_label_search :329-350)
+    sf = p.score_size
+    axis0 = (0 - sf // 2) * p.total_stride + p.instance_size // 2
+    axis1 = (sf - 1 - sf // 2) * p.total_stride + p.instance_size // 2
+    slope = (2 * (sf // 2)) / (axis1 - axis0)
+    gap = 1.0 / slope
+    box = np.clip(np.array([x1, y1, x2, y2], np.float32), a_min=axis0 - gap, a_max=axis1 + gap)
+    pool_box = torch.tensor([(box - axis0) * slope], dtype=torch.float32, device=x_crops.device)
+    feat_mem = net.extract_memory_feature(xf=xf, search_bbox=pool_box)
+    return new_pos, new_sz, float(score), feat_mem
