@@ -129,6 +129,6 @@ def update_device(net, x_crops, target_pos, target_sz, window, scale_z, p, queue
     slope = (2 * (sf // 2)) / (axis1 - axis0)
     gap = 1.0 / slope
     box = np.clip(np.array([x1, y1, x2, y2], np.float32), a_min=axis0 - gap, a_max=axis1 + gap)
-    pool_box = torch.tensor([(box - axis0) * slope], dtype=torch.float32, device=x_crops.device)
+    pool_box = torch.from_numpy(((box - axis0) * slope).astype(np.float32)[None]).to(x_crops.device)
     feat_mem = net.extract_memory_feature(xf=xf, search_bbox=pool_box)
     return new_pos, new_sz, float(score), feat_mem
