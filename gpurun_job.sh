@@ -1,10 +1,9 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -5
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -10
-python bench.py 2>&1 | tail -1 > gpurun_out/bench_default.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_default.json'))
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}); print('e2e',d['e2e']); print('roofline',d['roofline']); print('xcorr',d['xcorr_roofline']); print('cpu',d['cpu_baseline']); print(d['kernel_ms_per_step'])"
-python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 > gpurun_out/bench_reference.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_reference.json')); print('ref', d['value'], d['cpu_baseline'])"
-python bench.py --precision fp16 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_fp16_final.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_fp16_final.json')); print('fp16', d['value'], d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'])"
+nvidia-smi -L | wc -l
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_8gpu.json
+python -c "
+import json; d=json.load(open('gpurun_out/bench_8gpu.json')); print('8gpu value', d['value'], 'e2e', d['e2e']['value'], 'ms', d['ms_per_step'], d['clocks'])"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 tests/bench_cycle.py 2>&1 | tail -1 | tee gpurun_out/cycle_8gpu.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29523 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_4gpu.json
+python -c "
+import json; d=json.load(open('gpurun_out/bench_4gpu.json')); print('4gpu value', d['value'], 'e2e', d['e2e']['value'])"

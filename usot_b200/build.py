@@ -29,9 +29,22 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into usot_b200/libusot_b200.so.  Returns the library path."""
+    """Compile every CUDA source for sm_100a into usot_b200/libusot_b200.so.  Returns the library path.
+    Safe to call from several processes at once (torchrun ranks): an exclusive file lock serialises the build."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another rank built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = []
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
