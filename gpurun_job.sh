@@ -1,9 +1,8 @@
 mkdir -p gpurun_out
-nvidia-smi -L | wc -l
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_8gpu.json
-python -c "
-import json; d=json.load(open('gpurun_out/bench_8gpu.json')); print('8gpu value', d['value'], 'e2e', d['e2e']['value'], 'ms', d['ms_per_step'], d['clocks'])"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 tests/bench_cycle.py 2>&1 | tail -1 | tee gpurun_out/cycle_8gpu.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29523 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_4gpu.json
-python -c "
-import json; d=json.load(open('gpurun_out/bench_4gpu.json')); print('4gpu value', d['value'], 'e2e', d['e2e']['value'])"
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_gpu_tunables.py -q -m gpu -x -k "groupdw or memory or config1 or knob or fresh" 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_fp16x3.json
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_fp16x3.json"))
+print("value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "xcorr", round(d["xcorr_roofline"]["achieved"]), d["kernel_ms_per_step"], d["clocks"]["sm_mhz"])
+PY

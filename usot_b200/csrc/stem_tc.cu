@@ -1,10 +1,11 @@
 // Stem on the tensor cores: conv1 7x7 / stride 2 / pad 0 (Cin = 3) + folded BN + ReLU   lib/models/modules.py:70-74,138-140
 //
-// As a GEMM the stem is M = output pixels, N = 64, K = 3*7*7 = 147 (padded to 160 = ten k16 steps).  Cin = 3 is far too thin
+// As a GEMM the stem is M = output pixels, N = 64, K = 3*7*7 = 147 (laid out as 21 x 8 = 168, padded to 176 = eleven k16 steps).  Cin = 3 is far too thin
 // for a TMA-fed implicit GEMM, so the A operand is built in shared memory by the CTA itself ("software im2col"):
 //   1. the 7 input rows x 3 channels a tile of one output row needs are staged as fp32 with cp.async (double buffered),
 //   2. all 256 threads convert them into the split-fp16 (hi, lo) A tile, written directly in the 128-byte-swizzled K-major
-//      layout tcgen05.mma reads (one 16-byte store per 8 consecutive k),
+//      layout tcgen05.mma reads; K is ordered k' = (c*7+kh)*8 + kw (kw padded to 8) so that one task = 7 contiguous patch floats
+//      -> one 16-byte store,
 //   3. one thread issues the 10 x 3 MMAs (hi*hi + hi*lo + lo*hi) against the weight tile that stays resident in shared memory,
 //      accumulating in one of two TMEM buffers (main + cross-term accumulator each, as in conv_tc.cu),
 //   4. while those MMAs run, all 8 warps drain the PREVIOUS tile's accumulator: scale/shift (BN) + ReLU -> NHWC fp32.
@@ -18,7 +19,7 @@
 
 namespace usot {
 
-constexpr int ST_KUSED = 160, ST_PW = 261, ST_PWP = 264, ST_PROWS = 21;
+constexpr int ST_KUSED = 176, ST_PW = 261, ST_PWP = 264, ST_PROWS = 21;  // K' = (c*7+kh)*8 + kw (kw padded 7 -> 8): 168 -> 176 = 11 k16 steps
 constexpr int ST_A_PLANE = 3 * 128 * 128;   // 3 chunks x 128 rows x 128 B
 constexpr int ST_B_PLANE = 3 * 64 * 128;    // 3 chunks x 64 rows x 128 B
 constexpr int ST_A_OFF = 0, ST_B_OFF = 2 * ST_A_PLANE, ST_P_OFF = ST_B_OFF + 2 * ST_B_PLANE;
@@ -26,7 +27,6 @@ constexpr int ST_PATCH_BYTES = ST_PROWS * ST_PWP * 4;
 constexpr int ST_SS_OFF = ST_P_OFF + 2 * ST_PATCH_BYTES, ST_BAR_OFF = ST_SS_OFF + 512;
 constexpr int ST_SMEM = ST_BAR_OFF + 64 + 1024;
 
-__constant__ int c_stem_koff[ST_KUSED];  // k -> offset of (c, kh, kw) inside the staged patch, -1 for the zero padding
 
 struct StemParams {
     const float* x;       // (n,3,S,S) nchw
@@ -119,6 +119,12 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const StemParams p) {
         tc_fence_before();
     };
 
+    // k' 168..175 (16-byte group 21 of every row) is padding that no build task ever writes: zero it once
+    for (int m = tid; m < 128; m += 256) {
+        const uint32_t a = ST_A_OFF + (21 >> 3) * (128 * 128) + m * 128 + (((21 & 7) ^ (m & 7)) << 4);
+        *reinterpret_cast<uint4*>(sm + a) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sm + ST_A_PLANE + a) = make_uint4(0, 0, 0, 0);
+    }
     const uint32_t idesc = make_idesc(128, 64);
     int it = 0, prev_tile = -1;
     if ((int)blockIdx.x < p.num_tiles) load_patch(blockIdx.x, 0);
@@ -132,15 +138,13 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const StemParams p) {
         }
         // ---- software im2col: patch (fp32) -> A tile (split fp16, 128B swizzle, K-major) ----
         const float* patch = reinterpret_cast<const float*>(sm + ST_P_OFF + (it & 1) * ST_PATCH_BYTES);
-#pragma unroll 2
-        for (int task = tid; task < 128 * (ST_KUSED / 8); task += 256) {
-            const int m = task & 127, g = task >> 7;
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int off = c_stem_koff[g * 8 + e];
-                v[e] = off >= 0 ? patch[off + 2 * m] : 0.f;
-            }
+#pragma unroll 3
+        for (int task = tid; task < 128 * ST_PROWS; task += 256) {
+            const int m = task & 127, r = task >> 7;  // r = c*7 + kh: the 7 taps kw = 0..6 are 7 contiguous patch floats
+            const float2* src = reinterpret_cast<const float2*>(patch + r * ST_PWP + 2 * m);
+            const float2 p0 = src[0], p1 = src[1], p2 = src[2];
+            const float p6 = patch[r * ST_PWP + 2 * m + 6];
+            const float v[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p6, 0.f};
             uint4 hi, lo;
             __half2* hh = reinterpret_cast<__half2*>(&hi);
             __half2* ll = reinterpret_cast<__half2*>(&lo);
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const StemParams p) {
                 hh[e] = h;
                 ll[e] = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
             }
-            const uint32_t a = ST_A_OFF + (g >> 3) * (128 * 128) + m * 128 + (((g & 7) ^ (m & 7)) << 4);
+            const uint32_t a = ST_A_OFF + (r >> 3) * (128 * 128) + m * 128 + (((r & 7) ^ (m & 7)) << 4);
             *reinterpret_cast<uint4*>(sm + a) = hi;
             if (SPLIT) *reinterpret_cast<uint4*>(sm + ST_A_PLANE + a) = lo;
         }
@@ -193,12 +197,6 @@ int launch_stem_tc(const float* x, int n, int s, const void* w_img, const float*
                    cudaStream_t st) {
     static bool init = false;
     if (!init) {
-        int koff[ST_KUSED];
-        for (int k = 0; k < ST_KUSED; ++k) {
-            if (k < 147) { const int c = k / 49, r = k % 49; koff[k] = (c * 7 + r / 7) * ST_PWP + r % 7; }
-            else koff[k] = -1;
-        }
-        USOT_CUDA_OK(cudaMemcpyToSymbol(c_stem_koff, koff, sizeof(koff)));
         USOT_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
         USOT_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
         init = true;
@@ -236,7 +234,8 @@ void pack_stem_tc_host(const float* w, const float* scale_in, std::vector<uint8_
         for (int k = 0; k < 147; ++k) {
             const float v = w[co * 147 + k] * s;
             const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
-            const int chunk = k / 64, kk = k % 64, g = kk / 8, e8 = kk % 8;
+            const int kp = (k / 7) * 8 + k % 7;  // k = (c*7+kh)*7 + kw  ->  k' = (c*7+kh)*8 + kw
+            const int chunk = kp / 64, kk = kp % 64, g = kk / 8, e8 = kk % 8;
             const size_t off = (size_t)chunk * (64 * 128) + co * 128 + ((g ^ (co & 7)) << 4) + e8 * 2;
             memcpy(&img[off], &h, 2);
             memcpy(&img[ST_B_PLANE + off], &l, 2);

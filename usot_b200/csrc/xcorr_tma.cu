@@ -13,7 +13,7 @@
 
 namespace usot {
 
-constexpr int GD_STAGES = 4, GD_SW = 9, GD_CONSUMERS = 192;
+constexpr int GD_STAGES = 2, GD_SW = 9, GD_CONSUMERS = 192;  // 2 stages x ~21 KB + 14 KB taps = 58 KB per CTA -> 3 CTAs per SM
 
 struct GdwParams {
     CUtensorMap m11, m12, m21;
@@ -23,16 +23,15 @@ struct GdwParams {
     float w0, w1, w2;
 };
 
-__global__ void __launch_bounds__(GD_CONSUMERS + 32, 2) groupdw_tma_kernel(const __grid_constant__ GdwParams p) {
+__global__ void __launch_bounds__(GD_CONSUMERS + 32, 3) groupdw_tma_kernel(const __grid_constant__ GdwParams p) {
     extern __shared__ __align__(128) uint8_t gsm_raw[];
     const uint32_t base = (smem_u32(gsm_raw) + 127u) & ~127u;
     uint8_t* sm = gsm_raw + (base - smem_u32(gsm_raw));
     const int F = p.F, R = F - 6, W11 = F - 2, H11 = F - 2, W12 = F - 2, H12 = F - 4, W21 = F - 4, C = p.C;
     const int row11 = W11 * 256, row21 = W21 * 256, row12 = W12 * 256;  // bytes of one staged row (64 ch x 4 B per pixel)
     const int stage_bytes = row11 + row21 + row12;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + GD_STAGES * stage_bytes);
-    const uint32_t bar_full = base + GD_STAGES * stage_bytes, bar_empty = bar_full + 8 * GD_STAGES;
-    (void)bars;
+    float* zs = reinterpret_cast<float*>(sm + GD_STAGES * stage_bytes);  // [55][64] taps of this CTA's channels, pre-scaled
+    const uint32_t bar_full = base + GD_STAGES * stage_bytes + 55 * 64 * 4, bar_empty = bar_full + 8 * GD_STAGES;
 
     const int cblocks = C / 64;
     const int cblk = blockIdx.x % cblocks, n = blockIdx.x / cblocks;
@@ -42,6 +41,12 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 2) groupdw_tma_kernel(const
     if (tid == 0) {
         for (int s = 0; s < GD_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, GD_CONSUMERS / 32); }
         fence_barrier_init();
+    }
+    if (tid < 64) {  // taps shared by the 3 column strips (registers are the scarce resource: 3 CTAs/SM need <= 96 per thread)
+        const int cc = cblk * 64 + tid;
+        for (int t = 0; t < 25; ++t) zs[t * 64 + tid] = p.w0 * __ldg(p.z11 + ((size_t)zb * 25 + t) * C + cc);
+        for (int t = 0; t < 15; ++t) zs[(25 + t) * 64 + tid] = p.w1 * __ldg(p.z12 + ((size_t)zb * 15 + t) * C + cc);
+        for (int t = 0; t < 15; ++t) zs[(40 + t) * 64 + tid] = p.w2 * __ldg(p.z21 + ((size_t)zb * 15 + t) * C + cc);
     }
     __syncthreads();
 
@@ -68,13 +73,7 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 2) groupdw_tma_kernel(const
     const int c = cblk * 64 + ch;
     const int j0 = strip * GD_SW;
     const int jn = min(GD_SW, R - j0);
-    float z[55];
-#pragma unroll
-    for (int t = 0; t < 25; ++t) z[t] = p.w0 * __ldg(p.z11 + ((size_t)zb * 25 + t) * C + c);
-#pragma unroll
-    for (int t = 0; t < 15; ++t) z[25 + t] = p.w1 * __ldg(p.z12 + ((size_t)zb * 15 + t) * C + c);
-#pragma unroll
-    for (int t = 0; t < 15; ++t) z[40 + t] = p.w2 * __ldg(p.z21 + ((size_t)zb * 15 + t) * C + c);
+    const float* z = zs + ch;  // tap t of this thread's channel: z[t * 64]
     float* out = p.out + (size_t)n * R * R * C + c;
 
     float acc[5][GD_SW];  // acc[k] = output row t-4+k at step t
@@ -94,9 +93,11 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 2) groupdw_tma_kernel(const
 #pragma unroll
             for (int u = 0; u < 5; ++u)
 #pragma unroll
-                for (int v = 0; v < 5; ++v)
+                for (int v = 0; v < 5; ++v) {
+                    const float zt = z[(u * 5 + v) * 64];
 #pragma unroll
-                    for (int j = 0; j < GD_SW; ++j) acc[4 - u][j] = fmaf(xr[j + v], z[u * 5 + v], acc[4 - u][j]);
+                    for (int j = 0; j < GD_SW; ++j) acc[4 - u][j] = fmaf(xr[j + v], zt, acc[4 - u][j]);
+                }
         }
         {   // 5x3 on x21 row t -> output rows t-u
             const float* x2 = xs + W11 * 64;
@@ -106,9 +107,11 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 2) groupdw_tma_kernel(const
 #pragma unroll
             for (int u = 0; u < 5; ++u)
 #pragma unroll
-                for (int v = 0; v < 3; ++v)
+                for (int v = 0; v < 3; ++v) {
+                    const float zt = z[(40 + u * 3 + v) * 64];
 #pragma unroll
-                    for (int j = 0; j < GD_SW; ++j) acc[4 - u][j] = fmaf(xr[j + v], z[40 + u * 3 + v], acc[4 - u][j]);
+                    for (int j = 0; j < GD_SW; ++j) acc[4 - u][j] = fmaf(xr[j + v], zt, acc[4 - u][j]);
+                }
         }
         if (t >= 2 && t - 2 < H12) {  // 3x5 on x12 row t-2 -> output rows t-2-u (ring slots 2-u)
             const float* x3 = xs + (W11 + W21) * 64;
@@ -118,9 +121,11 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 2) groupdw_tma_kernel(const
 #pragma unroll
             for (int u = 0; u < 3; ++u)
 #pragma unroll
-                for (int v = 0; v < 5; ++v)
+                for (int v = 0; v < 5; ++v) {
+                    const float zt = z[(25 + u * 5 + v) * 64];
 #pragma unroll
-                    for (int j = 0; j < GD_SW; ++j) acc[2 - u][j] = fmaf(xr[j + v], z[25 + u * 5 + v], acc[2 - u][j]);
+                    for (int j = 0; j < GD_SW; ++j) acc[2 - u][j] = fmaf(xr[j + v], zt, acc[2 - u][j]);
+                }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp is done reading the stage
@@ -159,7 +164,7 @@ int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaS
     p.z11 = a.z11; p.z12 = a.z12; p.z21 = a.z21; p.out = a.out;
     p.nx = a.nx; p.nz = a.nz; p.n_out = a.n_out; p.C = a.C; p.F = F; p.nstrips = 3;
     p.w0 = w0; p.w1 = w1; p.w2 = w2;
-    const int smem = GD_STAGES * (3 * F - 8) * 256 + 2 * GD_STAGES * 8 + 128;
+    const int smem = GD_STAGES * (3 * F - 8) * 256 + 55 * 64 * 4 + 2 * GD_STAGES * 8 + 128;
     static int smem_set = 0;
     if (smem > smem_set) {
         USOT_CUDA_OK(cudaFuncSetAttribute(groupdw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
