@@ -122,6 +122,7 @@ def workload_config(args, sample_note=None):
     c = {"workload": f"USOT.track(x): batch={args.batch} synthetic 255x255x3 search crops per GPU, ResNet-50 backbone+neck -> cls/reg encoders -> "
                      "fused depthwise xcorr (template batch 1) -> cls/reg towers+heads (BASELINE.json configs[1])",
          "batch_per_gpu": args.batch, "search_size": 255, "template_size": 127, "precision": args.precision,
+         **({"tunables": args.tunable} if getattr(args, "tunable", None) else {}),
          "l2": "inputs (200 MB/step) and activations (>5 GB/step) exceed the 126 MB L2; no explicit flush"}
     if sample_note:
         c["sample"] = sample_note
@@ -137,6 +138,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--precision", default=os.environ.get("USOT_B200_PRECISION", "fp16x3"), choices=["fp32", "fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tunable", action="append", default=[], help="name=value performance knob (usot_set_tunable), repeatable; A/B runs only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -153,6 +155,9 @@ def main():
     from usot_b200 import USOT, _lib, build
     from usot_b200.synth import synthetic_inputs, synthetic_state_dict
     build.build()
+    for kv in args.tunable:
+        name, val = kv.split("=")
+        _lib.check(_lib.load().usot_set_tunable(name.encode(), int(val)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

@@ -16,6 +16,7 @@
  * Reference interfaces replaced (file:line under /root/reference):
  *   usot_prroi_pool_forward          <- prroi_pooling_forward_cuda       lib/models/prroi_pool/src/prroi_pooling_gpu.c:22-44
  *                                       (+ PrRoIPoolingForwardGpu        lib/models/prroi_pool/src/prroi_pooling_gpu_impl.cu:381-402)
+ *   usot_prroi_pool_backward / _coor_backward <- prroi_pooling_backward_cuda / prroi_pooling_coor_backward_cuda   prroi_pooling_gpu.c:46-107
  *   usot_xcorr_depthwise             <- xcorr_depthwise                  lib/models/connect.py:147-157
  *   usot_groupdw_xcorr               <- GroupDW.forward                  lib/models/connect.py:86-102
  *   usot_conv2d_nhwc                 <- nn.Conv2d + BatchNorm2d (+ReLU)  lib/models/modules.py:37-58, connect.py:20-53
@@ -70,6 +71,18 @@ USOT_API int usot_profile_read(int family, double* out);
 USOT_API int usot_prroi_pool_forward(const float* features, const float* rois, float* output, int n_features, int n_rois,
                                      int channels, int height, int width, int pooled_height, int pooled_width,
                                      float spatial_scale, void* stream);
+
+/* PrRoIPool backward w.r.t. the features (replaces prroi_pooling_backward_cuda, prroi_pooling_gpu.c:46-75; kernel
+ * prroi_pooling_gpu_impl.cu:214-272).  features_diff (n_features,C,H,W) is zeroed and then accumulated with atomics. */
+USOT_API int usot_prroi_pool_backward(const float* rois, const float* output_diff, float* features_diff, int n_features, int n_rois,
+                                      int channels, int height, int width, int pooled_height, int pooled_width, float spatial_scale,
+                                      void* stream);
+
+/* PrRoIPool backward w.r.t. the roi coordinates (replaces prroi_pooling_coor_backward_cuda, prroi_pooling_gpu.c:77-107; kernel
+ * prroi_pooling_gpu_impl.cu:274-379).  rois_diff (n_rois,5): column 0 (batch index) is 0. */
+USOT_API int usot_prroi_pool_coor_backward(const float* features, const float* rois, const float* output, const float* output_diff,
+                                           float* rois_diff, int n_rois, int channels, int height, int width, int pooled_height,
+                                           int pooled_width, float spatial_scale, void* stream);
 
 /* Depth-wise cross-correlation, reference layout.  x (bx,C,hx,wx), kernel (bk,C,hk,wk) with bk == bx or bk == 1
  * (broadcast, the view trick of connect.py:151-156); out (bx,C,hx-hk+1,wx-wk+1). */

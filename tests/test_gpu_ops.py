@@ -157,3 +157,52 @@ def test_conv2d_nhwc(ops, case, precision):
     err = rel_err(ours, ref)
     print(precision, case[:6], f"{err:.2e}")
     assert err <= CONV_TOL[precision]
+
+
+def _ref_prroi_backward(features, rois, out, grad_out, ph, pw, scale, coor):
+    """The reference's own backward kernels (oracle/_ref, prroi_pooling_gpu_impl.cu:404-443) through ctypes."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libprroi_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libprroi_ref.so not built (make -C oracle)")
+    lib = ctypes.CDLL(path)
+    f, r, o, g = [t.cuda().contiguous() for t in (features, rois, out, grad_out)]
+    n, c, h, w = f.shape
+    res = torch.zeros_like(r) if coor else torch.zeros_like(f)
+    fn = lib.PrRoIPoolingCoorBackwardGpu if coor else lib.PrRoIPoolingBackwardGpu
+    P = ctypes.c_void_p
+    fn.argtypes = [P] * 6 + [ctypes.c_int] * 5 + [ctypes.c_float, ctypes.c_int, ctypes.c_int]
+    fn(P(torch.cuda.current_stream().cuda_stream), P(f.data_ptr()), P(r.data_ptr()), P(o.data_ptr()), P(g.data_ptr()), P(res.data_ptr()),
+       c, h, w, ph, pw, ctypes.c_float(scale), o.numel(), res.numel())
+    torch.cuda.synchronize()
+    return res.cpu()
+
+
+@pytest.mark.parametrize("h,n", [(15, 3), (31, 4)])
+def test_prroi_backward_vs_reference_kernels(ops, h, n):
+    g = torch.Generator().manual_seed(17 + h)
+    feat = torch.randn(n, 64, h, h, generator=g)
+    lo = torch.rand(n, 2, generator=g) * (h / 2) - 1.0
+    sz = torch.rand(n, 2, generator=g) * (h / 2) + 0.5
+    rois = torch.cat([torch.arange(n).float().view(-1, 1), lo, lo + sz], 1)
+    grad_out = torch.randn(n, 64, 7, 7, generator=g)
+    f = feat.cuda().requires_grad_(True)
+    r = rois.cuda().requires_grad_(True)
+    out = ops.prroi_pool2d(f, r, 7, 7, 1.0)
+    out.backward(grad_out.cuda())
+    ref_f = _ref_prroi_backward(feat, rois, out.detach().cpu(), grad_out, 7, 7, 1.0, coor=False)
+    ref_r = _ref_prroi_backward(feat, rois, out.detach().cpu(), grad_out, 7, 7, 1.0, coor=True)
+    assert rel_err(f.grad, ref_f) <= 1e-5      # atomics: summation order differs
+    assert rel_err(r.grad[:, 1:], ref_r[:, 1:]) <= 1e-4
+    assert float(r.grad[:, 0].abs().max()) == 0.0
+
+
+def test_prroi_backward_is_the_adjoint_of_forward(ops):
+    """Size-independent property: forward is linear in the features, so <P f, g> == <f, P^T g>."""
+    torch.manual_seed(3)
+    f = torch.randn(8, 256, 31, 31, device="cuda", requires_grad=True)
+    rois = torch.cat([torch.arange(8.0).view(-1, 1), torch.rand(8, 2) * 10 + 2, torch.rand(8, 2) * 10 + 15], 1).cuda()
+    g = torch.randn(8, 256, 7, 7, device="cuda")
+    out = ops.prroi_pool2d(f, rois, 7, 7, 1.0)
+    out.backward(g)
+    lhs, rhs = float((out.detach().double() * g.double()).sum()), float((f.detach().double() * f.grad.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))

@@ -33,6 +33,8 @@ SIGNATURES = {
     "usot_profile_family_name": (ctypes.c_char_p, [_I]),
     "usot_profile_read": (_I, [_I, ctypes.POINTER(ctypes.c_double)]),
     "usot_prroi_pool_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "usot_prroi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "usot_prroi_pool_coor_backward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "usot_xcorr_depthwise": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "usot_groupdw_xcorr": (_I, [_P] * 8 + [_I] * 5 + [_P]),
     "usot_conv2d_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P]),

@@ -93,6 +93,10 @@ int launch_tracker_post(const float* cls, const float* cls_mem, const float* bbo
                         double tw, double th, float ratio, double penalty_k, double window_influence, double* result, cudaStream_t st);
 int launch_cycle_glue(const float* off_cls, const float* mem_cls, const float* off_bbox, int n, int R, int search_size, int sf_size,
                       float ratio, float* pool_box, float* best_score, int* best_idx, cudaStream_t st);
+int launch_prroi_backward(const float* rois, const float* top_diff, float* bottom_diff, int n_features, int n_rois, int C, int H, int W,
+                          int PH, int PW, float scale, cudaStream_t st);
+int launch_prroi_coor_backward(const float* feat, const float* rois, const float* top, const float* top_diff, float* rois_diff, int n_rois,
+                               int C, int H, int W, int PH, int PW, float scale, cudaStream_t st);
 int launch_bce(const float* pred, const float* label, int count, float* out, cudaStream_t st);
 int launch_iou(const float* bbox, const float* target, const float* weight, int n, int cells, float* out, cudaStream_t st);
 int launch_center_crop_nhwc(const float* in, int n, int h, int w, int c, int l, float* out, cudaStream_t st);

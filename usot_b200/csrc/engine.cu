@@ -660,6 +660,23 @@ int usot_prroi_pool_forward(const float* features, const float* rois, float* out
                              (cudaStream_t)stream);
 }
 
+int usot_prroi_pool_backward(const float* rois, const float* output_diff, float* features_diff, int n_features, int n_rois, int channels,
+                             int height, int width, int pooled_height, int pooled_width, float spatial_scale, void* stream) {
+    USOT_REQUIRE(features_diff && (n_rois == 0 || (rois && output_diff)), "null pointer");
+    USOT_REQUIRE(n_features >= 0 && n_rois >= 0 && channels > 0 && height > 0 && width > 0 && pooled_height > 0 && pooled_width > 0, "bad shape");
+    return launch_prroi_backward(rois, output_diff, features_diff, n_features, n_rois, channels, height, width, pooled_height, pooled_width,
+                                 spatial_scale, (cudaStream_t)stream);
+}
+
+int usot_prroi_pool_coor_backward(const float* features, const float* rois, const float* output, const float* output_diff, float* rois_diff,
+                                  int n_rois, int channels, int height, int width, int pooled_height, int pooled_width, float spatial_scale,
+                                  void* stream) {
+    USOT_REQUIRE(n_rois == 0 || (features && rois && output && output_diff && rois_diff), "null pointer");
+    USOT_REQUIRE(n_rois >= 0 && channels > 0 && height > 0 && width > 0 && pooled_height > 0 && pooled_width > 0, "bad shape");
+    return launch_prroi_coor_backward(features, rois, output, output_diff, rois_diff, n_rois, channels, height, width, pooled_height,
+                                      pooled_width, spatial_scale, (cudaStream_t)stream);
+}
+
 int usot_xcorr_depthwise(const float* x, const float* kernel, float* out, int bx, int bk, int channels, int hx, int wx, int hk, int wk,
                          void* stream) {
     USOT_REQUIRE(x && kernel && out, "null pointer");

@@ -187,6 +187,121 @@ __global__ void __launch_bounds__(1024) iou_kernel(const float* __restrict__ bbo
     if (threadIdx.x == 0) *out = (float)(s / cnt);
 }
 
+// =============================================================================================
+// PrRoIPool backward (reference layouts: NCHW features, rois (n,5))      prroi_pooling_gpu_impl.cu:214-379
+// =============================================================================================
+static __device__ __forceinline__ float pr_g(float lim, float a) { return lim - 0.5f * lim * lim - a + 0.5f * a * a; }
+static __device__ __forceinline__ void pr_scatter(float* g, int h, int w, int H, int W, float v) {
+    if (h >= 0 && w >= 0 && h < H && w < W) atomicAdd(g + h * W + w, v);
+}
+struct PrBin { float ws_w, ws_h, we_w, we_h, win; };
+static __device__ __forceinline__ PrBin pr_bin(const float* r, int ph, int pw, int PH, int PW, float scale) {
+    const float sw = r[1] * scale, sh = r[2] * scale, ew = r[3] * scale, eh = r[4] * scale;
+    const float bw = fmaxf(ew - sw, 0.f) / (float)PW, bh = fmaxf(eh - sh, 0.f) / (float)PH;
+    PrBin b;
+    b.ws_w = sw + bw * pw; b.ws_h = sh + bh * ph; b.we_w = b.ws_w + bw; b.we_h = b.ws_h + bh;
+    b.win = fmaxf(0.f, bw * bh);
+    return b;
+}
+
+// d(out)/d(features): the forward's corner coefficients, scattered with atomics (several bins / rois touch the same cell)
+__global__ void prroi_backward_kernel(const float* __restrict__ rois, const float* __restrict__ top_diff, float* __restrict__ bottom_diff,
+                                      size_t total, int C, int H, int W, int PH, int PW, float scale) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int pw = idx % PW, ph = (idx / PW) % PH, c = (idx / ((size_t)PW * PH)) % C;
+    const int n = idx / ((size_t)PW * PH * C);
+    const float* r = rois + (size_t)n * 5;
+    const PrBin b = pr_bin(r, ph, pw, PH, PW, scale);
+    if (b.win == 0.f) return;
+    const float g = top_diff[idx] / b.win;
+    float* dst = bottom_diff + ((size_t)(int)r[0] * C + c) * H * W;
+    const int s_w = (int)floorf(b.ws_w), e_w = (int)ceilf(b.we_w), s_h = (int)floorf(b.ws_h), e_h = (int)ceilf(b.we_h);
+    for (int wi = s_w; wi < e_w; ++wi)
+        for (int hi = s_h; hi < e_h; ++hi) {
+            const float y0 = fmaxf(b.ws_h, (float)hi), x0 = fmaxf(b.ws_w, (float)wi);
+            const float y1 = fminf(b.we_h, (float)hi + 1.f), x1 = fminf(b.we_w, (float)wi + 1.f);
+            const float ax = pr_g(x1 - wi, x0 - wi), ay = pr_g(y1 - hi, y0 - hi);
+            const float bx = pr_g((float)(wi + 1) - x0, (float)(wi + 1) - x1), by = pr_g((float)(hi + 1) - y0, (float)(hi + 1) - y1);
+            pr_scatter(dst, hi, wi, H, W, g * (ax * ay));
+            pr_scatter(dst, hi, wi + 1, H, W, g * (bx * ay));
+            pr_scatter(dst, hi + 1, wi, H, W, g * (ax * by));
+            pr_scatter(dst, hi + 1, wi + 1, H, W, g * (bx * by));
+        }
+}
+
+static __device__ __forceinline__ float pr_at(const float* d, int h, int w, int H, int W) {
+    return (h < 0 || w < 0 || h >= H || w >= W) ? 0.f : d[h * W + w];
+}
+static __device__ float pr_bilinear(const float* d, float h, float w, int H, int W) {  // zero outside the map
+    const int h0 = (int)floorf(h), w0 = (int)floorf(w);
+    const float dh = h - (float)h0, dw = w - (float)w0;
+    return pr_at(d, h0, w0, H, W) * ((1.f - dh) * (1.f - dw)) + pr_at(d, h0 + 1, w0, H, W) * (dh * (1.f - dw)) +
+           pr_at(d, h0, w0 + 1, H, W) * ((1.f - dh) * dw) + pr_at(d, h0 + 1, w0 + 1, H, W) * (dh * dw);
+}
+// integral over [s,t] of the linear interpolant between c1 (at 0) and c2 (at 1); double sub-expressions as in the reference
+static __device__ __forceinline__ float pr_edge(float s, float t, float c1, float c2) {
+    return (float)(0.5 * (double)(t * t - s * s) * (double)c2 + ((double)t - 0.5 * (double)(t * t) - (double)s + 0.5 * (double)(s * s)) * (double)c1);
+}
+
+// d(out)/d(x1,y1,x2,y2): line integrals of the interpolant along the four bin edges (Leibniz rule)
+__global__ void prroi_coor_backward_kernel(const float* __restrict__ feat, const float* __restrict__ rois, const float* __restrict__ top,
+                                           const float* __restrict__ top_diff, float* __restrict__ rois_diff, size_t total, int C, int H,
+                                           int W, int PH, int PW, float scale) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int pw = idx % PW, ph = (idx / PW) % PH, c = (idx / ((size_t)PW * PH)) % C;
+    const int n = idx / ((size_t)PW * PH * C);
+    const float* r = rois + (size_t)n * 5;
+    const PrBin b = pr_bin(r, ph, pw, PH, PW, scale);
+    const float go = top_diff[idx];
+    if (b.win == 0.f || go / b.win == 0.f) return;  // (the reference skips zero upstream gradients, :323-325)
+    const float* d = feat + ((size_t)(int)r[0] * C + c) * H * W;
+    const int s_w = (int)floorf(b.ws_w), e_w = (int)ceilf(b.we_w), s_h = (int)floorf(b.ws_h), e_h = (int)ceilf(b.we_h);
+    float gx1 = 0.f, gx2 = 0.f, gy1 = 0.f, gy2 = 0.f;
+    for (int hi = s_h; hi < e_h; ++hi) {
+        const float s = fmaxf(b.ws_h, (float)hi) - hi, t = fminf(b.we_h, (float)(hi + 1)) - hi;
+        gx1 += pr_edge(s, t, pr_bilinear(d, (float)hi, b.ws_w, H, W), pr_bilinear(d, (float)(hi + 1), b.ws_w, H, W));
+        gx2 += pr_edge(s, t, pr_bilinear(d, (float)hi, b.we_w, H, W), pr_bilinear(d, (float)(hi + 1), b.we_w, H, W));
+    }
+    for (int wi = s_w; wi < e_w; ++wi) {
+        const float s = fmaxf(b.ws_w, (float)wi) - wi, t = fminf(b.we_w, (float)(wi + 1)) - wi;
+        gy1 += pr_edge(s, t, pr_bilinear(d, b.ws_h, (float)wi, H, W), pr_bilinear(d, b.ws_h, (float)(wi + 1), H, W));
+        gy2 += pr_edge(s, t, pr_bilinear(d, b.we_h, (float)wi, H, W), pr_bilinear(d, b.we_h, (float)(wi + 1), H, W));
+    }
+    const float o = top[idx];
+    float px1 = -gx1 + (b.we_h - b.ws_h) * o, py1 = -gy1 + (b.we_w - b.ws_w) * o;
+    float px2 = gx2 - (b.we_h - b.ws_h) * o, py2 = gy2 - (b.we_w - b.ws_w) * o;
+    px1 = px1 / b.win * scale; px2 = px2 / b.win * scale; py1 = py1 / b.win * scale; py2 = py2 / b.win * scale;
+    float* g = rois_diff + (size_t)n * 5;
+    const double fw0 = (double)((float)pw / PW), fw1 = (double)((float)(pw + 1) / PW);
+    const double fh0 = (double)((float)ph / PH), fh1 = (double)((float)(ph + 1) / PH);
+    atomicAdd(g + 1, (float)(((double)px1 * (1.0 - fw0) + (double)px2 * (1.0 - fw1)) * (double)go));
+    atomicAdd(g + 2, (float)(((double)py1 * (1.0 - fh0) + (double)py2 * (1.0 - fh1)) * (double)go));
+    atomicAdd(g + 3, (float)(((double)(px2 * (float)(pw + 1) / PW) + (double)(px1 * (float)pw / PW)) * (double)go));
+    atomicAdd(g + 4, (float)(((double)(py2 * (float)(ph + 1) / PH) + (double)(py1 * (float)ph / PH)) * (double)go));
+}
+
+int launch_prroi_backward(const float* rois, const float* top_diff, float* bottom_diff, int n_features, int n_rois, int C, int H, int W,
+                          int PH, int PW, float scale, cudaStream_t st) {
+    USOT_CUDA_OK(cudaMemsetAsync(bottom_diff, 0, (size_t)n_features * C * H * W * sizeof(float), st));
+    const size_t total = (size_t)n_rois * C * PH * PW;
+    if (total == 0) return 0;
+    prroi_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(rois, top_diff, bottom_diff, total, C, H, W, PH, PW, scale);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_prroi_coor_backward(const float* feat, const float* rois, const float* top, const float* top_diff, float* rois_diff, int n_rois,
+                               int C, int H, int W, int PH, int PW, float scale, cudaStream_t st) {
+    USOT_CUDA_OK(cudaMemsetAsync(rois_diff, 0, (size_t)n_rois * 5 * sizeof(float), st));
+    const size_t total = (size_t)n_rois * C * PH * PW;
+    if (total == 0) return 0;
+    prroi_coor_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(feat, rois, top, top_diff, rois_diff, total, C, H, W, PH, PW, scale);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_bce(const float* pred, const float* label, int count, float* out, cudaStream_t st) {
     bce_kernel<<<1, 1024, 0, st>>>(pred, label, count, out);
     USOT_CUDA_OK(cudaGetLastError());

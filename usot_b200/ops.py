@@ -39,17 +39,47 @@ def nhwc_view(t_nhwc):
     return t_nhwc.permute(0, 3, 1, 2)
 
 
+class PrRoIPool2DFunction(torch.autograd.Function):
+    """Forward + both backward passes of Precise RoI Pooling, same contract as lib/models/prroi_pool/functional.py:41-81."""
+
+    @staticmethod
+    def forward(ctx, features, rois, pooled_height, pooled_width, spatial_scale):
+        _need_float(features, rois)
+        _need_cuda(features, rois)
+        pooled_height, pooled_width, spatial_scale = int(pooled_height), int(pooled_width), float(spatial_scale)
+        features, rois = features.contiguous(), rois.contiguous()
+        n, c, h, w = features.shape
+        out = torch.empty((rois.shape[0], c, pooled_height, pooled_width), dtype=torch.float32, device=features.device)
+        with torch.cuda.device(features.device):
+            _lib.check(_lib.load().usot_prroi_pool_forward(_lib.ptr(features), _lib.ptr(rois), _lib.ptr(out), n, rois.shape[0], c, h, w,
+                                                           pooled_height, pooled_width, spatial_scale, _stream(features)))
+        ctx.params = (pooled_height, pooled_width, spatial_scale)
+        ctx.save_for_backward(features, rois, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        features, rois, out = ctx.saved_tensors
+        ph, pw, scale = ctx.params
+        n, c, h, w = features.shape
+        grad_input = grad_coor = None
+        grad_output = grad_output.contiguous().float()
+        lib = _lib.load()
+        with torch.cuda.device(features.device):
+            if ctx.needs_input_grad[0]:
+                grad_input = torch.empty_like(features)
+                _lib.check(lib.usot_prroi_pool_backward(_lib.ptr(rois), _lib.ptr(grad_output), _lib.ptr(grad_input), n, rois.shape[0], c, h, w,
+                                                        ph, pw, scale, _stream(features)))
+            if ctx.needs_input_grad[1]:
+                grad_coor = torch.empty_like(rois)
+                _lib.check(lib.usot_prroi_pool_coor_backward(_lib.ptr(features), _lib.ptr(rois), _lib.ptr(out), _lib.ptr(grad_output),
+                                                             _lib.ptr(grad_coor), rois.shape[0], c, h, w, ph, pw, scale, _stream(features)))
+        return grad_input, grad_coor, None, None, None
+
+
 def prroi_pool2d(features, rois, pooled_height, pooled_width, spatial_scale):
-    _need_float(features, rois)
-    _need_cuda(features, rois)
-    pooled_height, pooled_width, spatial_scale = int(pooled_height), int(pooled_width), float(spatial_scale)
-    features, rois = features.contiguous(), rois.contiguous()
-    n, c, h, w = features.shape
-    out = torch.empty((rois.shape[0], c, pooled_height, pooled_width), dtype=torch.float32, device=features.device)
-    with torch.cuda.device(features.device):
-        _lib.check(_lib.load().usot_prroi_pool_forward(_lib.ptr(features), _lib.ptr(rois), _lib.ptr(out), n, rois.shape[0], c, h, w,
-                                                       pooled_height, pooled_width, spatial_scale, _stream(features)))
-    return out
+    """Drop-in for lib.models.prroi_pool.functional.prroi_pool2d (differentiable w.r.t. features and roi coordinates)."""
+    return PrRoIPool2DFunction.apply(features, rois, pooled_height, pooled_width, spatial_scale)
 
 
 def xcorr_depthwise(x, kernel):
