@@ -253,6 +253,8 @@ def main():
         conv, xc = prof["conv"], prof["groupdw_xcorr"]
         conv_tflops = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
         xc_gbs = xc["bytes"] / (xc["ms"] / 1e3) / 1e9 if xc["ms"] > 0 else 0.0
+        pr = prof["pred_conv"]
+        pr_gbs = pr["bytes"] / (pr["ms"] / 1e3) / 1e9 if pr["ms"] > 0 else 0.0
         step_ms_prof = sum(f["ms"] for f in prof.values()) / nprof
         traffic = {}
         tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
@@ -280,10 +282,14 @@ def main():
                          "mma_per_algorithmic_flop": mma_per_flop,
                          "launches_per_step": conv["launches"] // nprof, "share_of_step": conv["ms"] / nprof / step_ms_prof if step_ms_prof else None,
                          "algorithmic_gflop_per_step": conv["flops"] / nprof / 1e9},
-            "xcorr_roofline": {"kernel": "groupdw_tma_kernel (fused 3-scale depthwise xcorr, TMA ring)", "bound": "hbm", "achieved": xc_gbs, "peak": pk["hbm_gbs"],
+            "xcorr_roofline": {"kernel": "groupdw_ffma2_kernel (fused 3-scale depthwise xcorr, TMA ring + packed fma.rn.f32x2)", "bound": "hbm", "achieved": xc_gbs, "peak": pk["hbm_gbs"],
                                "unit": "GB/s", "frac": xc_gbs / pk["hbm_gbs"],
-                               "traffic": traffic.get("groupdw_tma_kernel", {}).get("traffic_bytes_per_launch"), "launches_per_step": xc["launches"] // nprof,
-                               "algorithmic_mb_per_launch": xc["bytes"] / max(xc["launches"], 1) / 1e6},
+                               "traffic": traffic.get("groupdw_ffma2_kernel", traffic.get("groupdw_tma_kernel", {})).get("traffic_bytes_per_launch"),
+                               "launches_per_step": xc["launches"] // nprof, "algorithmic_mb_per_launch": xc["bytes"] / max(xc["launches"], 1) / 1e6},
+            "pred_roofline": {"kernel": "pred_gemm_kernel<4>/<1> (bbox_pred / cls_pred 3x3 heads, TMA-streamed per image)", "bound": "hbm",
+                              "achieved": pr_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": pr_gbs / pk["hbm_gbs"],
+                              "traffic": traffic.get("pred_gemm_kernel", {}).get("traffic_bytes_per_launch"),
+                              "launches_per_step": pr["launches"] // nprof, "algorithmic_mb_per_launch": pr["bytes"] / max(pr["launches"], 1) / 1e6},
             "backbone_flop_frac": value / world * GFLOP_BACKBONE_NECK * 1e9 / (pk["tflops_sustained"] * 1e12),
             "kernel_ms_per_step": {k: v["ms"] / nprof for k, v in prof.items() if v["launches"]},
         }

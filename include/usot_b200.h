@@ -20,6 +20,7 @@
  *   usot_xcorr_depthwise             <- xcorr_depthwise                  lib/models/connect.py:147-157
  *   usot_groupdw_xcorr               <- GroupDW.forward                  lib/models/connect.py:86-102
  *   usot_conv2d_nhwc                 <- nn.Conv2d + BatchNorm2d (+ReLU)  lib/models/modules.py:37-58, connect.py:20-53
+ *   usot_pred_conv                   <- bbox_pred / cls_pred / cls_memory_pred + their epilogues   lib/models/connect.py:235-241,274-275
  *   usot_engine_template             <- USOT_.template                   lib/models/models.py:173-177
  *   usot_engine_track                <- USOT_.track                      lib/models/models.py:179-198
  *   usot_engine_extract_memory_feature <- USOT_.extract_memory_feature   lib/models/models.py:200-206
@@ -52,7 +53,8 @@ USOT_API const char* usot_last_error(void);
 USOT_API int usot_abi_version(void);
 /* Process-wide performance knobs (never change results): "groupdw_strips" = 2 | 3; "tc_bn_max" = 64 | 128 | 256;
  * "tc_tma_store" = 0 | 1 (TMA-store epilogue), "tc_tma_res" = 0 | 1 (residual loaded by TMA), "stem_tc" = 0 | 1 (tensor-core stem),
- * "groupdw_tma" = 0 | 1 (TMA-pipelined GroupDW), "graph_max_batch" = 0..64 (track() with n <= this replays a CUDA graph).
+ * "groupdw_tma" = 0 | 1 | 2 (register-staged / TMA ring + scalar FMA / TMA ring + packed FFMA2, default 2),
+ * "pred_tma_min_batch" = 0.. (batches >= this use the TMA-streamed per-image pred-conv kernel, default 48; 0 = never), "graph_max_batch" = 0..64 (track() with n <= this replays a CUDA graph).
  * One accuracy knob: "tc_split_bn_max" = 64 | 128 (default; separate cross-term accumulator) | 256 (single accumulator). */
 USOT_API int usot_set_tunable(const char* name, int value);
 
@@ -101,6 +103,14 @@ USOT_API int usot_groupdw_xcorr(const float* x11, const float* x12, const float*
 USOT_API int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh, int kw,
                               int stride, int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift,
                               const float* residual, int relu, float* out, int precision, void* stream);
+
+/* Skinny prediction conv of the head: 3x3, pad 1, Cin = channels (256), Cout = 1 or 4, with bias, fused with the reference's
+ * epilogue.  in (n,r,r,channels) nhwc; weight (9, cout, channels) with tap = kh*3+kw; out (n,cout,r,r) nchw.
+ *   mode 0:  out = mul * (conv + bias)                          (`0.1 * cls_pred(x)`, connect.py:240-241,274-275)
+ *   mode 1:  out = exp(adjust[0] * (conv + bias) + bias4[co])   (`exp(adjust * bbox_pred(x) + bias)`, connect.py:235-237)
+ * adjust / bias4 are device pointers and may be NULL in mode 0. */
+USOT_API int usot_pred_conv(const float* in, int n, int r, int channels, const float* weight, const float* bias, int cout, int mode,
+                            float mul, const float* adjust, const float* bias4, float* out, void* stream);
 
 USOT_API int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream);
 USOT_API int usot_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, void* stream);

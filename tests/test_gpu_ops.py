@@ -78,12 +78,15 @@ def _groupdw_ref(xs, zs, w, rep):
 
 
 @pytest.mark.parametrize("F_,nx,nz,n_out,strips", [(31, 3, 1, 3, 3), (31, 2, 2, 2, 2), (33, 2, 6, 6, 3), (33, 1, 1, 1, 2), (31, 2, 14, 14, 3),
-                                                   (31, 6, 2, 6, 0), (31, 3, 1, 3, 0), (33, 2, 6, 6, 0), (31, 2, 14, 14, 0)])
+                                                   (31, 6, 2, 6, 0), (31, 3, 1, 3, 0), (33, 2, 6, 6, 0), (31, 2, 14, 14, 0),
+                                                   (29, 2, 1, 2, 0), (27, 3, 3, 3, 0),
+                                                   (31, 6, 2, 6, -1), (33, 2, 6, 6, -1), (31, 2, 14, 14, -1)])
 def test_groupdw_fused(ops, F_, nx, nz, n_out, strips):
-    """strips = 0 selects the TMA-pipelined kernel (default); 2 / 3 the register-staged variants."""
+    """strips = 0 selects the TMA-pipelined packed-FFMA2 kernel (default), -1 the scalar-FMA TMA kernel; 2 / 3 the
+    register-staged variants.  F = 29 / 27 exercise the masked (ragged last strip) path of the default kernel."""
     from usot_b200 import _lib
-    _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 1 if strips == 0 else 0))
-    if strips:
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 2 if strips == 0 else (1 if strips < 0 else 0)))
+    if strips > 0:
         _lib.check(_lib.load().usot_set_tunable(b"groupdw_strips", strips))
     g = torch.Generator().manual_seed(F_ + nx)
     C = 256
@@ -97,7 +100,26 @@ def test_groupdw_fused(ops, F_, nx, nz, n_out, strips):
     assert ours.shape == ref.shape
     assert rel_err(ours, ref) <= 3e-6  # pure fp32 FMA, only the summation order differs
     _lib.check(_lib.load().usot_set_tunable(b"groupdw_strips", 3))
-    _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 1))
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 2))
+
+
+@pytest.mark.parametrize("F_", [31, 33, 29])
+def test_groupdw_variants_bit_identical(ops, F_):
+    """The three GroupDW kernels accumulate every output element in the same order with IEEE fma.rn (FFMA2 = two independent
+    fma.rn), so they must agree bit for bit."""
+    from usot_b200 import _lib
+    g = torch.Generator().manual_seed(F_)
+    C, nx = 256, 5
+    xs = [torch.randn(nx, F_ - 2, F_ - 2, C, generator=g).cuda(), torch.randn(nx, F_ - 4, F_ - 2, C, generator=g).cuda(),
+          torch.randn(nx, F_ - 2, F_ - 4, C, generator=g).cuda()]
+    zs = [torch.randn(1, 5, 5, C, generator=g).cuda(), torch.randn(1, 3, 5, C, generator=g).cuda(), torch.randn(1, 5, 3, C, generator=g).cuda()]
+    w = torch.tensor([0.1, 0.7, -0.4]).cuda()
+    outs = []
+    for mode in (2, 1, 0):
+        _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", mode))
+        outs.append(ops.groupdw_xcorr(xs, zs, w, nx).clone())
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 2))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 def test_groupdw_linearity_full_size(ops):
@@ -115,6 +137,26 @@ def test_groupdw_linearity_full_size(ops):
     # and sample 17 of the batch equals the same sample run alone (no cross-sample leakage)
     y17 = ops.groupdw_xcorr([t[17:18].contiguous() for t in xa], zs, w, 1)
     assert torch.equal(y17[0], ya[17])
+
+
+@pytest.mark.parametrize("cout,mode,r,n,min_batch", [(4, 1, 25, 3, 1), (1, 0, 25, 5, 1), (4, 1, 27, 2, 1), (1, 0, 27, 2, 1), (4, 1, 19, 2, 1),
+                                                      (1, 0, 9, 3, 1), (4, 1, 25, 3, 0), (1, 0, 25, 3, 0), (4, 1, 25, 70, 48)])
+def test_pred_conv(ops, cout, mode, r, n, min_batch):
+    """bbox_pred / cls_pred heads (connect.py:235-241): TMA-streamed per-image kernel (min_batch >= 1 forces it at these small
+    batches; 48 is the default dispatch) and the warp-per-pixel kernel (min_batch = 0) against torch fp32."""
+    from usot_b200 import _lib
+    _lib.check(_lib.load().usot_set_tunable(b"pred_tma_min_batch", min_batch))
+    g = torch.Generator().manual_seed(100 * cout + r)
+    x = torch.randn(n, r, r, 256, generator=g)
+    w = torch.randn(cout, 256, 3, 3, generator=g) * 0.02
+    b = torch.randn(cout, generator=g) * 0.1
+    adjust, bias4 = torch.tensor([0.7]), torch.randn(1, 4, 1, 1, generator=g) * 0.3
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1)
+    ref = (0.1 * y if mode == 0 else torch.exp(adjust.double() * y + bias4.double())).float()
+    ours = ops.pred_conv(x.cuda(), w.cuda(), b.cuda(), mode=mode, mul=0.1, adjust=adjust.cuda(), bias4=bias4.cuda()).cpu()
+    _lib.check(_lib.load().usot_set_tunable(b"pred_tma_min_batch", 48))
+    assert ours.shape == ref.shape
+    assert rel_err(ours, ref) <= 5e-6
 
 
 CONV_CASES = [

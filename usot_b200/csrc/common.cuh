@@ -25,6 +25,22 @@ void set_error(const std::string& msg);
         }                                                                                       \
     } while (0)
 
+// Opt-in dynamic shared memory is a per-device function attribute: remember, per device, the largest size already granted
+// (engines of several devices may live in one process, e.g. DataParallel-style replicas).
+struct SmemAttrCache {
+    int granted[64] = {0};
+    template <typename Kernel>
+    int ensure(Kernel kernel, int bytes) {
+        int dev = 0;
+        USOT_CUDA_OK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || bytes > granted[dev]) {
+            USOT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            if (dev >= 0 && dev < 64) granted[dev] = bytes;
+        }
+        return 0;
+    }
+};
+
 // ---- activation storage ------------------------------------------------------------------
 // All internal activations are NHWC.  Two storage formats:
 //   F32   : one fp32 plane (SIMT path, bandwidth kernels)
@@ -81,6 +97,11 @@ int launch_xcorr_nchw(const float* x, const float* k, float* out, int nx, int nk
 // Skinny prediction conv 3x3 p1, Cin = C, Cout <= 4, NHWC in -> NCHW out.  mode 0: out = mul*(y+b) ; mode 1: exp(adjust*(y+b)+bias4[co])
 int launch_pred_conv(const float* in, int n, int r, int C, const float* w /*[9][cout][C]*/, const float* b, int cout,
                      int mode, float mul, const float* adjust, const float* bias4, float* out_nchw, cudaStream_t st);
+// TMA-streamed per-image variant for large batches (pred_tma.cu); launch_pred_conv dispatches to it when supported
+extern int g_pred_tma_min_batch;
+bool pred_tma_supported(int n, int r, int C, int cout);
+int launch_pred_tma(const float* in, int n, int r, int C, const float* w, const float* b, int cout, int mode, float mul,
+                    const float* adjust, const float* bias4, float* out_nchw, cudaStream_t st);
 int launch_conf_fusion(const float* conf, const float* value, int b, int nq, size_t per_map /*R*R*C*/, float* out,
                        cudaStream_t st);
 int launch_prroi_nhwc(const float* feat, int n_feat, int h, int w, int c, const float* boxes4, int n_rois, float* out_nhwc,

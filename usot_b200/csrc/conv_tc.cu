@@ -446,11 +446,8 @@ template <int BN, bool SPLIT>
 static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     using Cfg = TcCfg<BN, SPLIT>;
     static_assert(Cfg::STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
-    static bool attr = false;
-    if (!attr) {
-        USOT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    static SmemAttrCache attr;
+    if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT>, 227 * 1024)) return rc;
     if (!Cfg::TMA_OUT) { p.tma_store = 0; p.tma_res = 0; }
     if (p.tma_res && Cfg::STAGES_RES < 2) p.tma_res = 0;
     p.nbuf = p.tma_res ? 3 : 1;

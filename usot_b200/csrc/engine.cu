@@ -505,7 +505,9 @@ static int pred(Ctx& c, const PredW& pw, const T& in, int mode, float* out) {
     Arena& ar = c.ar;
     usot_engine* e = c.e;
     if (!ar.plan) {
-        Scope sc(FAM_PRED, c.st, 2.0 * in.n * in.h * in.w * 256.0 * 9 * pw.cout);
+        // algorithmic bytes: the tower output read once, the (n,cout,R,R) map written once, the weights once
+        Scope sc(FAM_PRED, c.st, 2.0 * in.n * in.h * in.w * 256.0 * 9 * pw.cout,
+                 4.0 * ((double)in.n * in.h * in.w * (256.0 + pw.cout) + 9.0 * pw.cout * 256));
         RUN(launch_pred_conv(in.f, in.n, in.h, 256, pw.w, pw.b, pw.cout, mode, mode == 0 ? 0.1f : 1.f, e->adjust, e->bias4, out, c.st));
     }
     return 0;
@@ -642,11 +644,12 @@ int usot_set_tunable(const char* name, int value) {
     USOT_REQUIRE(name, "null name");
     if (!strcmp(name, "tc_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_bn_max must be 64, 128 or 256"); g_tc_bn_max = value; return 0; }
     if (!strcmp(name, "graph_max_batch")) { USOT_REQUIRE(value >= 0 && value <= 64, "graph_max_batch must be in [0, 64]"); g_graph_max_batch = value; return 0; }
-    if (!strcmp(name, "groupdw_tma")) { USOT_REQUIRE(value == 0 || value == 1, "groupdw_tma must be 0 or 1"); g_groupdw_tma = value; return 0; }
+    if (!strcmp(name, "groupdw_tma")) { USOT_REQUIRE(value >= 0 && value <= 2, "groupdw_tma must be 0 (register-staged), 1 (TMA ring, scalar FMA) or 2 (TMA ring, packed FFMA2)"); g_groupdw_tma = value; return 0; }
     if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
     if (!strcmp(name, "tc_tma_store")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_store must be 0 or 1"); g_tc_tma_store = value; return 0; }
     if (!strcmp(name, "tc_split_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_split_bn_max must be 64, 128 or 256"); g_tc_split_bn_max = value; return 0; }
+    if (!strcmp(name, "pred_tma_min_batch")) { USOT_REQUIRE(value >= 0, "pred_tma_min_batch must be >= 0 (0 = never use the TMA-streamed pred kernel)"); g_pred_tma_min_batch = value; return 0; }
     if (!strcmp(name, "groupdw_strips")) { USOT_REQUIRE(value == 2 || value == 3, "groupdw_strips must be 2 or 3"); g_groupdw_strips = value; return 0; }
     USOT_REQUIRE(false, "unknown tunable");
 }
@@ -741,6 +744,15 @@ int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float*
     } while (0);
     cudaFree(d_whi); cudaFree(d_wlo); cudaFree(d_scale); cudaFree(d_ihi); cudaFree(d_ilo); cudaFree(d_rhi); cudaFree(d_rlo); cudaFree(d_ohi); cudaFree(d_olo);
     return rc;
+}
+
+int usot_pred_conv(const float* in, int n, int r, int channels, const float* weight, const float* bias, int cout, int mode, float mul,
+                   const float* adjust, const float* bias4, float* out, void* stream) {
+    USOT_REQUIRE(n == 0 || (in && weight && bias && out), "null pointer");
+    USOT_REQUIRE(n >= 0 && r > 0 && channels > 0, "bad shape");
+    USOT_REQUIRE(mode == 0 || (mode == 1 && adjust && bias4), "mode must be 0, or 1 with adjust and bias4");
+    g_prof.launches[FAM_PRED]++;
+    return launch_pred_conv(in, n, r, channels, weight, bias, cout, mode, mul, adjust, bias4, out, (cudaStream_t)stream);
 }
 
 int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream) {

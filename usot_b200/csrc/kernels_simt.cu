@@ -96,11 +96,8 @@ int launch_stem(const float* x, int n, int s, const float* wk, const float* scal
                 cudaStream_t st) {
     const int ho = (s - 7) / 2 + 1;
     const size_t smem = (147 * 64 + 3 * STEM_P * STEM_P) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        USOT_CUDA_OK(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    static SmemAttrCache attr;
+    if (int rc = attr.ensure(stem_kernel, (int)smem)) return rc;
     dim3 grid((ho + STEM_T - 1) / STEM_T, (ho + STEM_T - 1) / STEM_T, n);
     stem_kernel<<<grid, 256, smem, st>>>(x, s, ho, wk, scale, shift, out);
     USOT_CUDA_OK(cudaGetLastError());
@@ -394,7 +391,7 @@ int launch_groupdw(const GroupDWArgs& a, cudaStream_t st) {
 }
 
 int g_groupdw_strips = 3;  // tunable (usot_set_tunable("groupdw_strips", 2|3)) of the register-staged variant
-int g_groupdw_tma = 1;     // tunable: 1 = TMA-pipelined kernel (xcorr_tma.cu), 0 = register-staged kernel below
+int g_groupdw_tma = 2;     // tunable: 2 = TMA ring + packed FFMA2 (xcorr_tma.cu, default), 1 = TMA ring + scalar FMA, 0 = register-staged kernel below
 
 int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
     USOT_REQUIRE(a.nx > 0 && a.nz > 0 && a.n_out % a.nx == 0 && a.n_out % a.nz == 0, "groupdw: n_out must be a multiple of both batches");
@@ -497,6 +494,7 @@ int launch_pred_conv(const float* in, int n, int r, int C, const float* w, const
     USOT_REQUIRE(C % 128 == 0, "pred conv needs C % 128 == 0");
     const int total = n * r * r;
     if (total == 0) return 0;
+    if (pred_tma_supported(n, r, C, cout)) return launch_pred_tma(in, n, r, C, w, b, cout, mode, mul, adjust, bias4, out, st);
     const unsigned grid = (unsigned)((total + 7) / 8);
     if (cout == 1) pred_conv_kernel<1><<<grid, 256, 0, st>>>(in, n, r, C, w, b, mode, mul, adjust, bias4, out);
     else if (cout == 4) pred_conv_kernel<4><<<grid, 256, 0, st>>>(in, n, r, C, w, b, mode, mul, adjust, bias4, out);

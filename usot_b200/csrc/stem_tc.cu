@@ -195,12 +195,9 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const StemParams p) {
 
 int launch_stem_tc(const float* x, int n, int s, const void* w_img, const float* scale_tc, const float* shift, float* out, bool split,
                    cudaStream_t st) {
-    static bool init = false;
-    if (!init) {
-        USOT_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        USOT_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-        init = true;
-    }
+    static SmemAttrCache attr_split, attr_single;
+    if (int rc = attr_split.ensure(stem_tc_kernel<true>, ST_SMEM)) return rc;
+    if (int rc = attr_single.ensure(stem_tc_kernel<false>, ST_SMEM)) return rc;
     StemParams p;
     p.x = x; p.w_img = static_cast<const uint4*>(w_img); p.scale = scale_tc; p.shift = shift; p.out = out;
     p.S = s; p.HO = (s - 7) / 2 + 1;

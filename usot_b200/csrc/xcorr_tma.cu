@@ -144,6 +144,153 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 3) groupdw_tma_kernel(const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: packed-FMA variant (default).  The v1 kernel above is FMA-pipe bound: a 3-register FFMA issues every other cycle per
+// SM sub-partition on sm_100, so its 2.25 GFMA per batch-256 launch cost more than the HBM time of the 795 MB it streams.
+// Here every consumer thread owns a PAIR of adjacent channels and all accumulators, search values and taps are float2
+// operands of `fma.rn.f32x2` (SASS FFMA2): half the FMA-pipe instructions, and every shared-memory read is a conflict-free
+// 64-bit load (lanes = consecutive channel pairs).  Each half of an FFMA2 is an IEEE fma.rn, and the accumulation order per
+// output element is the same as v1 / the register-staged kernel, so the three variants agree bit for bit.
+// CTA = (output sample, 64-channel slab): 3 consumer warps (one column strip each, 32 channel pairs) + 1 TMA producer warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int G2_STAGES = 2, G2_CONSUMER_WARPS = 3;
+
+static __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
+
+// One consumer warp: output columns [j0, j0+SW) (the first `jn` are stored), channel pair `cp` of the slab.
+// MASK = false requires j0 + SW <= R (no column of any staged row is out of range), so no load needs a bounds check.
+template <int SW, bool MASK>
+static __device__ __forceinline__ void g2_consume(const GdwParams& p, const uint8_t* sm, uint32_t bar_full, uint32_t bar_empty,
+                                                  int stage_bytes, const float2* z, float2* out, int j0, int jn, int lane) {
+    const int F = p.F, R = F - 6, W11 = F - 2, H11 = F - 2, W12 = F - 2, H12 = F - 4, W21 = F - 4, C2 = p.C / 2;
+    const float2 zero = make_float2(0.f, 0.f);
+    float2 acc[5][SW];  // acc[k] = output row t-4+k at step t
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int j = 0; j < SW; ++j) acc[k][j] = zero;
+
+    for (int t = 0; t < H11; ++t) {
+        const int s = t % G2_STAGES;
+        mbar_wait(bar_full + 8 * s, (t / G2_STAGES) & 1);
+        const float2* xs = reinterpret_cast<const float2*>(sm + s * stage_bytes) + lane;  // pixel q of a staged row: xs[q * 32]
+        {   // 5x5 on x11 row t -> output rows t-u
+            float2 xr[SW + 4];
+#pragma unroll
+            for (int q = 0; q < SW + 4; ++q) xr[q] = (!MASK || j0 + q < W11) ? xs[(j0 + q) * 32] : zero;
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+#pragma unroll
+                for (int v = 0; v < 5; ++v) {
+                    const float2 zt = z[(u * 5 + v) * 32];
+#pragma unroll
+                    for (int j = 0; j < SW; ++j) ffma2(acc[4 - u][j], xr[j + v], zt);
+                }
+        }
+        {   // 5x3 on x21 row t -> output rows t-u
+            const float2* x2 = xs + W11 * 32;
+            float2 xr[SW + 2];
+#pragma unroll
+            for (int q = 0; q < SW + 2; ++q) xr[q] = (!MASK || j0 + q < W21) ? x2[(j0 + q) * 32] : zero;
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    const float2 zt = z[(40 + u * 3 + v) * 32];
+#pragma unroll
+                    for (int j = 0; j < SW; ++j) ffma2(acc[4 - u][j], xr[j + v], zt);
+                }
+        }
+        if (t >= 2 && t - 2 < H12) {  // 3x5 on x12 row t-2 -> output rows t-2-u (ring slots 2-u)
+            const float2* x3 = xs + (W11 + W21) * 32;
+            float2 xr[SW + 4];
+#pragma unroll
+            for (int q = 0; q < SW + 4; ++q) xr[q] = (!MASK || j0 + q < W12) ? x3[(j0 + q) * 32] : zero;
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+#pragma unroll
+                for (int v = 0; v < 5; ++v) {
+                    const float2 zt = z[(25 + u * 5 + v) * 32];
+#pragma unroll
+                    for (int j = 0; j < SW; ++j) ffma2(acc[2 - u][j], xr[j + v], zt);
+                }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp is done reading the stage
+        if (t >= 4) {  // output row t-4 is complete: 256 contiguous bytes per warp and column
+            float2* o = out + ((size_t)(t - 4) * R + j0) * C2;
+#pragma unroll
+            for (int j = 0; j < SW; ++j)
+                if (!MASK || j < jn) o[(size_t)j * C2] = acc[0][j];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < SW; ++j) acc[k][j] = acc[k + 1][j];
+#pragma unroll
+        for (int j = 0; j < SW; ++j) acc[4][j] = zero;
+    }
+}
+
+__global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_kernel(const __grid_constant__ GdwParams p) {
+    extern __shared__ __align__(128) uint8_t gsm_raw[];
+    const uint32_t base = (smem_u32(gsm_raw) + 127u) & ~127u;
+    uint8_t* sm = gsm_raw + (base - smem_u32(gsm_raw));
+    const int F = p.F, R = F - 6, W11 = F - 2, H11 = F - 2, W12 = F - 2, H12 = F - 4, W21 = F - 4, C = p.C;
+    const int row11 = W11 * 256, row21 = W21 * 256, row12 = W12 * 256;  // bytes of one staged row (64 ch x 4 B per pixel)
+    const int stage_bytes = row11 + row21 + row12;
+    float* zs = reinterpret_cast<float*>(sm + G2_STAGES * stage_bytes);  // [55][64] taps of this CTA's channels, pre-scaled
+    const uint32_t bar_full = base + G2_STAGES * stage_bytes + 55 * 64 * 4, bar_empty = bar_full + 8 * G2_STAGES;
+
+    const int cblocks = C / 64;
+    const int cblk = blockIdx.x % cblocks, n = blockIdx.x / cblocks;
+    const int xb = n / (p.n_out / p.nx), zb = n / (p.n_out / p.nz);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, G2_CONSUMER_WARPS); }
+        fence_barrier_init();
+    }
+    if (tid < 64) {
+        const int cc = cblk * 64 + tid;
+        for (int t = 0; t < 25; ++t) zs[t * 64 + tid] = p.w0 * __ldg(p.z11 + ((size_t)zb * 25 + t) * C + cc);
+        for (int t = 0; t < 15; ++t) zs[(25 + t) * 64 + tid] = p.w1 * __ldg(p.z12 + ((size_t)zb * 15 + t) * C + cc);
+        for (int t = 0; t < 15; ++t) zs[(40 + t) * 64 + tid] = p.w2 * __ldg(p.z21 + ((size_t)zb * 15 + t) * C + cc);
+    }
+    __syncthreads();
+
+    if (warp == G2_CONSUMER_WARPS) {
+        // ------------------------------- producer -------------------------------
+        if (lane == 0) {
+            tma_prefetch_desc(&p.m11); tma_prefetch_desc(&p.m12); tma_prefetch_desc(&p.m21);
+            for (int t = 0; t < H11; ++t) {
+                const int s = t % G2_STAGES;
+                if (t >= G2_STAGES) mbar_wait(bar_empty + 8 * s, ((t / G2_STAGES) + 1) & 1);
+                const bool has12 = t >= 2 && t - 2 < H12;
+                const uint32_t full = bar_full + 8 * s, dst = base + s * stage_bytes;
+                mbar_expect_tx(full, (uint32_t)(row11 + row21 + (has12 ? row12 : 0)));
+                tma_load_4d(dst, &p.m11, full, cblk * 64, 0, t, xb);
+                tma_load_4d(dst + row11, &p.m21, full, cblk * 64, 0, t, xb);
+                if (has12) tma_load_4d(dst + row11 + row21, &p.m12, full, cblk * 64, 0, t - 2, xb);
+            }
+        }
+        return;
+    }
+
+    // ------------------------------- consumers: warp = column strip, lane = channel pair -------------------------------
+    const int j0 = warp * 9;
+    const int jn = min(9, R - j0);
+    const float2* z = reinterpret_cast<const float2*>(zs) + lane;                           // tap t of this pair: z[t * 32]
+    float2* out = reinterpret_cast<float2*>(p.out + (size_t)n * R * R * C + cblk * 64) + lane;
+    if (jn == 9) g2_consume<9, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, j0, jn, lane);
+    else if (jn == 7) g2_consume<7, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, j0, jn, lane);
+    else g2_consume<9, true>(p, sm, bar_full, bar_empty, stage_bytes, z, out, j0, jn, lane);
+}
+
 int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
     USOT_REQUIRE(a.C % 64 == 0, "groupdw needs C % 64 == 0");
     USOT_REQUIRE(a.nx > 0 && a.nz > 0 && a.n_out % a.nx == 0 && a.n_out % a.nz == 0, "groupdw: n_out must be a multiple of both batches");
@@ -165,11 +312,16 @@ int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaS
     p.nx = a.nx; p.nz = a.nz; p.n_out = a.n_out; p.C = a.C; p.F = F; p.nstrips = 3;
     p.w0 = w0; p.w1 = w1; p.w2 = w2;
     const int smem = GD_STAGES * (3 * F - 8) * 256 + 55 * 64 * 4 + 2 * GD_STAGES * 8 + 128;
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        USOT_CUDA_OK(cudaFuncSetAttribute(groupdw_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
+    if (g_groupdw_tma >= 2) {
+        const int smem2 = G2_STAGES * (3 * F - 8) * 256 + 55 * 64 * 4 + 2 * G2_STAGES * 8 + 128;
+        static SmemAttrCache attr2;
+        if (int rc = attr2.ensure(groupdw_ffma2_kernel, smem2)) return rc;
+        groupdw_ffma2_kernel<<<(unsigned)(a.n_out * (a.C / 64)), G2_CONSUMER_WARPS * 32 + 32, smem2, st>>>(p);
+        USOT_CUDA_OK(cudaGetLastError());
+        return 0;
     }
+    static SmemAttrCache attr1;
+    if (int rc = attr1.ensure(groupdw_tma_kernel, smem)) return rc;
     groupdw_tma_kernel<<<(unsigned)(a.n_out * (a.C / 64)), GD_CONSUMERS + 32, smem, st>>>(p);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;

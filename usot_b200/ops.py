@@ -4,6 +4,7 @@
     xcorr_depthwise   lib/models/connect.py:147-157
     groupdw_xcorr     lib/models/connect.py:86-102 (fused, NHWC)
     conv2d_nhwc       nn.Conv2d + folded BatchNorm2d (+residual)(+ReLU)
+    pred_conv         bbox_pred / cls_pred / cls_memory_pred + epilogue, lib/models/connect.py:235-241,274-275
 
 torch is used for device memory and the current stream only.
 """
@@ -132,4 +133,21 @@ def conv2d_nhwc(x, weight_oihw, scale, shift, stride=1, padding=(0, 0), dilation
                                                 _lib.ptr(scale.contiguous()), _lib.ptr(shift.contiguous()),
                                                 _lib.ptr(None if residual is None else residual.contiguous()), int(bool(relu)),
                                                 _lib.ptr(out), _lib.PRECISIONS[precision], _stream(x)))
+    return out
+
+
+def pred_conv(x, weight_oihw, bias, mode=0, mul=0.1, adjust=None, bias4=None):
+    """x NHWC (n,r,r,256); weight (cout,256,3,3) OIHW as in the reference, cout in {1,4}; returns NCHW (n,cout,r,r).
+    mode 0: mul * (conv(x) + bias); mode 1: exp(adjust * (conv(x) + bias) + bias4)."""
+    _need_float(x, weight_oihw, bias, adjust, bias4)
+    _need_cuda(x, weight_oihw, bias, adjust, bias4)
+    n, r, r2, c = x.shape
+    cout = weight_oihw.shape[0]
+    assert r == r2 and tuple(weight_oihw.shape) == (cout, c, 3, 3)
+    w = weight_oihw.permute(2, 3, 0, 1).reshape(9, cout, c).contiguous()
+    out = torch.empty((n, cout, r, r), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().usot_pred_conv(_lib.ptr(x.contiguous()), n, r, c, _lib.ptr(w), _lib.ptr(bias.contiguous()), cout, int(mode),
+                                              float(mul), _lib.ptr(None if adjust is None else adjust.contiguous()),
+                                              _lib.ptr(None if bias4 is None else bias4.reshape(-1).contiguous()), _lib.ptr(out), _stream(x)))
     return out
