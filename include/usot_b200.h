@@ -27,6 +27,7 @@
  *   usot_engine_backbone_neck        <- feature_extractor + neck         lib/models/models.py:39-40,181-184
  *   usot_engine_forward_train        <- USOT_.forward                    lib/models/models.py:208-295
  *   usot_tracker_postprocess         <- USOTTracker.update tensor path   lib/tracker/usot_tracker.py:137-163
+ *   usot_crop_resize                 <- get_subwindow_tracking + cv2.resize  lib/utils/track_utils.py:30-119 (im_to_torch :24-27)
  *   usot_engine_load_tensor/finalize <- load_state_dict contract         lib/utils/train_utils.py:92-128
  */
 #ifndef USOT_B200_H
@@ -111,6 +112,16 @@ USOT_API int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, con
  * adjust / bias4 are device pointers and may be NULL in mode 0. */
 USOT_API int usot_pred_conv(const float* in, int n, int r, int channels, const float* weight, const float* bias, int cout, int mode,
                             float mul, const float* adjust, const float* bias4, float* out, void* stream);
+
+/* SiamFC-style crops for the tracker (replaces the host path get_subwindow_tracking -> cv2.resize -> im_to_torch).
+ * frames (n_frames,height,width,3) uint8 HWC (cv2 BGR frames) on the DEVICE; crops (n,4) int32 on the device =
+ * [frame index, context_xmin, context_ymin, original_sz] with the context window in frame coordinates BEFORE padding
+ * (track_utils.py:44-47; may lie partly or wholly outside the frame); fill (n,3) uint8 on the device = the channel means
+ * truncated to uint8 (what the reference's uint8 canvas stores, track_utils.py:58-70).  out (n,3,model_sz,model_sz) float32 nchw,
+ * every value an integer in [0,255], bit-identical to the reference's patch.  original_sz == model_sz copies, == 2*model_sz
+ * averages 2x2 blocks (OpenCV's INTER_AREA route), anything else is OpenCV's 11-bit fixed-point bilinear. */
+USOT_API int usot_crop_resize(const uint8_t* frames, int n_frames, int height, int width, const int32_t* crops, const uint8_t* fill,
+                              int n, int model_sz, float* out, void* stream);
 
 USOT_API int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream);
 USOT_API int usot_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, void* stream);

@@ -159,6 +159,24 @@ def test_pred_conv(ops, cout, mode, r, n, min_batch):
     assert rel_err(ours, ref) <= 5e-6
 
 
+@pytest.mark.parametrize("cout,mode,r", [(4, 1, 25), (1, 0, 25), (4, 1, 27), (1, 0, 19)])
+def test_pred_conv_variants_bit_identical(ops, cout, mode, r):
+    """The per-image TMA kernel and the small-batch kernel build the same sequential fma chains: results must not depend on
+    which one the batch size selects."""
+    from usot_b200 import _lib
+    g = torch.Generator().manual_seed(cout + r)
+    x = torch.randn(3, r, r, 256, generator=g).cuda()
+    w = (torch.randn(cout, 256, 3, 3, generator=g) * 0.02).cuda()
+    b = (torch.randn(cout, generator=g) * 0.1).cuda()
+    adjust, bias4 = torch.tensor([0.7]).cuda(), (torch.randn(4, generator=g) * 0.3).cuda()
+    outs = []
+    for min_batch in (1, 0):
+        _lib.check(_lib.load().usot_set_tunable(b"pred_tma_min_batch", min_batch))
+        outs.append(ops.pred_conv(x, w, b, mode=mode, mul=0.1, adjust=adjust, bias4=bias4).clone())
+    _lib.check(_lib.load().usot_set_tunable(b"pred_tma_min_batch", 48))
+    assert torch.equal(outs[0], outs[1])
+
+
 CONV_CASES = [
     # cin, cout, k, stride, pad, dil, h, w, residual, relu
     (64, 64, 1, 1, (0, 0), (1, 1), 17, 17, False, True),

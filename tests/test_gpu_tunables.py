@@ -28,7 +28,7 @@ def net():
 
 
 @pytest.mark.parametrize("knob,value,exact", [("tc_tma_store", 0, True), ("tc_tma_res", 0, True), ("groupdw_tma", 0, True), ("groupdw_tma", 1, True),
-                                              ("stem_tc", 0, False), ("pred_tma_min_batch", 1, False), ("tc_bn_max", 64, False)])
+                                              ("stem_tc", 0, False), ("pred_tma_min_batch", 1, True), ("tc_bn_max", 64, False)])
 def test_knob_keeps_results(net, knob, value, exact):
     z, x, tb, sb = O.synth_inputs(91, batch=3)
     net.template(z.cuda(), tb.cuda())

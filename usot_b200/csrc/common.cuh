@@ -94,9 +94,11 @@ int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStr
 // Single depth-wise xcorr, NCHW (the reference op, connect.py:147-157)
 int launch_xcorr_nchw(const float* x, const float* k, float* out, int nx, int nk, int C, int hx, int wx, int hk, int wk,
                       cudaStream_t st);
-// Skinny prediction conv 3x3 p1, Cin = C, Cout <= 4, NHWC in -> NCHW out.  mode 0: out = mul*(y+b) ; mode 1: exp(adjust*(y+b)+bias4[co])
-int launch_pred_conv(const float* in, int n, int r, int C, const float* w /*[9][cout][C]*/, const float* b, int cout,
-                     int mode, float mul, const float* adjust, const float* bias4, float* out_nchw, cudaStream_t st);
+// Skinny prediction conv 3x3 p1, Cin = C, Cout in {1,4}, NHWC in -> NCHW out (pred_tma.cu).  mode 0: out = mul*(y+b) ; mode 1:
+// exp(adjust*(y+b)+bias4[co]).  w4 = launch_pred_repack(w) or nullptr (repacked on the fly).
+int launch_pred_conv(const float* in, int n, int r, int C, const float* w /*[9][cout][C]*/, const float* w4 /*[C/4][9*cout][4]*/,
+                     const float* b, int cout, int mode, float mul, const float* adjust, const float* bias4, float* out_nchw, cudaStream_t st);
+int launch_pred_repack(const float* w, int cout, int C, float* w4, cudaStream_t st);
 // TMA-streamed per-image variant for large batches (pred_tma.cu); launch_pred_conv dispatches to it when supported
 extern int g_pred_tma_min_batch;
 bool pred_tma_supported(int n, int r, int C, int cout);
@@ -120,6 +122,9 @@ int launch_prroi_coor_backward(const float* feat, const float* rois, const float
                                int C, int H, int W, int PH, int PW, float scale, cudaStream_t st);
 int launch_bce(const float* pred, const float* label, int count, float* out, cudaStream_t st);
 int launch_iou(const float* bbox, const float* target, const float* weight, int n, int cells, float* out, cudaStream_t st);
+// crop.cu: batched context-window crop + average-colour padding + fixed-point bilinear resize (bit-exact with cv2.resize on uint8)
+int launch_crop_resize(const uint8_t* frames, int n_frames, int H, int W, const int* crops /*[n][4] = frame, xmin, ymin, original_sz*/,
+                       const uint8_t* fills /*[n][3]*/, int n, int model_sz, float* out_nchw, cudaStream_t st);
 int launch_center_crop_nhwc(const float* in, int n, int h, int w, int c, int l, float* out, cudaStream_t st);
 
 }  // namespace usot

@@ -130,7 +130,8 @@ struct T {
 };
 
 struct PredW {
-    float* w = nullptr;  // [9][cout][256]
+    float* w = nullptr;   // [9][cout][256]
+    float* w4 = nullptr;  // [64][9*cout][4]: same weights, channel groups outermost (small-batch kernel)
     float* b = nullptr;
     int cout = 0;
 };
@@ -305,7 +306,10 @@ static int finalize_impl(usot_engine* e) {
             for (int c = 0; c < 256; ++c)
                 for (int t = 0; t < 9; ++t) packed[((size_t)t * cout + co) * 256 + c] = (*w)[((size_t)co * 256 + c) * 9 + t];
         pw.cout = cout;
-        if (upload(e, packed, &pw.w) || upload(e, *b, &pw.b)) return 1;
+        std::vector<float> packed4(packed.size());
+        for (int k = 0; k < 9 * cout; ++k)
+            for (int c = 0; c < 256; ++c) packed4[((size_t)(c / 4) * 9 * cout + k) * 4 + (c & 3)] = packed[(size_t)k * 256 + c];
+        if (upload(e, packed, &pw.w) || upload(e, packed4, &pw.w4) || upload(e, *b, &pw.b)) return 1;
         return 0;
     };
     if (int rc = pack_pred("connect_model.bbox_pred", 4, e->bbox_pred)) return rc;
@@ -508,7 +512,7 @@ static int pred(Ctx& c, const PredW& pw, const T& in, int mode, float* out) {
         // algorithmic bytes: the tower output read once, the (n,cout,R,R) map written once, the weights once
         Scope sc(FAM_PRED, c.st, 2.0 * in.n * in.h * in.w * 256.0 * 9 * pw.cout,
                  4.0 * ((double)in.n * in.h * in.w * (256.0 + pw.cout) + 9.0 * pw.cout * 256));
-        RUN(launch_pred_conv(in.f, in.n, in.h, 256, pw.w, pw.b, pw.cout, mode, mode == 0 ? 0.1f : 1.f, e->adjust, e->bias4, out, c.st));
+        RUN(launch_pred_conv(in.f, in.n, in.h, 256, pw.w, pw.w4, pw.b, pw.cout, mode, mode == 0 ? 0.1f : 1.f, e->adjust, e->bias4, out, c.st));
     }
     return 0;
 }
@@ -752,7 +756,15 @@ int usot_pred_conv(const float* in, int n, int r, int channels, const float* wei
     USOT_REQUIRE(n >= 0 && r > 0 && channels > 0, "bad shape");
     USOT_REQUIRE(mode == 0 || (mode == 1 && adjust && bias4), "mode must be 0, or 1 with adjust and bias4");
     g_prof.launches[FAM_PRED]++;
-    return launch_pred_conv(in, n, r, channels, weight, bias, cout, mode, mul, adjust, bias4, out, (cudaStream_t)stream);
+    return launch_pred_conv(in, n, r, channels, weight, nullptr, bias, cout, mode, mul, adjust, bias4, out, (cudaStream_t)stream);
+}
+
+int usot_crop_resize(const uint8_t* frames, int n_frames, int height, int width, const int32_t* crops, const uint8_t* fill, int n,
+                     int model_sz, float* out, void* stream) {
+    USOT_REQUIRE(n == 0 || (frames && crops && fill && out), "null pointer");
+    USOT_REQUIRE(n >= 0 && n <= 65535 && n_frames > 0 && height > 0 && width > 0 && model_sz > 0 && model_sz <= 4096, "bad shape");
+    g_prof.launches[FAM_OTHER]++;
+    return launch_crop_resize(frames, n_frames, height, width, crops, fill, n, model_sz, out, (cudaStream_t)stream);
 }
 
 int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream) {

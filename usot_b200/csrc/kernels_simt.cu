@@ -448,62 +448,6 @@ int launch_xcorr_nchw(const float* x, const float* k, float* out, int nx, int nk
 }
 
 // =============================================================================================
-// Prediction convs (3x3 p1, Cin = 256, Cout in {1,4}): one warp per output pixel, lanes over channels.
-// =============================================================================================
-template <int COUT>
-__global__ void __launch_bounds__(256) pred_conv_kernel(const float* __restrict__ in, int n, int r, int C,
-                                                        const float* __restrict__ w, const float* __restrict__ b, int mode,
-                                                        float mul, const float* __restrict__ adjust,
-                                                        const float* __restrict__ bias4, float* __restrict__ out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int total = n * r * r;
-    if (warp >= total) return;
-    const int ox = warp % r, oy = (warp / r) % r, bi = warp / (r * r);
-    float acc[COUT];
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-        const int y = oy + tap / 3 - 1, x = ox + tap % 3 - 1;
-        if (y < 0 || y >= r || x < 0 || x >= r) continue;
-        const float* ip = in + (((size_t)bi * r + y) * r + x) * C;
-        for (int c0 = lane * 4; c0 < C; c0 += 128) {
-            const float4 v = ldg4(ip + c0);
-#pragma unroll
-            for (int co = 0; co < COUT; ++co) {
-                const float4 ww = ldg4(w + ((size_t)tap * COUT + co) * C + c0);
-                acc[co] = fmaf(v.x, ww.x, fmaf(v.y, ww.y, fmaf(v.z, ww.z, fmaf(v.w, ww.w, acc[co]))));
-            }
-        }
-    }
-#pragma unroll
-    for (int co = 0; co < COUT; ++co)
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], off);
-    if (lane < COUT) {
-        float y = 0.f;
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) if (co == lane) y = acc[co];
-        y += __ldg(b + lane);
-        y = (mode == 0) ? mul * y : expf(fmaf(__ldg(adjust), y, __ldg(bias4 + lane)));
-        out[(((size_t)bi * COUT + lane) * r + oy) * r + ox] = y;
-    }
-}
-
-int launch_pred_conv(const float* in, int n, int r, int C, const float* w, const float* b, int cout, int mode, float mul,
-                     const float* adjust, const float* bias4, float* out, cudaStream_t st) {
-    USOT_REQUIRE(C % 128 == 0, "pred conv needs C % 128 == 0");
-    const int total = n * r * r;
-    if (total == 0) return 0;
-    if (pred_tma_supported(n, r, C, cout)) return launch_pred_tma(in, n, r, C, w, b, cout, mode, mul, adjust, bias4, out, st);
-    const unsigned grid = (unsigned)((total + 7) / 8);
-    if (cout == 1) pred_conv_kernel<1><<<grid, 256, 0, st>>>(in, n, r, C, w, b, mode, mul, adjust, bias4, out);
-    else if (cout == 4) pred_conv_kernel<4><<<grid, 256, 0, st>>>(in, n, r, C, w, b, mode, mul, adjust, bias4, out);
-    else { USOT_REQUIRE(false, "pred conv: Cout must be 1 or 4"); }
-    USOT_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-// =============================================================================================
 // Conf_Fusion epilogue: out[b] = sum_q exp(clamp(conf[b,q],-6,4)) * value[b,q] / sum_q exp(clamp(conf[b,q],-6,4))
 // =============================================================================================
 __global__ void conf_fusion_kernel(const float4* __restrict__ conf, const float4* __restrict__ value, int nq, size_t per_map4,

@@ -10,8 +10,10 @@
 //     w[tap,co,:]> for all 9 taps at once (a 625 x 36 x 256 GEMM per image) with packed `fma.rn.f32x2`: the (w_a, w_b) pairs
 //     are broadcast 128-bit shared-memory loads shared by both pixels, the activation is duplicated into both halves;
 //   * the 9-tap neighbourhood sum, bias and the exp / 0.1x epilogue run from shared memory; NCHW output stores are coalesced.
-// Small batches (fewer CTAs than half the SMs) keep the warp-per-pixel kernel in kernels_simt.cu, which spreads one image over
-// many SMs (launch_pred_conv dispatches).
+// Small batches (fewer images than a third of the SMs) run pred_dot_kernel instead, which spreads one image over many SMs: one
+// thread per (output pixel, tap, co) dot product.  Both kernels build every partial product as the SAME sequential fma.rn chain
+// over the 256 channels and add the nine taps in the same order, so they agree bit for bit and a sample's result does not
+// depend on the batch it is computed in (tests/test_gpu_model.py::test_batch_256_independence, sharded == single device).
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
@@ -154,6 +156,77 @@ __global__ void __launch_bounds__(13 * 32, 1) pred_gemm_kernel(const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// small-batch variant: thread = (output pixel, k = tap*COUT+co); w4 is the [C/4][9*COUT][4] repack of the weights so that the
+// lanes of a warp (consecutive k) read consecutive 16-byte groups; the activation row of the tap's neighbour pixel is a
+// broadcast read.
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(144) pred_dot_kernel(const float* __restrict__ in, int total_pix, int R, int C, const float* __restrict__ w4,
+                                                       const float* __restrict__ b, int mode, float mul, const float* __restrict__ adjust,
+                                                       const float* __restrict__ bias4, float* __restrict__ out) {
+    constexpr int K = 9 * COUT, PXB = 144 / K;
+    __shared__ float P[PXB][K];
+    __shared__ int valid[PXB][9];
+    const int t = threadIdx.x, px = t / K, k = t - px * K;
+    const int tap = k / COUT;
+    const int npix = R * R;
+    const int o = blockIdx.x * PXB + px;  // flat (image, y, x)
+    bool ok = o < total_pix;
+    int img = 0, y = 0, x = 0;
+    if (ok) {
+        img = o / npix;
+        const int pix = o - img * npix;
+        y = pix / R; x = pix - y * R;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        ok = yy >= 0 && yy < R && xx >= 0 && xx < R;
+        if (ok) {
+            const float4* xr = reinterpret_cast<const float4*>(in + (((size_t)img * R + yy) * R + xx) * C);
+            const float4* wr = reinterpret_cast<const float4*>(w4) + k;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int c4 = 0; c4 < C / 4; ++c4) {
+                const float4 xv = __ldg(xr + c4), wv = __ldg(wr + (size_t)c4 * K);
+                acc = fmaf(xv.x, wv.x, acc);
+                acc = fmaf(xv.y, wv.y, acc);
+                acc = fmaf(xv.z, wv.z, acc);
+                acc = fmaf(xv.w, wv.w, acc);
+            }
+            P[px][k] = acc;
+        }
+    }
+    if (k % COUT == 0) valid[px][tap] = ok ? 1 : 0;
+    __syncthreads();
+    if (t < PXB * COUT) {
+        const int p2 = t / COUT, co = t - p2 * COUT;
+        const int o2 = blockIdx.x * PXB + p2;
+        if (o2 < total_pix) {
+            float v = 0.f;
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp)
+                if (valid[p2][tp]) v += P[p2][tp * COUT + co];
+            v += __ldg(b + co);
+            v = (mode == 0) ? mul * v : expf(fmaf(__ldg(adjust), v, __ldg(bias4 + co)));
+            const int img2 = o2 / npix, pix2 = o2 - img2 * npix;
+            out[((size_t)img2 * COUT + co) * npix + pix2] = v;
+        }
+    }
+}
+
+__global__ void pred_repack_kernel(const float* __restrict__ w, int K, int C, float* __restrict__ w4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [k][c]
+    if (i >= K * C) return;
+    const int k = i / C, c = i - k * C;
+    w4[((size_t)(c / 4) * K + k) * 4 + (c & 3)] = w[i];
+}
+
+int launch_pred_repack(const float* w, int cout, int C, float* w4, cudaStream_t st) {
+    const int total = 9 * cout * C;
+    pred_repack_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, 9 * cout, C, w4);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int g_pred_tma_min_batch = 48;  // tunable "pred_tma_min_batch": batches of at least this many images use the kernel above (0 = never)
 
 bool pred_tma_supported(int n, int r, int C, int cout) {
@@ -189,6 +262,29 @@ int launch_pred_tma(const float* in, int n, int r, int C, const float* w, const 
         pred_gemm_kernel<1><<<n, threads, smem, st>>>(p);
     }
     USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Dispatcher.  w = [9][cout][C] (tap-major, the layout pred_gemm_kernel transposes itself); w4 = its [C/4][9*cout][4] repack for the
+// small-batch kernel, or nullptr (stand-alone op): then the repack runs into a stream-ordered temporary.
+int launch_pred_conv(const float* in, int n, int r, int C, const float* w, const float* w4, const float* b, int cout, int mode, float mul,
+                     const float* adjust, const float* bias4, float* out, cudaStream_t st) {
+    USOT_REQUIRE(C % 4 == 0 && (cout == 1 || cout == 4), "pred conv needs C % 4 == 0 and Cout in {1, 4}");
+    const int total = n * r * r;
+    if (total == 0) return 0;
+    if (pred_tma_supported(n, r, C, cout)) return launch_pred_tma(in, n, r, C, w, b, cout, mode, mul, adjust, bias4, out, st);
+    float* tmp = nullptr;
+    if (!w4) {
+        USOT_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&tmp), (size_t)9 * cout * C * sizeof(float), st));
+        if (int rc = launch_pred_repack(w, cout, C, tmp, st)) return rc;
+        w4 = tmp;
+    }
+    const int pxb = 144 / (9 * cout);
+    const unsigned grid = (unsigned)((total + pxb - 1) / pxb);
+    if (cout == 1) pred_dot_kernel<1><<<grid, 144, 0, st>>>(in, total, r, C, w4, b, mode, mul, adjust, bias4, out);
+    else pred_dot_kernel<4><<<grid, 144, 0, st>>>(in, total, r, C, w4, b, mode, mul, adjust, bias4, out);
+    USOT_CUDA_OK(cudaGetLastError());
+    if (tmp) USOT_CUDA_OK(cudaFreeAsync(tmp, st));
     return 0;
 }
 

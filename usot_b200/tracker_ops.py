@@ -1,7 +1,12 @@
 """Device-side tensor path of the per-frame tracker update (lib/tracker/usot_tracker.py:137-163).
 
 ``postprocess`` replaces the reference's 3 blocking D2H copies + numpy post-processing by one kernel; the caller reads the
-8 result doubles back with a single ``.cpu()`` (or keeps them on the device)."""
+8 result doubles back with a single ``.cpu()`` (or keeps them on the device).
+
+``get_subwindow_tracking`` / ``crop_resize`` replace the host crop in front of the model (lib/utils/track_utils.py:30-119:
+context window, average-colour padding, ``cv2.resize``, ``im_to_torch``) by one kernel whose output is bit-identical to the
+reference patch; the frame is uploaded once as uint8 (0.9 MB for 480x640) and every crop of that frame -- template, search,
+several scales or several videos -- is produced on the device as the fp32 NCHW tensor ``USOT.template()/track()`` take."""
 import numpy as np
 import torch
 
@@ -132,3 +137,87 @@ def update_device(net, x_crops, target_pos, target_sz, window, scale_z, p, queue
     pool_box = torch.from_numpy(((box - axis0) * slope).astype(np.float32)[None]).to(x_crops.device)
     feat_mem = net.extract_memory_feature(xf=xf, search_bbox=pool_box)
     return new_pos, new_sz, float(score), feat_mem
+
+
+def upload_frame(im, device="cuda"):
+    """cv2 frame (H,W,3) uint8 numpy -> (1,H,W,3) uint8 CUDA tensor (accepts an already-uploaded tensor)."""
+    if isinstance(im, np.ndarray):
+        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+            raise AssertionError("frames must be (H, W, 3) uint8 arrays as cv2.imread returns them")
+        im = torch.from_numpy(np.ascontiguousarray(im)).to(device, non_blocking=True)
+    _need_cuda(im)
+    if im.dtype != torch.uint8:
+        raise AssertionError("frames must be uint8, got {}".format(im.dtype))
+    return im.reshape((-1,) + tuple(im.shape[-3:])).contiguous()
+
+
+def crop_resize(frames, crops, fill, model_sz):
+    """Batched crops.  frames (F,H,W,3) uint8 CUDA; crops (n,4) int32 [frame index, context_xmin, context_ymin, original_sz]
+    (window in frame coordinates before padding); fill (n,3) uint8 = truncated channel means.  Returns (n,3,model_sz,model_sz)
+    float32 CUDA, bit-identical to get_subwindow_tracking(...)[0] of the reference for each window."""
+    _need_cuda(frames, crops, fill)
+    assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+    assert crops.dtype == torch.int32 and crops.dim() == 2 and crops.shape[1] == 4
+    assert fill.dtype == torch.uint8 and tuple(fill.shape) == (crops.shape[0], 3)
+    frames, crops, fill = frames.contiguous(), crops.contiguous(), fill.contiguous()
+    n = crops.shape[0]
+    out = torch.empty((n, 3, int(model_sz), int(model_sz)), dtype=torch.float32, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _lib.check(_lib.load().usot_crop_resize(_lib.ptr(frames), frames.shape[0], frames.shape[1], frames.shape[2], _lib.ptr(crops),
+                                                _lib.ptr(fill), n, int(model_sz), _lib.ptr(out), _stream(frames)))
+    return out
+
+
+def crop_geometry(im_shape, pos, model_sz, original_sz, target_sz=None, need_bbox=False):
+    """Host bookkeeping of get_subwindow_tracking (track_utils.py:41-55,81-115): returns (context_xmin, context_ymin) in frame
+    coordinates before padding, and the reference's crop_info dict (without the never-filled 'empty_mask' canvas)."""
+    if isinstance(pos, float):
+        pos = [pos, pos]
+    sz = original_sz
+    r, c = int(im_shape[0]), int(im_shape[1])
+    half = (original_sz + 1) / 2
+    xmin = round(pos[0] - half)
+    xmax = xmin + sz - 1
+    ymin = round(pos[1] - half)
+    ymax = ymin + sz - 1
+    left_pad = int(max(0., -xmin))
+    top_pad = int(max(0., -ymin))
+    right_pad = int(max(0., xmax - c + 1))
+    bottom_pad = int(max(0., ymax - r + 1))
+    info = {}
+    cxmin, cxmax, cymin, cymax = xmin + left_pad, xmax + left_pad, ymin + top_pad, ymax + top_pad
+    if target_sz is not None:
+        t_xmin = round(pos[0] - target_sz[0] / 2)
+        t_xmax = round(pos[0] + target_sz[0] / 2)
+        t_ymin = round(pos[1] - target_sz[1] / 2)
+        t_ymax = round(pos[1] + target_sz[1] / 2)
+        info['original_image_bbox'] = [t_xmin, t_ymin, t_xmax, t_ymax]
+        if need_bbox:
+            patch_sz = int(cymax + 1) - int(cymin)
+            x_slope = patch_sz / (cxmax - cxmin)
+            y_slope = patch_sz / (cymax - cymin)
+            scale_resize = (model_sz if model_sz != original_sz else patch_sz) / patch_sz
+            info['template_bbox'] = [scale_resize * (left_pad - 1 + x_slope * (t_xmin - cxmin)),
+                                     scale_resize * (top_pad - 1 + y_slope * (t_ymin - cymin)),
+                                     scale_resize * (left_pad - 1 + x_slope * (t_xmax - cxmin)),
+                                     scale_resize * (top_pad - 1 + y_slope * (t_ymax - cymin))]
+    info['crop_cords'] = [cxmin, cxmax, cymin, cymax]
+    info['pad_info'] = [top_pad, left_pad, r, c]
+    return int(xmin), int(ymin), info
+
+
+def get_subwindow_tracking(im, pos, model_sz, original_sz, avg_chans, target_sz=None, out_mode='torch', need_bbox=False, vis=False):
+    """Drop-in for lib.utils.track_utils.get_subwindow_tracking (same arguments, same crop_info) producing the patch on the GPU.
+
+    ``im`` is the cv2 frame (numpy uint8, uploaded here) or an ``upload_frame`` tensor, so a caller cropping several windows of
+    one frame uploads it once.  Returns ((3,model_sz,model_sz) float32 CUDA tensor, crop_info); the reference returns the same
+    values on the CPU and its caller moves them with ``.cuda()`` (usot_tracker.py:66-71,99-105,219-220)."""
+    if out_mode != 'torch':
+        raise NotImplementedError("usot_b200.tracker_ops.get_subwindow_tracking only produces torch CUDA tensors")
+    frames = upload_frame(im)
+    h, w = frames.shape[1], frames.shape[2]
+    xmin, ymin, info = crop_geometry((h, w), pos, model_sz, original_sz, target_sz, need_bbox)
+    dev = frames.device
+    crops = torch.tensor([[0, xmin, ymin, int(original_sz)]], dtype=torch.int32).to(dev, non_blocking=True)
+    fill = torch.from_numpy(np.asarray(avg_chans, np.float64).astype(np.uint8).reshape(1, 3)).to(dev, non_blocking=True)
+    return crop_resize(frames[:1], crops, fill, model_sz)[0], info
