@@ -149,6 +149,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(TC_BM, BN);
+            // Fused cross term: the lo weight tile sits right behind the hi tile in the stage and `cross` right behind `main` in
+            // TMEM, so ONE MMA with N = 2*BN computes a_hi*w_hi -> main and a_hi*w_lo -> cross while reading a_hi from shared
+            // memory once (the operand reads of three N=128 MMAs per k-step saturate the 128 B/clk shared-memory port).
+            const uint32_t idesc2 = make_idesc(TC_BM, 2 * BN);
+            const bool fuse = Cfg::XACC && p.fuse_cross;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -167,6 +172,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         const uint64_t a_hi = make_smem_desc(sa + k * 32), b_hi = make_smem_desc(sb + k * 32);
+                        if (SPLIT && fuse) {
+                            const uint64_t a_lo = make_smem_desc(sa + TC_A_BYTES + k * 32);
+                            umma_f16(tmem_d, a_hi, b_hi, idesc2, (ks | k) ? 1u : 0u);
+                            umma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
+                            continue;
+                        }
                         umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) ? 1u : 0u);
                         if (SPLIT) {
                             const uint64_t a_lo = make_smem_desc(sa + TC_A_BYTES + k * 32), b_lo = make_smem_desc(sb + Cfg::B_BYTES + k * 32);
@@ -301,6 +312,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const uint32_t buf = eg * p.nbuf + (p.tma_res ? gc % 3 : 0);
                         uint8_t* rp = s_out + buf * Cfg::BUF_BYTES + row * 64;
                         const int sw = (row >> 1) & 3;
+                        if (p.tma_f32) {
+                            // fp32-only outputs (encoders -> xcorr, last tower conv -> pred): same staging buffer, rows of 128 B
+                            // (32 floats) in the 128B-swizzled layout of the fp32 output map, ONE bulk tensor store per chunk
+                            if (et == 0) bulk_wait_read<0>();
+                            asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
+                            uint8_t* rp32 = s_out + buf * Cfg::BUF_BYTES + row * 128;
+                            const int sw7 = row & 7;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4*>(rp32 + ((q ^ sw7) << 4)) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                            fence_proxy_async_smem();
+                            asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
+                            if (et == 0) {
+                                tma_store_4d(&p.o[0], s_out_u32 + buf * Cfg::BUF_BYTES, n0 + c0, tw * p.bw, th * p.bh, img);
+                                bulk_commit();
+                            }
+                            ++gc;
+                            continue;
+                        }
                         if (p.tma_res) {
                             mbar_wait(bar_res + 8 * (eg * 3 + gc % 3), (gc / 3) & 1);
 #pragma unroll
@@ -462,6 +492,8 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
 int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
 int g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
 int g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
+int g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
+int g_tc_fuse_cross = 1;       // split mode with two accumulators: a_hi*[w_hi|w_lo] as ONE N = 2*BN MMA (A/B switch; same arithmetic)
 int g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cross-term accumulator (accuracy); 256 trades it for reuse
 
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st) {
@@ -520,8 +552,19 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         if (int rc = encode_map(&p.b[pl], pl == 0 ? w.hi : w.lo, 2, wd, ws, wb)) return rc;
     }
 
+    p.fuse_cross = g_tc_fuse_cross;
     p.tma_store = (g_tc_tma_store && p.out_hi && !(split && bn == 256)) ? 1 : 0;
-    if (p.tma_store) {
+    p.tma_f32 = 0;
+    if (g_tc_tma_store && g_tc_tma_f32 && !p.out_hi && p.out_f32 && !p.res_hi && !(split && bn == 256)) {
+        // fp32-only output: one fp32 map, box {32 floats = 128 B, bw, bh, 1}, 128B swizzle; uses the split path's staging buffers
+        cuuint64_t od[4] = {(cuuint64_t)g.cout, (cuuint64_t)g.wo, (cuuint64_t)g.ho, (cuuint64_t)g.n};
+        cuuint64_t os[3] = {(cuuint64_t)g.cout * 4, (cuuint64_t)g.wo * g.cout * 4, (cuuint64_t)g.ho * g.wo * g.cout * 4};
+        cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+        if (int rc = encode_tmap(&p.o[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.out_f32, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+        p.o[1] = p.o[0];
+        p.tma_store = 1;
+        p.tma_f32 = 1;
+    } else if (p.tma_store) {
         cuuint64_t od[4] = {(cuuint64_t)g.cout, (cuuint64_t)g.wo, (cuuint64_t)g.ho, (cuuint64_t)g.n};
         cuuint64_t os[3] = {(cuuint64_t)g.cout * 2, (cuuint64_t)g.wo * g.cout * 2, (cuuint64_t)g.ho * g.wo * g.cout * 2};
         cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};

@@ -651,6 +651,8 @@ int usot_set_tunable(const char* name, int value) {
     if (!strcmp(name, "groupdw_tma")) { USOT_REQUIRE(value >= 0 && value <= 2, "groupdw_tma must be 0 (register-staged), 1 (TMA ring, scalar FMA) or 2 (TMA ring, packed FFMA2)"); g_groupdw_tma = value; return 0; }
     if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
+    if (!strcmp(name, "tc_tma_f32")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_f32 must be 0 or 1"); g_tc_tma_f32 = value; return 0; }
+    if (!strcmp(name, "tc_fuse_cross")) { USOT_REQUIRE(value == 0 || value == 1, "tc_fuse_cross must be 0 or 1"); g_tc_fuse_cross = value; return 0; }
     if (!strcmp(name, "tc_tma_store")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_store must be 0 or 1"); g_tc_tma_store = value; return 0; }
     if (!strcmp(name, "tc_split_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_split_bn_max must be 64, 128 or 256"); g_tc_split_bn_max = value; return 0; }
     if (!strcmp(name, "pred_tma_min_batch")) { USOT_REQUIRE(value >= 0, "pred_tma_min_batch must be >= 0 (0 = never use the TMA-streamed pred kernel)"); g_pred_tma_min_batch = value; return 0; }
