@@ -135,6 +135,16 @@ USOT_API int usot_engine_load_tensor(usot_engine* e, const char* name, const flo
 /* Fold BN, repack and upload every staged tensor.  Synchronises the device.  May be called again after reloading. */
 USOT_API int usot_engine_finalize(usot_engine* e);
 /* Bytes of device memory currently owned by the engine (weights + workspace arena). */
+/* Packed-weight image (offline BN folding + packed-weight cache).  After finalize() the engine can write
+ * everything it uploaded -- folded scale/shift vectors, repacked fp32 weights, the fp16 hi/lo planes of the tensor-core path,
+ * the prediction-head layouts -- into one host buffer; usot_engine_import_packed() restores an engine of the SAME precision
+ * from such a buffer without the state_dict and without repeating the host-side packing (it replaces load_tensor + finalize).
+ * The image is only meaningful for the library ABI version and precision recorded in its header; mismatches fail.
+ * The Python host keys cache files by a content hash of the state_dict (usot_b200/engine.py, usot_b200/checkpoint.py). */
+USOT_API int64_t usot_engine_packed_size(const usot_engine* e);
+USOT_API int usot_engine_export_packed(usot_engine* e, void* host_buf, int64_t capacity);
+USOT_API int usot_engine_import_packed(usot_engine* e, const void* host_buf, int64_t size);
+
 USOT_API int64_t usot_engine_device_bytes(const usot_engine* e);
 
 /* feature_extractor + neck:  x (n,3,size,size) nchw -> xf (n,F,F,256) nhwc, F = ((size-7)/2+1 -> pool -> s2) */

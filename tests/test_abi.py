@@ -18,7 +18,7 @@ def test_header_symbols_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.usot_abi_version() == 1
+    assert lib.usot_abi_version() == 2
     assert lib.usot_feature_size(255) == 31 and lib.usot_feature_size(271) == 33 and lib.usot_feature_size(127) == 15
     rc = lib.usot_set_tunable(b"no_such_knob", 1)
     assert rc != 0 and b"unknown tunable" in lib.usot_last_error()

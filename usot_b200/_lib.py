@@ -47,6 +47,9 @@ SIGNATURES = {
     "usot_engine_load_tensor": (_I, [_P, ctypes.c_char_p, _P, _I64]),
     "usot_engine_finalize": (_I, [_P]),
     "usot_engine_device_bytes": (_I64, [_P]),
+    "usot_engine_packed_size": (_I64, [_P]),
+    "usot_engine_export_packed": (_I, [_P, _P, _I64]),
+    "usot_engine_import_packed": (_I, [_P, _P, _I64]),
     "usot_engine_backbone_neck": (_I, [_P, _P, _I, _I, _P, _P]),
     "usot_feature_size": (_I, [_I]),
     "usot_engine_template": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),

@@ -161,6 +161,12 @@ struct usot_engine {
     std::map<std::string, ConvW> convs;
     std::vector<void*> owned;  // device allocations holding weights
     int64_t weight_bytes = 0;
+    // packed-weight image (usot_engine_export_packed / usot_engine_import_packed): every buffer finalize() uploads, in upload
+    // order.  `records` remembers (device pointer or host copy, bytes); `replay` is the cursor over an imported image.
+    struct Record { const void* dev; std::vector<uint8_t> host; size_t bytes; };
+    std::vector<Record> records;
+    const uint8_t* replay = nullptr;
+    const uint8_t* replay_end = nullptr;
     float *stem_w = nullptr, *stem_scale = nullptr, *stem_shift = nullptr;
     void* stem_tc_img = nullptr;      // tensor-core stem: packed weight tile + scale*2^-e
     float* stem_tc_scale = nullptr;
@@ -197,23 +203,55 @@ namespace usot {
         }                                \
     } while (0)
 
-static int upload(usot_engine* e, const std::vector<float>& h, float** out) {
-    void* d = nullptr;
-    USOT_CUDA_OK(cudaMalloc(&d, h.size() * sizeof(float)));
-    USOT_CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
-    e->owned.push_back(d);
-    e->weight_bytes += (int64_t)h.size() * sizeof(float);
-    *out = static_cast<float*>(d);
+// Next record of an imported packed image: [u64 bytes][payload, padded to 8 bytes]
+static int replay_next(usot_engine* e, const uint8_t** data, size_t* bytes) {
+    USOT_REQUIRE(e->replay + 8 <= e->replay_end, "packed weight image is truncated");
+    uint64_t n = 0;
+    memcpy(&n, e->replay, 8);
+    const uint8_t* p = e->replay + 8;
+    const size_t padded = (size_t)((n + 7) & ~uint64_t(7));
+    USOT_REQUIRE(padded <= (size_t)(e->replay_end - p), "packed weight image is truncated");
+    *data = p;
+    *bytes = (size_t)n;
+    e->replay = p + padded;
     return 0;
 }
 
-static int upload_half(usot_engine* e, const std::vector<__half>& h, __half** out) {
+// Upload one packed buffer (or, when replaying an imported image, the next record instead of `host`; `expect` = 0 skips the size check).
+static int upload_bytes(usot_engine* e, const void* host, size_t bytes, size_t expect, void** out) {
+    if (e->replay) {
+        const uint8_t* p = nullptr;
+        if (int rc = replay_next(e, &p, &bytes)) return rc;
+        USOT_REQUIRE(expect == 0 || bytes == expect, "packed weight image does not match this architecture / precision");
+        host = p;
+    }
     void* d = nullptr;
-    USOT_CUDA_OK(cudaMalloc(&d, h.size() * sizeof(__half)));
-    USOT_CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    USOT_CUDA_OK(cudaMalloc(&d, bytes ? bytes : 1));
+    USOT_CUDA_OK(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
     e->owned.push_back(d);
-    e->weight_bytes += (int64_t)h.size() * sizeof(__half);
-    *out = static_cast<__half*>(d);
+    e->weight_bytes += (int64_t)bytes;
+    e->records.push_back({d, {}, bytes});
+    *out = d;
+    return 0;
+}
+static int upload(usot_engine* e, const std::vector<float>& h, float** out, size_t expect_count = 0) {
+    return upload_bytes(e, h.data(), h.size() * sizeof(float), expect_count * sizeof(float), reinterpret_cast<void**>(out));
+}
+static int upload_half(usot_engine* e, const std::vector<__half>& h, __half** out, size_t expect_count = 0) {
+    return upload_bytes(e, h.data(), h.size() * sizeof(__half), expect_count * sizeof(__half), reinterpret_cast<void**>(out));
+}
+// Small host-side constants that finalize() derives from the state_dict (softmaxed GroupDW weights) travel in the image too.
+static int host_record(usot_engine* e, float* data, size_t count) {
+    if (e->replay) {
+        const uint8_t* p = nullptr;
+        size_t bytes = 0;
+        if (int rc = replay_next(e, &p, &bytes)) return rc;
+        USOT_REQUIRE(bytes == count * sizeof(float), "packed weight image does not match this architecture / precision");
+        memcpy(data, p, bytes);
+    }
+    usot_engine::Record r{nullptr, {}, count * sizeof(float)};
+    r.host.assign(reinterpret_cast<uint8_t*>(data), reinterpret_cast<uint8_t*>(data) + count * sizeof(float));
+    e->records.push_back(std::move(r));
     return 0;
 }
 
@@ -250,86 +288,112 @@ static int fold_bn(usot_engine* e, const std::string& conv, const std::string& b
     return 0;
 }
 
+// Packs every weight (BN folding in double, layout changes, fp16 hi/lo split) and uploads the result.  With e->replay set
+// (usot_engine_import_packed) nothing is computed and no state_dict tensor is needed: each upload takes the next record of the
+// imported image instead, in the same order.
 static int finalize_impl(usot_engine* e) {
     USOT_CUDA_OK(cudaSetDevice(e->device));
     for (void* p : e->owned) cudaFree(p);
     e->owned.clear();
     e->convs.clear();
+    e->records.clear();
     e->weight_bytes = 0;
+    e->finalized = false;
+    const bool rp = e->replay != nullptr;
+    const bool tc = e->precision != USOT_PREC_FP32_SIMT;
     std::vector<float> scale, shift, packed;
     {   // stem: OIHW (64,3,7,7) -> [(c*7+kh)*7+kw][co]
-        const auto* w = find(e, "features.features.conv1.weight", 64 * 147);
-        if (!w) return 3;
-        packed.assign(147 * 64, 0.f);
-        for (int co = 0; co < 64; ++co)
-            for (int k = 0; k < 147; ++k) packed[(size_t)k * 64 + co] = (*w)[(size_t)co * 147 + k];
-        if (int rc = fold_bn(e, "features.features.conv1", "features.features.bn1", 64, false, scale, shift)) return rc;
-        if (upload(e, packed, &e->stem_w) || upload(e, scale, &e->stem_scale) || upload(e, shift, &e->stem_shift)) return 1;
-        if (e->precision != USOT_PREC_FP32_SIMT) {
-            std::vector<uint8_t> img;
-            std::vector<float> scale_tc;
-            pack_stem_tc_host(w->data(), scale.data(), img, scale_tc);
-            std::vector<float> as_f(img.size() / 4);
-            memcpy(as_f.data(), img.data(), img.size());
+        std::vector<uint8_t> img;
+        std::vector<float> scale_tc, as_f;
+        if (!rp) {
+            const auto* w = find(e, "features.features.conv1.weight", 64 * 147);
+            if (!w) return 3;
+            packed.assign(147 * 64, 0.f);
+            for (int co = 0; co < 64; ++co)
+                for (int k = 0; k < 147; ++k) packed[(size_t)k * 64 + co] = (*w)[(size_t)co * 147 + k];
+            if (int rc = fold_bn(e, "features.features.conv1", "features.features.bn1", 64, false, scale, shift)) return rc;
+            if (tc) {
+                pack_stem_tc_host(w->data(), scale.data(), img, scale_tc);
+                as_f.resize(img.size() / 4);
+                memcpy(as_f.data(), img.data(), img.size());
+            }
+        }
+        if (upload(e, packed, &e->stem_w, 147 * 64) || upload(e, scale, &e->stem_scale, 64) || upload(e, shift, &e->stem_shift, 64)) return 1;
+        if (tc) {
             float* d = nullptr;
-            if (upload(e, as_f, &d) || upload(e, scale_tc, &e->stem_tc_scale)) return 1;
+            if (upload(e, as_f, &d) || upload(e, scale_tc, &e->stem_tc_scale, 64)) return 1;
             e->stem_tc_img = d;
         }
     }
     for (const ConvSpec& s : build_specs()) {
         const int K = s.k * s.k * s.cin;
-        const auto* w = find(e, s.name + ".weight", (size_t)s.cout * K);
-        if (!w) return 3;
-        packed.assign((size_t)K * s.cout, 0.f);
-        for (int co = 0; co < s.cout; ++co)
-            for (int c = 0; c < s.cin; ++c)
-                for (int t = 0; t < s.k * s.k; ++t)
-                    packed[((size_t)t * s.cin + c) * s.cout + co] = (*w)[((size_t)co * s.cin + c) * s.k * s.k + t];
-        if (int rc = fold_bn(e, s.name, s.bn, s.cout, s.bias, scale, shift)) return rc;
+        std::vector<__half> hi, lo;
+        std::vector<float> scale_tc;
+        if (!rp) {
+            const auto* w = find(e, s.name + ".weight", (size_t)s.cout * K);
+            if (!w) return 3;
+            packed.assign((size_t)K * s.cout, 0.f);
+            for (int co = 0; co < s.cout; ++co)
+                for (int c = 0; c < s.cin; ++c)
+                    for (int t = 0; t < s.k * s.k; ++t)
+                        packed[((size_t)t * s.cin + c) * s.cout + co] = (*w)[((size_t)co * s.cin + c) * s.k * s.k + t];
+            if (int rc = fold_bn(e, s.name, s.bn, s.cout, s.bias, scale, shift)) return rc;
+            if (tc) pack_tc_weights_host(packed.data(), K, s.cout, scale.data(), hi, lo, scale_tc);
+        }
         ConvW cw;
         cw.s = s;
-        if (upload(e, packed, &cw.w_kn) || upload(e, scale, &cw.scale) || upload(e, shift, &cw.shift)) return 1;
-        if (e->precision != USOT_PREC_FP32_SIMT) {
-            std::vector<__half> hi, lo;
-            std::vector<float> scale_tc;
-            pack_tc_weights_host(packed.data(), K, s.cout, scale.data(), hi, lo, scale_tc);
-            if (upload_half(e, hi, &cw.w_hi) || upload_half(e, lo, &cw.w_lo) || upload(e, scale_tc, &cw.scale_tc)) return 1;
-        }
+        const size_t nw = (size_t)K * s.cout;
+        if (upload(e, packed, &cw.w_kn, nw) || upload(e, scale, &cw.scale, s.cout) || upload(e, shift, &cw.shift, s.cout)) return 1;
+        if (tc)
+            if (upload_half(e, hi, &cw.w_hi, nw) || upload_half(e, lo, &cw.w_lo, nw) || upload(e, scale_tc, &cw.scale_tc, s.cout)) return 1;
         e->convs[s.name] = cw;
     }
     auto pack_pred = [&](const std::string& name, int cout, PredW& pw) -> int {
-        const auto* w = find(e, name + ".weight", (size_t)cout * 256 * 9);
-        const auto* b = find(e, name + ".bias", cout);
-        if (!w || !b) return 3;
-        packed.assign((size_t)9 * cout * 256, 0.f);
-        for (int co = 0; co < cout; ++co)
-            for (int c = 0; c < 256; ++c)
-                for (int t = 0; t < 9; ++t) packed[((size_t)t * cout + co) * 256 + c] = (*w)[((size_t)co * 256 + c) * 9 + t];
+        std::vector<float> packed4, bias;
+        const size_t nw = (size_t)9 * cout * 256;
+        if (!rp) {
+            const auto* w = find(e, name + ".weight", nw);
+            const auto* b = find(e, name + ".bias", cout);
+            if (!w || !b) return 3;
+            packed.assign(nw, 0.f);
+            for (int co = 0; co < cout; ++co)
+                for (int c = 0; c < 256; ++c)
+                    for (int t = 0; t < 9; ++t) packed[((size_t)t * cout + co) * 256 + c] = (*w)[((size_t)co * 256 + c) * 9 + t];
+            packed4.resize(nw);
+            for (int k = 0; k < 9 * cout; ++k)
+                for (int c = 0; c < 256; ++c) packed4[((size_t)(c / 4) * 9 * cout + k) * 4 + (c & 3)] = packed[(size_t)k * 256 + c];
+            bias = *b;
+        }
         pw.cout = cout;
-        std::vector<float> packed4(packed.size());
-        for (int k = 0; k < 9 * cout; ++k)
-            for (int c = 0; c < 256; ++c) packed4[((size_t)(c / 4) * 9 * cout + k) * 4 + (c & 3)] = packed[(size_t)k * 256 + c];
-        if (upload(e, packed, &pw.w) || upload(e, packed4, &pw.w4) || upload(e, *b, &pw.b)) return 1;
+        if (upload(e, packed, &pw.w, nw) || upload(e, packed4, &pw.w4, nw) || upload(e, bias, &pw.b, cout)) return 1;
         return 0;
     };
     if (int rc = pack_pred("connect_model.bbox_pred", 4, e->bbox_pred)) return rc;
     if (int rc = pack_pred("connect_model.cls_pred", 1, e->cls_pred)) return rc;
     if (int rc = pack_pred("connect_model.cls_memory_pred", 1, e->cls_memory_pred)) return rc;
     auto softmax3 = [&](const std::string& name, float* out) -> int {
-        const auto* w = find(e, name, 3);
-        if (!w) return 3;
-        double m = std::fmax((*w)[0], std::fmax((*w)[1], (*w)[2]));
-        double ex[3], s = 0;
-        for (int i = 0; i < 3; ++i) { ex[i] = std::exp((double)(*w)[i] - m); s += ex[i]; }
-        for (int i = 0; i < 3; ++i) out[i] = (float)(ex[i] / s);
-        return 0;
+        if (!rp) {
+            const auto* w = find(e, name, 3);
+            if (!w) return 3;
+            double m = std::fmax((*w)[0], std::fmax((*w)[1], (*w)[2]));
+            double ex[3], sum = 0;
+            for (int i = 0; i < 3; ++i) { ex[i] = std::exp((double)(*w)[i] - m); sum += ex[i]; }
+            for (int i = 0; i < 3; ++i) out[i] = (float)(ex[i] / sum);
+        }
+        return host_record(e, out, 3);
     };
     if (int rc = softmax3("connect_model.cls_dw.weight", e->dw_cls)) return rc;
     if (int rc = softmax3("connect_model.reg_dw.weight", e->dw_reg)) return rc;
-    const auto* adj = find(e, "connect_model.adjust", 1);
-    const auto* b4 = find(e, "connect_model.bias", 4);
-    if (!adj || !b4) return 3;
-    if (upload(e, *adj, &e->adjust) || upload(e, *b4, &e->bias4)) return 1;
+    std::vector<float> adj, b4;
+    if (!rp) {
+        const auto* a1 = find(e, "connect_model.adjust", 1);
+        const auto* a4 = find(e, "connect_model.bias", 4);
+        if (!a1 || !a4) return 3;
+        adj = *a1;
+        b4 = *a4;
+    }
+    if (upload(e, adj, &e->adjust, 1) || upload(e, b4, &e->bias4, 4)) return 1;
+    if (rp) USOT_REQUIRE(e->replay == e->replay_end, "packed weight image has trailing data (built for another architecture?)");
     USOT_CUDA_OK(cudaDeviceSynchronize());
     e->finalized = true;
     return 0;
@@ -621,7 +685,7 @@ static int g_graph_max_batch = 8;  // tunable "graph_max_batch": track() with n 
 extern "C" {
 
 const char* usot_last_error(void) { return g_err.c_str(); }
-int usot_abi_version(void) { return 1; }
+int usot_abi_version(void) { return 2; }
 
 /* Profiling: kernel launches are always counted; with on=1 every launch is also bracketed by CUDA events on its stream. */
 int usot_profile_reset(int on) {
@@ -808,6 +872,56 @@ int usot_engine_finalize(usot_engine* e) {
     USOT_REQUIRE(e, "null engine");
     std::lock_guard<std::mutex> lk(e->mu);
     return finalize_impl(e);
+}
+
+/* Packed-weight image: header {magic, abi, precision, record count} + records [u64 bytes][payload padded to 8]. */
+static const uint64_t kPackedMagic = 0x55534f5442323030ull;  // "USOTB200"
+
+int64_t usot_engine_packed_size(const usot_engine* e) {
+    if (!e || !e->finalized) return 0;
+    int64_t n = 32;
+    for (const auto& r : e->records) n += 8 + (int64_t)((r.bytes + 7) & ~size_t(7));
+    return n;
+}
+
+int usot_engine_export_packed(usot_engine* e, void* host_buf, int64_t capacity) {
+    USOT_REQUIRE(e && e->finalized, "engine not finalized");
+    USOT_REQUIRE(host_buf && capacity >= usot_engine_packed_size(e), "buffer too small (see usot_engine_packed_size)");
+    std::lock_guard<std::mutex> lk(e->mu);
+    USOT_CUDA_OK(cudaSetDevice(e->device));
+    uint8_t* p = static_cast<uint8_t*>(host_buf);
+    const uint64_t hdr[4] = {kPackedMagic, (uint64_t)usot_abi_version(), (uint64_t)e->precision, (uint64_t)e->records.size()};
+    memcpy(p, hdr, 32);
+    p += 32;
+    for (const auto& r : e->records) {
+        const uint64_t n = r.bytes;
+        memcpy(p, &n, 8);
+        p += 8;
+        if (r.dev) USOT_CUDA_OK(cudaMemcpy(p, r.dev, r.bytes, cudaMemcpyDeviceToHost));
+        else memcpy(p, r.host.data(), r.bytes);
+        const size_t padded = (r.bytes + 7) & ~size_t(7);
+        memset(p + r.bytes, 0, padded - r.bytes);
+        p += padded;
+    }
+    return 0;
+}
+
+int usot_engine_import_packed(usot_engine* e, const void* host_buf, int64_t size) {
+    USOT_REQUIRE(e && host_buf && size >= 32, "bad argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    const uint8_t* p = static_cast<const uint8_t*>(host_buf);
+    uint64_t hdr[4];
+    memcpy(hdr, p, 32);
+    USOT_REQUIRE(hdr[0] == kPackedMagic, "not a usot_b200 packed weight image");
+    USOT_REQUIRE(hdr[1] == (uint64_t)usot_abi_version(), "packed weight image was written by another ABI version");
+    USOT_REQUIRE(hdr[2] == (uint64_t)e->precision, "packed weight image was written for another precision mode");
+    e->replay = p + 32;
+    e->replay_end = p + size;
+    int rc = finalize_impl(e);
+    if (rc == 0 && e->records.size() != hdr[3]) { set_error("usot_b200: packed weight image has an unexpected record count"); rc = 2; }
+    e->replay = e->replay_end = nullptr;
+    if (rc) e->finalized = false;
+    return rc;
 }
 
 int64_t usot_engine_device_bytes(const usot_engine* e) { return e ? e->weight_bytes + (int64_t)e->arena.cap : 0; }

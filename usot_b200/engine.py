@@ -4,6 +4,7 @@ All feature maps that cross this boundary are contiguous NHWC fp32 CUDA tensors;
 NCHW like the reference.  torch only provides device memory and the current stream.
 """
 import ctypes
+import os
 
 import torch
 
@@ -41,9 +42,25 @@ class Engine:
             pass
 
     # ---- weights -------------------------------------------------------------------------------------
-    def load_state_dict(self, state_dict):
-        """Stage every float tensor of a reference-layout state_dict and (re)pack.  Synchronises the device."""
+    def load_state_dict(self, state_dict, cache_dir=None):
+        """Stage every float tensor of a reference-layout state_dict and (re)pack.  Synchronises the device.
+
+        ``cache_dir`` (default: $USOT_B200_WEIGHT_CACHE, unset = no cache): directory of packed-weight images keyed by
+        sha256(state_dict) + precision + ABI version.  A hit restores the engine with one read + upload instead of the
+        host-side BN folding / fp16 splitting; a miss packs as usual and writes the image (atomically) for the next start."""
         lib = _lib.load()
+        cache_dir = cache_dir if cache_dir is not None else os.environ.get("USOT_B200_WEIGHT_CACHE")
+        path = None
+        if cache_dir:
+            from .checkpoint import state_dict_hash
+            key = "{}_{}_abi{}.usotw".format(state_dict_hash(state_dict)[:32], self.precision, lib.usot_abi_version())
+            path = os.path.join(cache_dir, key)
+            if os.path.exists(path):
+                try:
+                    self.import_packed(path)
+                    return
+                except RuntimeError:  # stale / truncated image: fall through to a fresh pack and overwrite it
+                    pass
         for k, v in state_dict.items():
             if not torch.is_tensor(v) or not v.dtype.is_floating_point:
                 continue  # num_batches_tracked
@@ -51,6 +68,28 @@ class Engine:
             _lib.check(lib.usot_engine_load_tensor(self._h, k.encode(), _lib.ptr(h), h.numel()))
         with torch.cuda.device(self.device):
             _lib.check(lib.usot_engine_finalize(self._h))
+        if path:
+            os.makedirs(cache_dir, exist_ok=True)
+            self.export_packed(path)
+
+    def export_packed(self, path):
+        """Write the packed-weight image of this (finalized) engine to ``path`` (atomic rename)."""
+        lib = _lib.load()
+        n = int(lib.usot_engine_packed_size(self._h))
+        buf = torch.empty(n, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.usot_engine_export_packed(self._h, _lib.ptr(buf), n))
+        tmp = "{}.tmp{}".format(path, os.getpid())
+        buf.numpy().tofile(tmp)
+        os.replace(tmp, path)
+        return n
+
+    def import_packed(self, path):
+        """Restore the weights from an image written by export_packed (same precision / ABI version; otherwise RuntimeError)."""
+        import numpy as np
+        buf = torch.from_numpy(np.fromfile(path, dtype=np.uint8))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().usot_engine_import_packed(self._h, _lib.ptr(buf), buf.numel()))
 
     def device_bytes(self):
         return int(_lib.load().usot_engine_device_bytes(self._h))

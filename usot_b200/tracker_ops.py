@@ -140,10 +140,10 @@ def update_device(net, x_crops, target_pos, target_sz, window, scale_z, p, queue
 
 
 def upload_frame(im, device="cuda"):
-    """cv2 frame (H,W,3) uint8 numpy -> (1,H,W,3) uint8 CUDA tensor (accepts an already-uploaded tensor)."""
+    """cv2 frame (H,W,3) -- or a stack (F,H,W,3) -- uint8 numpy -> (F,H,W,3) uint8 CUDA tensor (accepts an already-uploaded tensor)."""
     if isinstance(im, np.ndarray):
-        if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
-            raise AssertionError("frames must be (H, W, 3) uint8 arrays as cv2.imread returns them")
+        if im.dtype != np.uint8 or im.ndim not in (3, 4) or im.shape[-1] != 3:
+            raise AssertionError("frames must be (H, W, 3) or (F, H, W, 3) uint8 arrays as cv2.imread returns them")
         im = torch.from_numpy(np.ascontiguousarray(im)).to(device, non_blocking=True)
     _need_cuda(im)
     if im.dtype != torch.uint8:
