@@ -58,6 +58,10 @@ class MemoryQueue:
         self._mem_rows = [self._first]
         self.confidences = [0.9]
 
+    def __len__(self):
+        """len(state['memory_features']) of the reference."""
+        return len(self._mem_rows)
+
     def _append_raw(self, feat_nchw):
         if self._n == self._buf.shape[0]:
             new = torch.empty((2 * self._n,) + tuple(self._buf.shape[1:]), dtype=torch.float32, device=self.device)
