@@ -257,7 +257,7 @@ def main():
         pr_gbs = pr["bytes"] / (pr["ms"] / 1e3) / 1e9 if pr["ms"] > 0 else 0.0
         step_ms_prof = sum(f["ms"] for f in prof.values()) / nprof
         traffic = {}
-        tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r01b_roofline_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f)
@@ -275,7 +275,7 @@ def main():
                          "bound": "tensor", "achieved": conv_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": conv_tflops / pk["tflops_sustained"],
                          "traffic": traffic.get("conv_tc_kernel", {}).get("traffic_bytes_per_launch"),
-                         "traffic_note": "dram bytes of the dominant launch (layer3.0.downsample) from profiles/r01_roofline_traffic.json; equals its algorithmic bytes",
+                         "traffic_note": "dram bytes of the dominant launch (layer3.0.downsample) from profiles/r01b_roofline_traffic.json (ncu --set full); equals its algorithmic bytes",
                          "peak_source": pk["source"] + ", bf16 dense sustained",
                          "achieved_is": "ALGORITHMIC conv FLOPs / summed CUDA-event time of the family's launches (profiled pass of the same step)",
                          "executed_mma_tflops": conv_tflops * mma_per_flop, "executed_mma_frac": conv_tflops * mma_per_flop / pk["tflops_sustained"],

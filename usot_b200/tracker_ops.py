@@ -210,7 +210,30 @@ def crop_geometry(im_shape, pos, model_sz, original_sz, target_sz=None, need_bbo
     return int(xmin), int(ymin), info
 
 
-def get_subwindow_tracking(im, pos, model_sz, original_sz, avg_chans, target_sz=None, out_mode='torch', need_bbox=False, vis=False):
+class FrameStager:
+    """Per-video staging of cv2 frames: one pinned host buffer + one device buffer of the frame size, reused every frame, so the
+    upload is a host memcpy into pinned memory followed by an asynchronous H2D copy on the current stream."""
+
+    def __init__(self, shape, device):
+        self.pinned = torch.empty(tuple(shape), dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty((1,) + tuple(shape), dtype=torch.uint8, device=device)
+        self.done = torch.cuda.Event()
+        self._first = True
+
+    def upload(self, im):
+        if tuple(im.shape) != tuple(self.pinned.shape) or im.dtype != np.uint8:
+            raise AssertionError("frame shape / dtype changed inside one video")
+        if not self._first:
+            self.done.synchronize()  # the previous H2D copy has left the pinned buffer
+        self._first = False
+        self.pinned.numpy()[...] = im
+        self.dev[0].copy_(self.pinned, non_blocking=True)
+        self.done.record()
+        return self.dev
+
+
+def get_subwindow_tracking(im, pos, model_sz, original_sz, avg_chans, target_sz=None, out_mode='torch', need_bbox=False, vis=False,
+                           fill=None):
     """Drop-in for lib.utils.track_utils.get_subwindow_tracking (same arguments, same crop_info) producing the patch on the GPU.
 
     ``im`` is the cv2 frame (numpy uint8, uploaded here) or an ``upload_frame`` tensor, so a caller cropping several windows of
@@ -223,5 +246,11 @@ def get_subwindow_tracking(im, pos, model_sz, original_sz, avg_chans, target_sz=
     xmin, ymin, info = crop_geometry((h, w), pos, model_sz, original_sz, target_sz, need_bbox)
     dev = frames.device
     crops = torch.tensor([[0, xmin, ymin, int(original_sz)]], dtype=torch.int32).to(dev, non_blocking=True)
-    fill = torch.from_numpy(np.asarray(avg_chans, np.float64).astype(np.uint8).reshape(1, 3)).to(dev, non_blocking=True)
+    if fill is None:  # (callers cropping many windows of one video pass the cached device copy: the means are per-video constants)
+        fill = fill_color(avg_chans, dev)
     return crop_resize(frames[:1], crops, fill, model_sz)[0], info
+
+
+def fill_color(avg_chans, device):
+    """(1,3) uint8 device tensor of the channel means truncated as the reference's uint8 canvas stores them (track_utils.py:58-70)."""
+    return torch.from_numpy(np.asarray(avg_chans, np.float64).astype(np.uint8).reshape(1, 3)).to(device, non_blocking=True)
