@@ -52,7 +52,25 @@ def test_ops_reject_cpu_tensors():
 
 def test_namespace_shadowing():
     """lib.models.models resolves to this repo when it precedes a reference-like tree on PYTHONPATH."""
-    code = "import lib.models.models as m, usot_b200; assert m.USOT is usot_b200.USOT; print('shadow-ok')"
+    code = ("import lib.models.models as m, lib.tracker.usot_tracker as t, usot_b200, usot_b200.tracker as ut; "
+            "assert m.USOT is usot_b200.USOT and t.USOTTracker is ut.USOTTracker and t.USOTConfig is ut.USOTConfig; print('shadow-ok')")
     env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "shadow-ok" in r.stdout, r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("USOT_REFERENCE", "/root/reference")), reason="reference tree not present (GPU box)")
+def test_namespace_shadowing_leaves_the_rest_of_the_reference_visible():
+    """With this repo BEFORE the reference on PYTHONPATH, lib.models.models / lib.tracker.usot_tracker come from
+    here and lib.utils.* still comes from the reference, whose load_pretrain / get_subwindow_tracking signatures we mirror."""
+    ref = os.environ.get("USOT_REFERENCE", "/root/reference")
+    code = ("import inspect, lib.models.models as m, lib.tracker.usot_tracker as t, lib.utils.track_utils as tu, lib.utils.train_utils as tr, "
+            "usot_b200.tracker_ops as ops, usot_b200.checkpoint as ck; "
+            f"assert m.__file__.startswith({ROOT!r}) and t.__file__.startswith({ROOT!r}) and tu.__file__.startswith({ref!r}); "
+            "a = list(inspect.signature(tu.get_subwindow_tracking).parameters); b = list(inspect.signature(ops.get_subwindow_tracking).parameters); "
+            "assert b[:len(a)] == a, (a, b); "
+            "a = list(inspect.signature(tr.load_pretrain).parameters); b = list(inspect.signature(ck.load_pretrain).parameters); "
+            "assert b[:len(a)] == a, (a, b); print('shadow-ok')")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + ref)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and "shadow-ok" in r.stdout, r.stderr

@@ -202,8 +202,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int eall = threadIdx.x - 128;        // 0..255 over both groups
         const uint32_t s_out_u32 = smem_u32(s_out);
         uint32_t gc = 0;                      // running chunk counter: selects the store-staging buffer
-        if (eall == 0 && p.tma_store) { tma_prefetch_desc(&p.o[0]); tma_prefetch_desc(&p.o[1]); }
-        if (eall == 32 && p.tma_res) { tma_prefetch_desc(&p.r[0]); tma_prefetch_desc(&p.r[1]); }
+        // (single-fp16 mode has no lo planes: nothing is loaded, staged or stored for them)
+        if (eall == 0 && p.tma_store) { tma_prefetch_desc(&p.o[0]); if (SPLIT) tma_prefetch_desc(&p.o[1]); }
+        if (eall == 32 && p.tma_res) { tma_prefetch_desc(&p.r[0]); if (SPLIT) tma_prefetch_desc(&p.r[1]); }
         // TMA-prefetched residual: the group's leader requests chunk j+1 into staging buffer (j+1) % 3 while chunk j is being
         // processed; that buffer was last used by chunk j-2, whose bulk store has finished reading when wait_group.read 1 returns.
         auto issue_res = [&](int t, int c0, uint32_t b) {
@@ -213,9 +214,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int th_ = mt_ % p.tiles_h;
             const int img_ = mt_ / p.tiles_h;
             const uint32_t dst = s_out_u32 + (eg * p.nbuf + b) * Cfg::BUF_BYTES, rb = bar_res + 8 * (eg * 3 + b);
-            mbar_expect_tx(rb, 2u * p.bw * p.bh * 64u);
+            mbar_expect_tx(rb, (SPLIT ? 2u : 1u) * p.bw * p.bh * 64u);
             tma_load_4d(dst, &p.r[0], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
-            tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
+            if (SPLIT) tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
         };
         if (p.tma_res && et == 0 && (int)blockIdx.x < p.num_tiles && eg * 32 < BN) issue_res(blockIdx.x, eg * 32, 0);
         int it = 0;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0 + cfirst) + q);
-                    rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + cfirst) + q);
+                    rl[q] = SPLIT ? __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + cfirst) + q) : make_uint4(0, 0, 0, 0);
                 }
             }
             mbar_wait(bar_tfull + 8 * as, aphase);
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         rh[q] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + off0 + c0 + cstep) + q);
-                        rl[q] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + c0 + cstep) + q);
+                        rl[q] = SPLIT ? __ldg(reinterpret_cast<const uint4*>(p.res_lo + off0 + c0 + cstep) + q) : make_uint4(0, 0, 0, 0);
                     }
                 }
                 if (Cfg::XACC) {
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint4 a = *reinterpret_cast<const uint4*>(rp + ((q ^ sw) << 4));
-                                const uint4 b = *reinterpret_cast<const uint4*>(rp + TC_BM * 64 + ((q ^ sw) << 4));
+                                const uint4 b = SPLIT ? *reinterpret_cast<const uint4*>(rp + TC_BM * 64 + ((q ^ sw) << 4)) : make_uint4(0, 0, 0, 0);
                                 const __half2* ah = reinterpret_cast<const __half2*>(&a);
                                 const __half2* bl = reinterpret_cast<const __half2*>(&b);
 #pragma unroll
@@ -368,14 +369,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                 bl[e] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
                             }
                             *reinterpret_cast<uint4*>(rp + ((q ^ sw) << 4)) = a;
-                            *reinterpret_cast<uint4*>(rp + TC_BM * 64 + ((q ^ sw) << 4)) = b;
+                            if (SPLIT) *reinterpret_cast<uint4*>(rp + TC_BM * 64 + ((q ^ sw) << 4)) = b;
                         }
                         fence_proxy_async_smem();
                         asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
                         if (et == 0) {
                             const uint32_t src = s_out_u32 + buf * Cfg::BUF_BYTES;
                             tma_store_4d(&p.o[0], src, n0 + c0, tw * p.bw, th * p.bh, img);
-                            tma_store_4d(&p.o[1], src + TC_BM * 64, n0 + c0, tw * p.bw, th * p.bh, img);
+                            if (SPLIT) tma_store_4d(&p.o[1], src + TC_BM * 64, n0 + c0, tw * p.bw, th * p.bh, img);
                             bulk_commit();
                         }
                         ++gc;
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                 bl[e] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
                             }
                             oh4[q] = a;
-                            ol4[q] = b;
+                            if (SPLIT) ol4[q] = b;
                         }
                     }
                     if (p.out_f32 && valid) {
@@ -522,8 +523,8 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     p.res_hi = ep.res_hi; p.res_lo = ep.res_lo;
     p.out_hi = ep.out_hi; p.out_lo = ep.out_lo; p.out_f32 = ep.out_f32;
     p.relu = ep.relu;
-    USOT_REQUIRE(!p.res_hi || p.res_lo, "conv_tc: residual needs both planes");
-    USOT_REQUIRE(!p.out_hi || p.out_lo, "conv_tc: split output needs both planes");
+    USOT_REQUIRE(!split || !p.res_hi || p.res_lo, "conv_tc: split-mode residual needs both planes");
+    USOT_REQUIRE(!split || !p.out_hi || p.out_lo, "conv_tc: split-mode output needs both planes");
 
     // ---- activation maps: dims {C, W', H', N}, one per (plane, parity) ----
     const int planes = split ? 2 : 1;
@@ -569,11 +570,13 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         cuuint64_t os[3] = {(cuuint64_t)g.cout * 2, (cuuint64_t)g.wo * g.cout * 2, (cuuint64_t)g.ho * g.wo * g.cout * 2};
         cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
         if (int rc = encode_map(&p.o[0], p.out_hi, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-        if (int rc = encode_map(&p.o[1], p.out_lo, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+        if (split) { if (int rc = encode_map(&p.o[1], p.out_lo, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc; }
+        else p.o[1] = p.o[0];
         if (p.res_hi && g_tc_tma_res) {
             p.tma_res = 1;
             if (int rc = encode_map(&p.r[0], p.res_hi, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-            if (int rc = encode_map(&p.r[1], p.res_lo, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+            if (split) { if (int rc = encode_map(&p.r[1], p.res_lo, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc; }
+            else p.r[1] = p.r[0];
         }
     }
 

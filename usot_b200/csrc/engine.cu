@@ -410,8 +410,6 @@ struct Ctx {
     bool split() const { return e->precision == USOT_PREC_FP16X3_TC; }
 };
 
-static inline int conv_hw(int in, int k, int s, int p, int d) { return conv_out(in, k, s, p, d); }
-
 // make sure `t` has the fp16 planes the tensor-core path reads (hi always, lo in split mode)
 static int ensure_split(Ctx& c, T& t) {
     Arena& ar = c.ar;
@@ -463,18 +461,10 @@ static int run_conv(Ctx& c, const std::string& name, T& in, T* residual, int wan
             o.hi = ar.h(o.numel());
             o.lo = c.split() ? ar.h(o.numel()) : nullptr;
         }
-        // in single-fp16 mode the lo planes do not exist: write into a scratch plane so the kernel has one code path
-        __half* lo_dst = o.lo;
-        if ((want & OUT_SPLIT) && !lo_dst) lo_dst = ar.h(o.numel());
-        const __half* res_lo = residual ? (residual->lo ? residual->lo : nullptr) : nullptr;
+        // (in single-fp16 mode the lo planes do not exist: the kernel neither reads nor writes them)
         TcTensor ti{in.hi, in.lo};
         TcWeights tw{cw.w_hi, cw.w_lo, cw.scale_tc, g.kh * g.kw * g.cin};
-        TcEpilogue ep{cw.shift, residual ? residual->hi : nullptr, res_lo, o.hi, lo_dst, o.f, cw.s.relu ? 1 : 0};
-        if (residual && !res_lo) {  // single-fp16 mode: an all-zero lo plane is not stored; reuse hi with a zeroed scratch instead
-            __half* z = ar.h(o.numel());
-            if (!ar.plan) USOT_CUDA_OK(cudaMemsetAsync(z, 0, o.numel() * sizeof(__half), c.st));
-            ep.res_lo = z;
-        }
+        TcEpilogue ep{cw.shift, residual ? residual->hi : nullptr, residual ? residual->lo : nullptr, o.hi, o.lo, o.f, cw.s.relu ? 1 : 0};
         if (!ar.plan) {
             Scope sc(FAM_CONV, c.st, flops);
             RUN(launch_conv_tc(ti, g, tw, ep, c.split(), c.st));
