@@ -63,6 +63,12 @@ static __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// Hint: pull one tensor box into L2 (no shared-memory destination, no completion tracking).
+static __device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 static __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 static __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
