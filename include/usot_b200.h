@@ -27,6 +27,7 @@
  *   usot_engine_backbone_neck        <- feature_extractor + neck         lib/models/models.py:39-40,181-184
  *   usot_engine_forward_train        <- USOT_.forward                    lib/models/models.py:208-295
  *   usot_tracker_postprocess         <- USOTTracker.update tensor path   lib/tracker/usot_tracker.py:137-163
+ *   usot_engine_track_frame          <- USOTTracker.track + update       lib/tracker/usot_tracker.py:133-276 (one call per frame)
  *   usot_crop_resize                 <- get_subwindow_tracking + cv2.resize  lib/utils/track_utils.py:30-119 (im_to_torch :24-27)
  *   usot_engine_load_tensor/finalize <- load_state_dict contract         lib/utils/train_utils.py:92-128
  */
@@ -53,7 +54,7 @@ enum {
 USOT_API const char* usot_last_error(void);
 USOT_API int usot_abi_version(void);
 /* Process-wide performance knobs (never change results): "groupdw_strips" = 2 | 3; "tc_bn_max" = 64 | 128 | 256;
- * "tc_l2_prefetch" = 0 | 1 (TMA L2-prefetch hints for the next tile's residual / 1x1 activations, default 1), "tc_tma_f32" = 0 | 1 (fp32-only conv outputs through smem staging + TMA store, default 1), "tc_fuse_cross" = 0 | 1 (split mode: a_hi x [w_hi|w_lo] as one N = 2*BN MMA, default 1), "tc_tma_store" = 0 | 1 (TMA-store epilogue), "tc_tma_res" = 0 | 1 (residual loaded by TMA), "stem_tc" = 0 | 1 (tensor-core stem),
+ * "tc_l2_prefetch" = 0 | 1 (TMA L2-prefetch hints for the next tile's residual / 1x1 activations, default 0), "tc_tma_f32" = 0 | 1 (fp32-only conv outputs through smem staging + TMA store, default 1), "tc_fuse_cross" = 0 | 1 (split mode: a_hi x [w_hi|w_lo] as one N = 2*BN MMA, default 1), "tc_tma_store" = 0 | 1 (TMA-store epilogue), "tc_tma_res" = 0 | 1 (residual loaded by TMA), "stem_tc" = 0 | 1 (tensor-core stem),
  * "groupdw_tma" = 0 | 1 | 2 (register-staged / TMA ring + scalar FMA / TMA ring + packed FFMA2, default 2),
  * "pred_tma_min_batch" = 0.. (batches >= this use the TMA-streamed per-image pred-conv kernel, default 48; 0 = never), "graph_max_batch" = 0..64 (track() with n <= this replays a CUDA graph).
  * One accuracy knob: "tc_split_bn_max" = 64 | 128 (default; separate cross-term accumulator) | 256 (single accumulator). */
@@ -176,6 +177,21 @@ USOT_API int usot_engine_extract_memory_feature(usot_engine* e, const float* ori
 USOT_API int usot_engine_forward_train(usot_engine* e, const float* zf, const float* xf, const float* xf_mem, int n, int m, int feat,
                                        const float* label, const float* reg_target, const float* reg_weight, const float* search_bbox,
                                        float cls_ratio, float* losses, float* backward_map, float* pool_box, void* stream);
+
+/* One whole tracker frame on the device, enqueued on `stream` without any host synchronisation (USOTTracker.track + update,
+ * lib/tracker/usot_tracker.py:133-276, minus the scalar position / size smoothing that stays on the host):
+ *   crop (context window [context_xmin, context_ymin, original_sz] of the uint8 HWC `frame`, fill = truncated channel means,
+ *   resized to instance_size; bit-exact with get_subwindow_tracking)  ->  gather of the nq memory templates
+ *   mem_buf[mem_rows[k]] (mem_rows is a HOST array of row indices into the device-resident queue buffer of (7,7,256) nhwc rows)
+ *   ->  track() with the memory branch  ->  usot_tracker_postprocess  ->  pool_label_search of the winning box  ->  PrPool of
+ *   the new memory feature from xf into feat_out ((7,7,256) nhwc, typically the next free row of the queue buffer).
+ * zf (1,7,7,256) nhwc; window (R,R) float64; target_w/h already multiplied by scale_z; result[8] as usot_tracker_postprocess.
+ * frame, fill (3 bytes), zf, mem_buf, window, result, feat_out are DEVICE pointers. */
+USOT_API int usot_engine_track_frame(usot_engine* e, const uint8_t* frame, int height, int width, int context_xmin, int context_ymin,
+                                     int original_sz, const uint8_t* fill, int instance_size, const float* zf, const float* mem_buf,
+                                     const int32_t* mem_rows, int nq, const double* window, double target_w, double target_h, double ratio,
+                                     double penalty_k, double window_influence, int total_stride, double* result, float* feat_out,
+                                     void* stream);
 
 /* Tensor path of USOTTracker.update for one frame, on the device (no host sync): sigmoid, ratio mix, box decode on the
  * stride-8 grid, size/ratio penalty, cosine window, argmax.  cls / cls_mem (1,1,R,R), bbox (1,4,R,R) nchw fp32; window (R,R)

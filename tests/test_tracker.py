@@ -54,8 +54,8 @@ def test_tracker_mirror_host_logic():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision", ["fp16x3", "fp32"])
-def test_gpu_tracker_follows_reference_trace(precision):
+@pytest.mark.parametrize("precision,fused", [("fp16x3", True), ("fp32", True), ("fp16x3", False)])
+def test_gpu_tracker_follows_reference_trace(precision, fused):
     from usot_b200 import USOT
     from usot_b200.tracker import USOTTracker
     g, frames, pos0, sz0 = _fixture()
@@ -63,6 +63,7 @@ def test_gpu_tracker_follows_reference_trace(precision):
     net.load_state_dict(load_weights("damp025"))
     net = net.eval().cuda()
     tracker = USOTTracker(types.SimpleNamespace(arch="USOT"))
+    tracker.fused_frame = fused  # one usot_engine_track_frame call per frame vs the op-by-op path
     state = tracker.init(frames[0], pos0.copy(), sz0.copy(), net)
     assert tuple(net.zf.shape) == (1, 256, 7, 7)
     rows = []
@@ -75,3 +76,27 @@ def test_gpu_tracker_follows_reference_trace(precision):
     assert np.abs(rows[:, :4] - ref[:, :4]).max() <= 0.1, np.abs(rows - ref).max(axis=0)
     assert np.abs(rows[:, 4] - ref[:, 4]).max() <= 2e-3
     assert len(state['memory_confidences']) == len(frames) and len(state['memory_queue'].selected_rows()[0]) == 7
+
+
+@pytest.mark.gpu
+def test_fused_frame_equals_op_by_op_path():
+    """usot_engine_track_frame must produce exactly what the separate crop / track / postprocess / PrPool calls produce."""
+    from usot_b200 import USOT
+    from usot_b200.tracker import USOTTracker
+    g, frames, pos0, sz0 = _fixture()
+    traces = []
+    for fused in (True, False):
+        net = USOT(precision="fp16x3")
+        net.load_state_dict(load_weights("damp025"))
+        net = net.eval().cuda()
+        tracker = USOTTracker(types.SimpleNamespace(arch="USOT"))
+        tracker.fused_frame = fused
+        state = tracker.init(frames[0], pos0.copy(), sz0.copy(), net)
+        rows = []
+        for im in frames[1:4]:
+            state = tracker.track(state, im)
+            rows.append(np.concatenate([state['target_pos'], state['target_sz'], [state['cls_score']]]))
+        q = state['memory_queue']
+        traces.append((np.array(rows), q._buf[: q._n].clone()))
+    assert np.array_equal(traces[0][0], traces[1][0])
+    assert torch.allclose(traces[0][1], traces[1][1], rtol=0, atol=1e-6)  # pool box: float32 here vs numpy's float64 intermediate

@@ -125,6 +125,11 @@ int launch_iou(const float* bbox, const float* target, const float* weight, int 
 // crop.cu: batched context-window crop + average-colour padding + fixed-point bilinear resize (bit-exact with cv2.resize on uint8)
 int launch_crop_resize(const uint8_t* frames, int n_frames, int H, int W, const int* crops /*[n][4] = frame, xmin, ymin, original_sz*/,
                        const uint8_t* fills /*[n][3]*/, int n, int model_sz, float* out_nchw, cudaStream_t st);
+int launch_crop_resize_one(const uint8_t* frame, int H, int W, int xmin, int ymin, int osz, const uint8_t* fill3, int model_sz, float* out_nchw,
+                           cudaStream_t st);
+// kernels_glue.cu: pieces of the one-call tracker frame (usot_engine_track_frame)
+int launch_gather_rows(const float* buf, const int* rows_host, int n_rows, size_t row_floats, float* out, cudaStream_t st);
+int launch_pool_box_from_result(const double* result, int score_size, int instance_size, int total_stride, float* box4, cudaStream_t st);
 int launch_center_crop_nhwc(const float* in, int n, int h, int w, int c, int l, float* out, cudaStream_t st);
 
 }  // namespace usot

@@ -120,21 +120,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int th = mt % p.tiles_h;
                 const int img = mt / p.tiles_h;
                 const int h0 = th * p.bh, w0 = tw * p.bw;
-                // DRAM-bound 1x1 layers (K <= 1024, ring only 2-4 stages deep): pull the NEXT tile's activation boxes into L2 now,
-                // so its ring loads are L2 hits; every byte is still fetched from HBM once.  (3x3 layers re-read A from L2 per tap.)
-                if (p.l2_prefetch && p.taps == 1 && p.stride == 1 && nb == p.n_tiles_n - 1) {
-                    const int nt = tile + gridDim.x;  // same M tile is shared by the n_tiles_n consecutive tiles: prefetch once
-                    if (nt < p.num_tiles) {
-                        int mt2 = nt / p.n_tiles_n;
-                        const int tw2 = mt2 % p.tiles_w; mt2 /= p.tiles_w;
-                        const int th2 = mt2 % p.tiles_h;
-                        const int img2 = mt2 / p.tiles_h;
-                        for (int cc2 = 0; cc2 < p.cin_chunks; ++cc2) {
-                            tma_prefetch_l2_4d(&p.a[0][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
-                            if (SPLIT) tma_prefetch_l2_4d(&p.a[1][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
-                        }
-                    }
-                }
                 for (int ks = 0; ks < nK; ++ks) {
                     const int tap = ks / p.cin_chunks, cc = ks - tap * p.cin_chunks;
                     const int kh = tap / p.kw, kwi = tap - kh * p.kw;
@@ -157,6 +142,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         tma_load_2d(sb + Cfg::B_BYTES, &p.b[1], full, ks * TC_BK, nb * BN);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                // DRAM-bound 1x1 layers (K <= 1024, ring only 2-4 stages deep): once every load of THIS tile is queued, pull the NEXT
+                // tile's activation boxes into L2 (hints queue behind the demand loads), so its ring loads are L2 hits; every byte
+                // is still fetched from HBM once.  (3x3 layers re-read A from L2 per tap anyway.)
+                if (p.l2_prefetch && p.taps == 1 && p.stride == 1 && nb == p.n_tiles_n - 1) {
+                    const int nt = tile + gridDim.x;  // same M tile is shared by the n_tiles_n consecutive tiles: prefetch once
+                    if (nt < p.num_tiles) {
+                        int mt2 = nt / p.n_tiles_n;
+                        const int tw2 = mt2 % p.tiles_w; mt2 /= p.tiles_w;
+                        const int th2 = mt2 % p.tiles_h;
+                        const int img2 = mt2 / p.tiles_h;
+                        for (int cc2 = 0; cc2 < p.cin_chunks; ++cc2) {
+                            tma_prefetch_l2_4d(&p.a[0][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
+                            if (SPLIT) tma_prefetch_l2_4d(&p.a[1][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
+                        }
+                    }
                 }
             }
         }
@@ -246,22 +247,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool valid = hl < p.bh && oh < p.ho && ow < p.wo;
             const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
             const int n0 = nb * BN;
-            if (p.l2_prefetch && p.tma_res && et == 0) {
-                // the residual of the NEXT tile (this group's chunks) starts its trip from HBM to L2 now; the per-chunk TMA loads
-                // into the staging buffers (one chunk ahead) then hit L2 instead of paying the DRAM latency once per chunk
-                const int nt = tile + gridDim.x;
-                if (nt < p.num_tiles) {
-                    const int nb2 = nt % p.n_tiles_n;
-                    int mt2 = nt / p.n_tiles_n;
-                    const int tw2 = mt2 % p.tiles_w; mt2 /= p.tiles_w;
-                    const int th2 = mt2 % p.tiles_h;
-                    const int img2 = mt2 / p.tiles_h;
-                    for (int c2 = eg * 32; c2 < BN; c2 += 32 * TC_EPI_GROUPS) {
-                        tma_prefetch_l2_4d(&p.r[0], nb2 * BN + c2, tw2 * p.bw, th2 * p.bh, img2);
-                        if (SPLIT) tma_prefetch_l2_4d(&p.r[1], nb2 * BN + c2, tw2 * p.bw, th2 * p.bh, img2);
-                    }
-                }
-            }
             // stage this tile's scale/shift (previous tile's readers are past the barrier at the end of the loop body)
             for (int i = eall; i < BN; i += 128 * TC_EPI_GROUPS) { s_scale[i] = __ldg(p.scale + n0 + i); s_shift[i] = __ldg(p.shift + n0 + i); }
             asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");
@@ -287,10 +272,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int c0 = cfirst; c0 < BN; c0 += cstep) {
                 if (p.tma_res && et == 0) {
                     int nc0 = c0 + cstep, ntile = tile;
-                    if (nc0 >= BN) { nc0 = cfirst; ntile = tile + gridDim.x; }
+                    const bool wrap = nc0 >= BN;
+                    if (wrap) { nc0 = cfirst; ntile = tile + gridDim.x; }
                     if (ntile < p.num_tiles) {
                         bulk_wait_read<1>();
                         issue_res(ntile, nc0, (gc + 1) % 3);
+                        if (wrap && p.l2_prefetch) {
+                            // the first chunk of the next tile is on its way; its REMAINING chunks start their trip from HBM to L2
+                            // now (behind that demand load), so the per-chunk loads one chunk ahead no longer pay DRAM latency each
+                            const int nb2 = ntile % p.n_tiles_n;
+                            int mt2 = ntile / p.n_tiles_n;
+                            const int tw2 = mt2 % p.tiles_w; mt2 /= p.tiles_w;
+                            const int th2 = mt2 % p.tiles_h;
+                            const int img2 = mt2 / p.tiles_h;
+                            for (int c2 = cfirst + cstep; c2 < BN; c2 += cstep) {
+                                tma_prefetch_l2_4d(&p.r[0], nb2 * BN + c2, tw2 * p.bw, th2 * p.bh, img2);
+                                if (SPLIT) tma_prefetch_l2_4d(&p.r[1], nb2 * BN + c2, tw2 * p.bw, th2 * p.bh, img2);
+                            }
+                        }
                     }
                 }
                 uint32_t v[32];
@@ -524,7 +523,7 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
 int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
 int g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
 int g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
-int g_tc_l2_prefetch = 1;     // TMA L2-prefetch of the next tile's residual chunks and (1x1 layers) activation boxes
+int g_tc_l2_prefetch = 0;     // TMA L2-prefetch hints for the next tile's residual chunks / 1x1 activation boxes (off: measured slower)
 int g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
 int g_tc_fuse_cross = 1;       // split mode with two accumulators: a_hi*[w_hi|w_lo] as ONE N = 2*BN MMA (A/B switch; same arithmetic)
 int g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cross-term accumulator (accuracy); 256 trades it for reuse

@@ -38,13 +38,15 @@ static __device__ __forceinline__ Px fetch(const uint8_t* __restrict__ frame, in
 }
 
 __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frames, int n_frames, int H, int W,
-                                                          const int* __restrict__ crops, const uint8_t* __restrict__ fills, int msz,
+                                                          const int* __restrict__ crops, int4 one, const uint8_t* __restrict__ fills, int msz,
                                                           float* __restrict__ out) {
     const int i = blockIdx.y;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= msz * msz) return;
     const int dy = pix / msz, dx = pix - dy * msz;
-    const int fi = min(max(crops[i * 4 + 0], 0), n_frames - 1), xmin = crops[i * 4 + 1], ymin = crops[i * 4 + 2], osz = crops[i * 4 + 3];
+    // windows come from a device table, or (crops == nullptr, one window) by value so that a per-frame caller uploads nothing
+    const int4 cw = crops ? make_int4(crops[i * 4 + 0], crops[i * 4 + 1], crops[i * 4 + 2], crops[i * 4 + 3]) : one;
+    const int fi = min(max(cw.x, 0), n_frames - 1), xmin = cw.y, ymin = cw.z, osz = cw.w;
     const uint8_t* frame = frames + (size_t)fi * H * W * 3;
     const uint8_t* fill = fills + i * 3;
     int r[3];
@@ -80,7 +82,15 @@ int launch_crop_resize(const uint8_t* frames, int n_frames, int H, int W, const 
                        cudaStream_t st) {
     if (n == 0) return 0;
     dim3 grid((unsigned)((msz * msz + 255) / 256), (unsigned)n);
-    crop_resize_kernel<<<grid, 256, 0, st>>>(frames, n_frames, H, W, crops, fills, msz, out);
+    crop_resize_kernel<<<grid, 256, 0, st>>>(frames, n_frames, H, W, crops, make_int4(0, 0, 0, 0), fills, msz, out);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_crop_resize_one(const uint8_t* frame, int H, int W, int xmin, int ymin, int osz, const uint8_t* fill3, int msz, float* out,
+                           cudaStream_t st) {
+    dim3 grid((unsigned)((msz * msz + 255) / 256), 1u);
+    crop_resize_kernel<<<grid, 256, 0, st>>>(frame, 1, H, W, nullptr, make_int4(0, xmin, ymin, osz), fill3, msz, out);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -181,6 +181,9 @@ struct usot_engine {
     cudaStream_t gstream = nullptr;   // graphs are captured and replayed on an engine-owned stream (the caller's may be the
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // legacy default stream, which cannot be captured); ordered by events
     std::mutex mu;  // one forward at a time per engine (DataParallel replicas own separate engines)
+    // scratch of usot_engine_track_frame (crop, gathered memory templates, score / box maps, xf, pool box); grow-only, outside the arena
+    char* frame_ws = nullptr;
+    size_t frame_ws_cap = 0;
 
     ~usot_engine() {
         cudaSetDevice(device);
@@ -190,6 +193,7 @@ struct usot_engine {
         if (ev_out) cudaEventDestroy(ev_out);
         for (void* p : owned) cudaFree(p);
         if (arena.base) cudaFree(arena.base);
+        if (frame_ws) cudaFree(frame_ws);
     }
 };
 
@@ -1039,6 +1043,50 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
     USOT_CUDA_OK(cudaEventRecord(e->ev_out, st));
     USOT_CUDA_OK(cudaStreamWaitEvent(caller, e->ev_out, 0));  // the caller's stream sees the outputs in order
     return 0;
+}
+
+int usot_engine_track_frame(usot_engine* e, const uint8_t* frame, int height, int width, int context_xmin, int context_ymin,
+                            int original_sz, const uint8_t* fill, int instance_size, const float* zf, const float* mem_buf,
+                            const int32_t* mem_rows, int nq, const double* window, double target_w, double target_h, double ratio,
+                            double penalty_k, double window_influence, int total_stride, double* result, float* feat_out, void* stream) {
+    USOT_REQUIRE(e && e->finalized, "engine not finalized");
+    USOT_REQUIRE(frame && fill && zf && mem_buf && mem_rows && window && result && feat_out, "null pointer");
+    USOT_REQUIRE(height > 0 && width > 0 && original_sz > 0 && nq > 0 && nq <= 16, "bad argument");
+    USOT_REQUIRE(total_stride == 8, "the response grid of this network has stride 8");
+    USOT_REQUIRE(target_w > 0 && target_h > 0, "target size must be positive");
+    const int F = usot_feature_size(instance_size), R = F - 6;
+    USOT_REQUIRE(F >= 9, "search crop too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    USOT_CUDA_OK(cudaSetDevice(e->device));
+    // carve the frame workspace (256-byte aligned pieces)
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t a = (off + 255) & ~size_t(255); off = a + bytes; return a; };
+    const size_t o_x = take((size_t)3 * instance_size * instance_size * 4), o_mem = take((size_t)nq * 49 * 256 * 4);
+    const size_t o_cls = take((size_t)R * R * 4), o_bbox = take((size_t)4 * R * R * 4), o_cm = take((size_t)R * R * 4);
+    const size_t o_xf = take((size_t)F * F * 256 * 4), o_box = take(16);
+    if (off > e->frame_ws_cap) {
+        std::lock_guard<std::mutex> lk(e->mu);
+        USOT_CUDA_OK(cudaDeviceSynchronize());
+        if (e->frame_ws) USOT_CUDA_OK(cudaFree(e->frame_ws));
+        e->frame_ws = nullptr;
+        e->frame_ws_cap = 0;
+        void* p = nullptr;
+        USOT_CUDA_OK(cudaMalloc(&p, off));
+        e->frame_ws = static_cast<char*>(p);
+        e->frame_ws_cap = off;
+    }
+    char* ws = e->frame_ws;
+    float *x = reinterpret_cast<float*>(ws + o_x), *mem = reinterpret_cast<float*>(ws + o_mem), *cls = reinterpret_cast<float*>(ws + o_cls);
+    float *bbox = reinterpret_cast<float*>(ws + o_bbox), *cm = reinterpret_cast<float*>(ws + o_cm), *xf = reinterpret_cast<float*>(ws + o_xf);
+    float* box = reinterpret_cast<float*>(ws + o_box);
+    g_prof.launches[FAM_OTHER] += 4;
+    if (int rc = launch_crop_resize_one(frame, height, width, context_xmin, context_ymin, original_sz, fill, instance_size, x, st)) return rc;
+    if (int rc = launch_gather_rows(mem_buf, mem_rows, nq, (size_t)49 * 256, mem, st)) return rc;
+    if (int rc = usot_engine_track(e, x, 1, instance_size, zf, 1, mem, nq, cls, bbox, cm, xf, stream)) return rc;
+    if (int rc = launch_tracker_post(cls, cm, bbox, window, R, instance_size, target_w, target_h, (float)ratio, penalty_k, window_influence,
+                                     result, st)) return rc;
+    if (int rc = launch_pool_box_from_result(result, R, instance_size, total_stride, box, st)) return rc;
+    return usot_engine_extract_memory_feature(e, nullptr, 1, 0, xf, F, box, feat_out, stream);
 }
 
 int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n, int size, const float* xf, int feat,

@@ -90,6 +90,44 @@ int launch_tracker_post(const float* cls, const float* cls_mem, const float* bbo
     return 0;
 }
 
+// ---- one-call tracker frame helpers ------------------------------------------------------------------------------
+struct RowList { int r[16]; };
+__global__ void gather_rows_kernel(const float4* __restrict__ buf, RowList rows, size_t row4, float4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < row4) out[(size_t)blockIdx.y * row4 + i] = __ldg(buf + (size_t)rows.r[blockIdx.y] * row4 + i);
+}
+// Memory templates of this frame: out[k] = buf[rows[k]] (device-resident queue, usot_tracker.py:222-261 without the host round trip)
+int launch_gather_rows(const float* buf, const int* rows_host, int n_rows, size_t row_floats, float* out, cudaStream_t st) {
+    USOT_REQUIRE(n_rows > 0 && n_rows <= 16 && row_floats % 4 == 0, "gather: 1..16 rows of a multiple of 4 floats");
+    RowList rl;
+    for (int k = 0; k < 16; ++k) rl.r[k] = k < n_rows ? rows_host[k] : 0;
+    const size_t row4 = row_floats / 4;
+    dim3 grid((unsigned)((row4 + 255) / 256), (unsigned)n_rows);
+    gather_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(buf), rl, row4, reinterpret_cast<float4*>(out));
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// pool_label_search (usot_tracker.py:339-362) of the winning box, in the reference's float32 arithmetic:
+//   bbox = clip(float32([x1,y1,x2,y2]), reg_min - gap, reg_max + gap);  (bbox - reg_min) * slope
+__global__ void pool_box_kernel(const double* __restrict__ result, float reg_min, float reg_max, float slope, float gap, float* __restrict__ box4) {
+    const int k = threadIdx.x;
+    if (k < 4) {
+        float v = (float)result[2 + k];
+        v = fminf(fmaxf(v, reg_min - gap), reg_max + gap);
+        box4[k] = __fmul_rn(__fsub_rn(v, reg_min), slope);
+    }
+}
+int launch_pool_box_from_result(const double* result, int score_size, int instance_size, int total_stride, float* box4, cudaStream_t st) {
+    const int sf = score_size;
+    const double reg_min = (double)(0 - sf / 2) * total_stride + instance_size / 2;
+    const double reg_max = (double)(sf - 1 - sf / 2) * total_stride + instance_size / 2;
+    const double slope = (2 * (sf / 2)) / (reg_max - reg_min);
+    pool_box_kernel<<<1, 32, 0, st>>>(result, (float)reg_min, (float)reg_max, (float)slope, (float)(1.0 / slope), box4);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ---- cycle-memory glue: one block per memory sample --------------------------------------------------------------
 // res = r*off_cls + (1-r)*mem_cls ; idx = argmax ; box = grid(idx) -/+ off_bbox[:, idx] ; pool_box = map to PrPool coordinates
 __global__ void __launch_bounds__(256) cycle_glue_kernel(const float* __restrict__ off_cls, const float* __restrict__ mem_cls,

@@ -76,6 +76,8 @@ class USOTTracker(object):
     def __init__(self, info):
         super(USOTTracker, self).__init__()
         self.info = info
+        # per-frame path: one usot_engine_track_frame call (default) or the op-by-op path through the Python façade
+        self.fused_frame = os.environ.get("USOT_B200_TRACK_FRAME", "1") != "0"
 
     # ---- per-video initialisation (usot_tracker.py:22-131) ----
     def init(self, im, target_pos, target_sz, model):
@@ -152,11 +154,19 @@ class USOTTracker(object):
         target_sz = state['target_sz']
         _, scale_z, s_x = self._search_window(p, target_sz)
         frame = state['frame_stager'].upload(im)
-        x_crop, _ = get_subwindow_tracking(frame, target_pos, p.instance_size, python2round(s_x), state['avg_chans'], fill=state['fill_dev'])
         queue = state['memory_queue']
-        target_pos, target_sz, confidence, feat_mem = tracker_ops.update_device(net, x_crop.unsqueeze(0), target_pos, target_sz * scale_z,
-                                                                                state['window_dev'], scale_z, p, queue)
-        queue.append(feat_mem, confidence)
+        if self.fused_frame:
+            # one library call per frame: crop -> memory gather -> track() -> post-process -> PrPool into the queue's next row
+            xmin, ymin, _ = tracker_ops.crop_geometry(frame.shape[1:3], target_pos, p.instance_size, python2round(s_x))
+            res = tracker_ops.track_frame(net, frame, xmin, ymin, python2round(s_x), state['fill_dev'], queue, state['window_dev'],
+                                          target_sz * scale_z, p).cpu().numpy()
+            target_pos, target_sz, confidence = tracker_ops.smooth_update(res, target_pos, target_sz * scale_z, scale_z, p)
+            queue.commit_row(confidence)
+        else:
+            x_crop, _ = get_subwindow_tracking(frame, target_pos, p.instance_size, python2round(s_x), state['avg_chans'], fill=state['fill_dev'])
+            target_pos, target_sz, confidence, feat_mem = tracker_ops.update_device(net, x_crop.unsqueeze(0), target_pos, target_sz * scale_z,
+                                                                                    state['window_dev'], scale_z, p, queue)
+            queue.append(feat_mem, confidence)
         target_pos[0] = max(0, min(state['im_w'], target_pos[0]))
         target_pos[1] = max(0, min(state['im_h'], target_pos[1]))
         target_sz[0] = max(10, min(state['im_w'], target_sz[0]))

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ops import _need_cuda, _stream
+from .ops import _need_cuda, _stream, as_nhwc
 
 
 def cosine_window(score_size, device):
@@ -71,6 +71,20 @@ class MemoryQueue:
         self._n += 1
         return self._n - 1
 
+    def next_row(self):
+        """(7,7,C) view of the next free row of the device buffer (grown if full): usot_engine_track_frame writes the new memory
+        feature straight into it; ``commit_row`` then makes it part of the queue."""
+        if self._n == self._buf.shape[0]:
+            new = torch.empty((2 * self._n,) + tuple(self._buf.shape[1:]), dtype=torch.float32, device=self.device)
+            new[: self._n].copy_(self._buf)
+            self._buf = new
+        return self._buf[self._n]
+
+    def commit_row(self, confidence):
+        self._mem_rows.append(self._n)
+        self._n += 1
+        self.confidences.append(float(confidence))
+
     def append(self, feature, confidence):
         """state['memory_features'].append(feat_mem); state['memory_confidences'].append(confidence)."""
         self._mem_rows.append(self._append_raw(feature))
@@ -109,6 +123,45 @@ class MemoryQueue:
         return mem.permute(0, 3, 1, 2), torch.tensor([scores], dtype=torch.float32, device=self.device)
 
 
+def smooth_update(res, target_pos, target_sz, scale_z, p):
+    """Host part of USOTTracker.update after the arg-max (usot_tracker.py:165-193): res = the 8 doubles of ``postprocess``;
+    target_sz is the size already multiplied by scale_z.  Returns (new target_pos, new target_sz, confidence)."""
+    x1, y1, x2, y2, penalty, score = res[2], res[3], res[4], res[5], res[6], res[7]
+    half = p.instance_size // 2
+    dx, dy = ((x1 + x2) / 2 - half) / scale_z, ((y1 + y2) / 2 - half) / scale_z
+    pw, ph = (x2 - x1) / scale_z, (y2 - y1) / scale_z
+    tsz = np.asarray(target_sz, dtype=np.float64) / scale_z
+    lr = penalty * score * p.lr
+    new_pos = np.array([target_pos[0] + dx, target_pos[1] + dy])
+    blended = np.array([pw * lr + (1 - lr) * tsz[0], ph * lr + (1 - lr) * tsz[1]])
+    new_sz = tsz * (1 - lr) + lr * blended
+    return new_pos, new_sz, float(score)
+
+
+def track_frame(net, frame, context_xmin, context_ymin, original_sz, fill, queue, window, target_sz, p):
+    """One tracker frame in ONE library call (usot_engine_track_frame): crop -> memory gather -> track() -> post-process ->
+    PrPool of the new memory feature into the queue's next row; nothing is copied to or from the host.  ``frame`` (1,H,W,3)
+    uint8 CUDA, ``fill`` (1,3) uint8 CUDA, ``window`` (R,R) float64 CUDA, ``target_sz`` already multiplied by scale_z.
+    Returns the (8,) float64 CUDA result of ``postprocess``; the caller reads it (one 64-byte D2H copy) and then calls
+    ``queue.commit_row(confidence)``."""
+    import ctypes
+    eng = net._engine(frame.device)
+    if net.zf is None or net.zf.shape[0] != 1:
+        raise RuntimeError("track_frame needs a single template (call template() first)")
+    zf = as_nhwc(net.zf)  # net.zf is a channels-last view of a contiguous NHWC tensor: no copy
+    rows, _ = queue.selected_rows()
+    rows_c = (ctypes.c_int32 * len(rows))(*rows)
+    out_row = queue.next_row()
+    result = torch.empty(8, dtype=torch.float64, device=frame.device)
+    with torch.cuda.device(frame.device):
+        _lib.check(_lib.load().usot_engine_track_frame(
+            eng._h, _lib.ptr(frame), frame.shape[1], frame.shape[2], int(context_xmin), int(context_ymin), int(original_sz), _lib.ptr(fill),
+            int(p.instance_size), _lib.ptr(zf), _lib.ptr(queue._buf), rows_c, len(rows), _lib.ptr(window), float(target_sz[0]),
+            float(target_sz[1]), float(p.ratio), float(p.penalty_k), float(p.window_influence), int(p.total_stride), _lib.ptr(result),
+            _lib.ptr(out_row), _stream(frame)))
+    return result
+
+
 def update_device(net, x_crops, target_pos, target_sz, window, scale_z, p, queue):
     """Device-side version of USOTTracker.update (lib/tracker/usot_tracker.py:133-200) for one frame.
 
@@ -121,16 +174,8 @@ def update_device(net, x_crops, target_pos, target_sz, window, scale_z, p, queue
     cls_score, bbox_pred, cls_memory, xf = net.track(x_crops, template_mem=template_mem, score_mem=score_mem)
     res = postprocess(cls_score, bbox_pred, cls_memory, window, target_sz, instance_size=p.instance_size, ratio=p.ratio,
                       penalty_k=p.penalty_k, window_influence=p.window_influence).cpu().numpy()
-    x1, y1, x2, y2, penalty, score = res[2], res[3], res[4], res[5], res[6], res[7]
-    # box / size update (usot_tracker.py:165-193)
-    half = p.instance_size // 2
-    dx, dy = ((x1 + x2) / 2 - half) / scale_z, ((y1 + y2) / 2 - half) / scale_z
-    pw, ph = (x2 - x1) / scale_z, (y2 - y1) / scale_z
-    tsz = np.asarray(target_sz, dtype=np.float64) / scale_z
-    lr = penalty * score * p.lr
-    new_pos = np.array([target_pos[0] + dx, target_pos[1] + dy])
-    blended = np.array([pw * lr + (1 - lr) * tsz[0], ph * lr + (1 - lr) * tsz[1]])
-    new_sz = tsz * (1 - lr) + lr * blended
+    new_pos, new_sz, score = smooth_update(res, target_pos, target_sz, scale_z, p)
+    x1, y1, x2, y2 = res[2], res[3], res[4], res[5]
     # memory feature of the predicted box, PrPool'ed from xf on the device (usot_tracker.py:196-199, pool_label_search :329-350)
     sf = p.score_size
     axis0 = (0 - sf // 2) * p.total_stride + p.instance_size // 2
