@@ -76,7 +76,8 @@ int launch_stem(const float* x_nchw, int n, int s, const float* w_packed /*[147]
 // tensor-core stem (stem_tc.cu): w_img = packed shared-memory image of the weight tile, see pack_stem_tc_host
 int launch_stem_tc(const float* x_nchw, int n, int s, const void* w_img, const float* scale_tc, const float* shift, float* out_nhwc,
                    bool split, cudaStream_t st);
-int launch_maxpool3x3s2p1(const float* in, int n, int h, int w, int c, float* out, cudaStream_t st);
+int launch_maxpool3x3s2p1(const float* in, int n, int h, int w, int c, float* out /*fp32 or null*/, __half* out_hi /*split planes or null*/,
+                          __half* out_lo, cudaStream_t st);
 int launch_conv_simt(const float* in, const ConvGeom& g, const float* w_kn /*[kh*kw*cin][cout]*/, const Epilogue& ep,
                      float* out, cudaStream_t st);
 // Fused GroupDW: out[n] = sum_i sw[i] * xcorr(x_i[n / (n_out/nx)], z_i[n / (n_out/nz)])
@@ -86,8 +87,11 @@ struct GroupDWArgs {
     const float* dw_weight;                                // [3] raw (softmax applied inside)
     float* out;                                            // [n_out][R][R][C]
     int nx, nz, n_out, C, F;                               // R = F - 6
+    __half* out_hi = nullptr;                              // optional: write the split-fp16 planes the tower convs read instead of
+    __half* out_lo = nullptr;                              // fp32 `out` (FFMA2 kernel only; out_lo may be null in single-fp16 mode)
 };
 extern int g_groupdw_strips, g_groupdw_tma;
+bool groupdw_split_output_supported(int F);  // true when launch_groupdw_w will run the FFMA2 kernel, which can write split-fp16 planes
 int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st);  // xcorr_tma.cu
 int launch_groupdw(const GroupDWArgs& a, cudaStream_t st);  // reads dw_weight back (one stream sync)
 int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st);  // softmaxed weights given

@@ -492,10 +492,15 @@ static int backbone_neck(Ctx& c, const float* x, int n, int S, float* xf_dst, T*
     }
     T cur;
     cur.n = n; cur.h = cur.w = h2; cur.c = 64;
-    cur.f = ar.f(cur.numel());
+    if (c.tc()) {  // only the tensor-core convs read the pooled map: write their operand format directly
+        cur.hi = ar.h(cur.numel());
+        cur.lo = c.split() ? ar.h(cur.numel()) : nullptr;
+    } else {
+        cur.f = ar.f(cur.numel());
+    }
     if (!ar.plan) {
         Scope sc(FAM_POOL, c.st, 0, 4.0 * n * 64 * ((double)h1 * h1 + (double)h2 * h2));
-        RUN(launch_maxpool3x3s2p1(a0, n, h1, h1, 64, cur.f, c.st));
+        RUN(launch_maxpool3x3s2p1(a0, n, h1, h1, 64, cur.f, cur.hi, cur.lo, c.st));
     }
     struct L { const char* name; int blocks; };
     const L layers[3] = {{"layer1", 3}, {"layer2", 4}, {"layer3", 6}};
@@ -548,11 +553,20 @@ static int groupdw(Ctx& c, const Enc3& x, const Enc3& z, int n_out, int F, const
     const int nx = x.m[0].n, nz = z.m[0].n, R = F - 6;
     T o;
     o.n = n_out; o.h = o.w = R; o.c = 256;
-    o.f = ar.f(o.numel());
+    // every consumer of the correlation map is a tensor-core conv (towers, conf/value generators): in the tcgen05 modes the FFMA2
+    // kernel writes their split-fp16 operand planes directly (same 4 B/element as fp32, no separate conversion pass)
+    const bool split_out = c.tc() && groupdw_split_output_supported(F);
+    if (split_out) {
+        o.hi = ar.h(o.numel());
+        o.lo = c.split() ? ar.h(o.numel()) : nullptr;
+    } else {
+        o.f = ar.f(o.numel());
+    }
     GroupDWArgs a;
     a.x11 = x.m[0].f; a.x12 = x.m[1].f; a.x21 = x.m[2].f;
     a.z11 = z.m[0].f; a.z12 = z.m[1].f; a.z21 = z.m[2].f;
     a.dw_weight = nullptr; a.out = o.f; a.nx = nx; a.nz = nz; a.n_out = n_out; a.C = 256; a.F = F;
+    a.out_hi = o.hi; a.out_lo = o.lo;
     if (!ar.plan) {
         // algorithmic bytes: every search map read once, every output written once, taps once
         const double per_x = 256.0 * ((F - 2.0) * (F - 2) + 2.0 * (F - 4) * (F - 2));

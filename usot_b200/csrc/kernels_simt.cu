@@ -107,8 +107,10 @@ int launch_stem(const float* x, int n, int s, const float* wk, const float* scal
 // =============================================================================================
 // MaxPool 3x3 stride 2 pad 1, NHWC, one float4 of channels per thread.
 // =============================================================================================
+// out != nullptr: fp32 result.  hi != nullptr: the result leaves as the split-fp16 planes the tensor-core convs read (lo may be
+// null in single-fp16 mode), which saves the fp32 round trip through HBM and the separate conversion launch.
 __global__ void maxpool_kernel(const float* __restrict__ in, int n, int h, int w, int c4, int ho, int wo,
-                               float* __restrict__ out) {
+                               float* __restrict__ out, uint2* __restrict__ hi, uint2* __restrict__ lo) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)n * ho * wo * c4;
     if (idx >= total) return;
@@ -130,14 +132,26 @@ __global__ void maxpool_kernel(const float* __restrict__ in, int n, int h, int w
             m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
         }
     }
-    reinterpret_cast<float4*>(out)[idx] = m;
+    if (out) reinterpret_cast<float4*>(out)[idx] = m;
+    if (hi) {
+        const __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(m.x - f0.x, m.y - f0.y), l1 = __floats2half2_rn(m.z - f1.x, m.w - f1.y);
+        uint2 a, b;
+        a.x = *reinterpret_cast<const uint32_t*>(&h0); a.y = *reinterpret_cast<const uint32_t*>(&h1);
+        b.x = *reinterpret_cast<const uint32_t*>(&l0); b.y = *reinterpret_cast<const uint32_t*>(&l1);
+        hi[idx] = a;
+        if (lo) lo[idx] = b;
+    }
 }
 
-int launch_maxpool3x3s2p1(const float* in, int n, int h, int w, int c, float* out, cudaStream_t st) {
+int launch_maxpool3x3s2p1(const float* in, int n, int h, int w, int c, float* out, __half* out_hi, __half* out_lo, cudaStream_t st) {
     USOT_REQUIRE(c % 4 == 0, "maxpool needs C % 4 == 0");
+    USOT_REQUIRE(out || out_hi, "maxpool needs an output");
     int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
     size_t total = (size_t)n * ho * wo * (c / 4);
-    maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, n, h, w, c / 4, ho, wo, out);
+    maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, n, h, w, c / 4, ho, wo, out, reinterpret_cast<uint2*>(out_hi),
+                                                                    reinterpret_cast<uint2*>(out_lo));
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -393,10 +407,13 @@ int launch_groupdw(const GroupDWArgs& a, cudaStream_t st) {
 int g_groupdw_strips = 3;  // tunable (usot_set_tunable("groupdw_strips", 2|3)) of the register-staged variant
 int g_groupdw_tma = 2;     // tunable: 2 = TMA ring + packed FFMA2 (xcorr_tma.cu, default), 1 = TMA ring + scalar FMA, 0 = register-staged kernel below
 
+bool groupdw_split_output_supported(int F) { return g_groupdw_tma >= 2 && (F - 6 + 8) / 9 == 3; }
+
 int launch_groupdw_w(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
     USOT_REQUIRE(a.nx > 0 && a.nz > 0 && a.n_out % a.nx == 0 && a.n_out % a.nz == 0, "groupdw: n_out must be a multiple of both batches");
     const int R = a.F - 6;
     if (g_groupdw_tma && (R + 8) / 9 == 3) return launch_groupdw_tma(a, w0, w1, w2, st);
+    USOT_REQUIRE(!a.out_hi, "split-fp16 GroupDW output needs the FFMA2 kernel (see groupdw_split_output_supported)");
     const int nstrips = (g_groupdw_strips == 2 && R <= 28) ? 2 : (R + 8) / 9;
     const int sw = (R + nstrips - 1) / nstrips;
     const unsigned grid = (unsigned)(a.n_out * (a.C / 64) * nstrips);

@@ -19,6 +19,8 @@ struct GdwParams {
     CUtensorMap m11, m12, m21;
     const float* z11; const float* z12; const float* z21;
     float* out;
+    __half2* out_hi;  // FFMA2 kernel: if set, results leave as split-fp16 planes (hi = rn16(v), lo = rn16(v - hi)) instead of fp32
+    __half2* out_lo;
     int nx, nz, n_out, C, F, nstrips;
     float w0, w1, w2;
 };
@@ -165,7 +167,8 @@ static __device__ __forceinline__ void ffma2(float2& d, const float2& a, const f
 // MASK = false requires j0 + SW <= R (no column of any staged row is out of range), so no load needs a bounds check.
 template <int SW, bool MASK>
 static __device__ __forceinline__ void g2_consume(const GdwParams& p, const uint8_t* sm, uint32_t bar_full, uint32_t bar_empty,
-                                                  int stage_bytes, const float2* z, float2* out, int j0, int jn, int lane) {
+                                                  int stage_bytes, const float2* z, float2* out, __half2* out_hi, __half2* out_lo, int j0,
+                                                  int jn, int lane) {
     const int F = p.F, R = F - 6, W11 = F - 2, H11 = F - 2, W12 = F - 2, H12 = F - 4, W21 = F - 4, C2 = p.C / 2;
     const float2 zero = make_float2(0.f, 0.f);
     float2 acc[5][SW];  // acc[k] = output row t-4+k at step t
@@ -222,10 +225,22 @@ static __device__ __forceinline__ void g2_consume(const GdwParams& p, const uint
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp is done reading the stage
         if (t >= 4) {  // output row t-4 is complete: 256 contiguous bytes per warp and column
-            float2* o = out + ((size_t)(t - 4) * R + j0) * C2;
+            const size_t o0 = ((size_t)(t - 4) * R + j0) * C2;
+            if (out_hi) {  // 128 contiguous bytes per warp, column and plane
 #pragma unroll
-            for (int j = 0; j < SW; ++j)
-                if (!MASK || j < jn) o[(size_t)j * C2] = acc[0][j];
+                for (int j = 0; j < SW; ++j)
+                    if (!MASK || j < jn) {
+                        const __half2 h = __floats2half2_rn(acc[0][j].x, acc[0][j].y);
+                        const float2 hf = __half22float2(h);
+                        out_hi[o0 + (size_t)j * C2] = h;
+                        if (out_lo) out_lo[o0 + (size_t)j * C2] = __floats2half2_rn(acc[0][j].x - hf.x, acc[0][j].y - hf.y);
+                    }
+            } else {
+                float2* o = out + o0;
+#pragma unroll
+                for (int j = 0; j < SW; ++j)
+                    if (!MASK || j < jn) o[(size_t)j * C2] = acc[0][j];
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -285,10 +300,13 @@ __global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_
     const int j0 = warp * 9;
     const int jn = min(9, R - j0);
     const float2* z = reinterpret_cast<const float2*>(zs) + lane;                           // tap t of this pair: z[t * 32]
-    float2* out = reinterpret_cast<float2*>(p.out + (size_t)n * R * R * C + cblk * 64) + lane;
-    if (jn == 9) g2_consume<9, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, j0, jn, lane);
-    else if (jn == 7) g2_consume<7, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, j0, jn, lane);
-    else g2_consume<9, true>(p, sm, bar_full, bar_empty, stage_bytes, z, out, j0, jn, lane);
+    const size_t obase = ((size_t)n * R * R * C + cblk * 64) / 2 + lane;  // in channel pairs
+    float2* out = reinterpret_cast<float2*>(p.out) + obase;
+    __half2* out_hi = p.out_hi ? p.out_hi + obase : nullptr;
+    __half2* out_lo = p.out_lo ? p.out_lo + obase : nullptr;
+    if (jn == 9) g2_consume<9, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane);
+    else if (jn == 7) g2_consume<7, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane);
+    else g2_consume<9, true>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane);
 }
 
 int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
@@ -309,6 +327,8 @@ int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaS
     if (int rc = mk(&p.m12, a.x12, F - 4, F - 2)) return rc;
     if (int rc = mk(&p.m21, a.x21, F - 2, F - 4)) return rc;
     p.z11 = a.z11; p.z12 = a.z12; p.z21 = a.z21; p.out = a.out;
+    p.out_hi = reinterpret_cast<__half2*>(a.out_hi); p.out_lo = reinterpret_cast<__half2*>(a.out_lo);
+    USOT_REQUIRE(!a.out_hi || g_groupdw_tma >= 2, "split-fp16 GroupDW output needs the FFMA2 kernel");
     p.nx = a.nx; p.nz = a.nz; p.n_out = a.n_out; p.C = a.C; p.F = F; p.nstrips = 3;
     p.w0 = w0; p.w1 = w1; p.w2 = w2;
     const int smem = GD_STAGES * (3 * F - 8) * 256 + 55 * 64 * 4 + 2 * GD_STAGES * 8 + 128;
