@@ -36,7 +36,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", default="1,8,64,256")
     ap.add_argument("--nq", type=int, default=0)
+    ap.add_argument("--tunable", action="append", default=[], help="name=value (usot_set_tunable), repeatable; A/B runs")
+    ap.add_argument("--ours-only", action="store_true", help="skip the PyTorch + cuDNN legs")
     args = ap.parse_args()
+    from usot_b200 import _lib
+    for kv in args.tunable:
+        name, val = kv.split("=")
+        _lib.check(_lib.load().usot_set_tunable(name.encode(), int(val)))
     sd = synthetic_state_dict("damp025")
     sd_cuda = {k: v.cuda() for k, v in sd.items()}
     nets = {}
@@ -60,6 +66,9 @@ def main():
             ms = timed(lambda: net.track(xc, mem, score), 5 if b >= 64 else 20)
             row[f"ours_{prec}_ms"] = round(ms, 3)
             row[f"ours_{prec}_crops_s"] = round(b / ms * 1e3, 1)
+        if args.ours_only:
+            print(json.dumps(row), flush=True)
+            continue
         with torch.no_grad():
             zf = O.template(sd, z, tb).cuda()
             mem_o = None if not args.nq else mem.contiguous()

@@ -523,6 +523,7 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
 int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
 int g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
 int g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
+int g_tc_latency_split = 1;   // small grids: halve the N tile until at least half of the SMs have a CTA (batch-1 latency; same arithmetic)
 int g_tc_l2_prefetch = 0;     // TMA L2-prefetch hints for the next tile's residual chunks / 1x1 activation boxes (off: measured slower)
 int g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
 int g_tc_fuse_cross = 1;       // split mode with two accumulators: a_hi*[w_hi|w_lo] as ONE N = 2*BN MMA (A/B switch; same arithmetic)
@@ -545,6 +546,20 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     else if (g.cout % 128 == 0 && bn_cap >= 128) bn = 128;
     choose_tiling(g.ho, g.wo, &p.tiles_w, &p.bw, &p.bh);
     p.tiles_h = (g.ho + p.bh - 1) / p.bh;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        USOT_CUDA_OK(cudaGetDevice(&dev));
+        USOT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // Latency mode (small batches): while the grid would leave at least half of the SMs idle, halve the N tile -- twice as many CTAs,
+    // and every MMA of a tile's K loop is half as wide (half as long).  The accumulation order of each output element does not
+    // change, so results stay bit-identical to the wide-tile launch of a large batch (tests: batch independence, graph replay).
+    // (Not across the 256 -> 128 step of split mode, which would switch to the two-accumulator arithmetic.)
+    if (g_tc_latency_split) {
+        const int m_tiles = g.n * p.tiles_h * p.tiles_w;
+        while (bn > 64 && !(split && bn == 256) && m_tiles * (g.cout / bn) * 2 <= num_sms) bn /= 2;
+    }
     p.n_img = g.n; p.ho = g.ho; p.wo = g.wo; p.cout = g.cout;
     p.n_tiles_n = g.cout / bn;
     p.num_tiles = g.n * p.tiles_h * p.tiles_w * p.n_tiles_n;
@@ -612,12 +627,6 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         }
     }
 
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        USOT_CUDA_OK(cudaGetDevice(&dev));
-        USOT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     const int grid = std::min(p.num_tiles, num_sms);
     if (split) {
         if (bn == 256) return launch_cfg<256, true>(p, grid, st);
