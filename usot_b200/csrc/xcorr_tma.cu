@@ -11,6 +11,8 @@
 #include "conv_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <algorithm>
+
 namespace usot {
 
 constexpr int GD_STAGES = 2, GD_SW = 9, GD_CONSUMERS = 192;  // 2 stages x ~21 KB + 14 KB taps = 58 KB per CTA -> 3 CTAs per SM
@@ -22,6 +24,7 @@ struct GdwParams {
     __half2* out_hi;  // FFMA2 kernel: if set, results leave as split-fp16 planes (hi = rn16(v), lo = rn16(v - hi)) instead of fp32
     __half2* out_lo;
     int nx, nz, n_out, C, F, nstrips;
+    int row_groups, rows_per_group;  // FFMA2 kernel: output rows split over row_groups CTAs (small batches; 1 = whole map per CTA)
     float w0, w1, w2;
 };
 
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 3) groupdw_tma_kernel(const
 // CTA = (output sample, 64-channel slab): 3 consumer warps (one column strip each, 32 channel pairs) + 1 TMA producer warp.
 // ---------------------------------------------------------------------------------------------
 constexpr int G2_STAGES = 2, G2_CONSUMER_WARPS = 3;
+int g_groupdw_row_split = 1;  // tunable "groupdw_row_split": small batches split the output rows of one map over several CTAs
 
 static __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;"
@@ -168,8 +172,8 @@ static __device__ __forceinline__ void ffma2(float2& d, const float2& a, const f
 template <int SW, bool MASK>
 static __device__ __forceinline__ void g2_consume(const GdwParams& p, const uint8_t* sm, uint32_t bar_full, uint32_t bar_empty,
                                                   int stage_bytes, const float2* z, float2* out, __half2* out_hi, __half2* out_lo, int j0,
-                                                  int jn, int lane) {
-    const int F = p.F, R = F - 6, W11 = F - 2, H11 = F - 2, W12 = F - 2, H12 = F - 4, W21 = F - 4, C2 = p.C / 2;
+                                                  int jn, int lane, int r0, int t_end) {
+    const int F = p.F, R = F - 6, W11 = F - 2, W12 = F - 2, H12 = F - 4, W21 = F - 4, C2 = p.C / 2;
     const float2 zero = make_float2(0.f, 0.f);
     float2 acc[5][SW];  // acc[k] = output row t-4+k at step t
 #pragma unroll
@@ -177,9 +181,11 @@ static __device__ __forceinline__ void g2_consume(const GdwParams& p, const uint
 #pragma unroll
         for (int j = 0; j < SW; ++j) acc[k][j] = zero;
 
-    for (int t = 0; t < H11; ++t) {
-        const int s = t % G2_STAGES;
-        mbar_wait(bar_full + 8 * s, (t / G2_STAGES) & 1);
+    // This CTA produces output rows [r0, t_end - 4): input rows t = r0 .. t_end-1 (rows below r0 only warm up the ring: what they add
+    // to the not-yet-stored slots is what the full-map loop adds too, so every stored row sees the same fma sequence).
+    for (int t = r0; t < t_end; ++t) {
+        const int lt = t - r0, s = lt % G2_STAGES;
+        mbar_wait(bar_full + 8 * s, (lt / G2_STAGES) & 1);
         const float2* xs = reinterpret_cast<const float2*>(sm + s * stage_bytes) + lane;  // pixel q of a staged row: xs[q * 32]
         {   // 5x5 on x11 row t -> output rows t-u
             float2 xr[SW + 4];
@@ -224,7 +230,7 @@ static __device__ __forceinline__ void g2_consume(const GdwParams& p, const uint
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // this warp is done reading the stage
-        if (t >= 4) {  // output row t-4 is complete: 256 contiguous bytes per warp and column
+        if (t - 4 >= r0) {  // output row t-4 is complete: 256 contiguous bytes per warp and column
             const size_t o0 = ((size_t)(t - 4) * R + j0) * C2;
             if (out_hi) {  // 128 contiguous bytes per warp, column and plane
 #pragma unroll
@@ -262,9 +268,12 @@ __global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_
     const uint32_t bar_full = base + G2_STAGES * stage_bytes + 55 * 64 * 4, bar_empty = bar_full + 8 * G2_STAGES;
 
     const int cblocks = C / 64;
-    const int cblk = blockIdx.x % cblocks, n = blockIdx.x / cblocks;
+    const int rg = blockIdx.x % p.row_groups, cb = blockIdx.x / p.row_groups;
+    const int cblk = cb % cblocks, n = cb / cblocks;
     const int xb = n / (p.n_out / p.nx), zb = n / (p.n_out / p.nz);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = rg * p.rows_per_group;                          // first output row of this CTA
+    const int t_end = min(H11, min(R, r0 + p.rows_per_group) + 4);  // one past the last input row it needs
 
     if (tid == 0) {
         for (int s = 0; s < G2_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, G2_CONSUMER_WARPS); }
@@ -282,9 +291,9 @@ __global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_
         // ------------------------------- producer -------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&p.m11); tma_prefetch_desc(&p.m12); tma_prefetch_desc(&p.m21);
-            for (int t = 0; t < H11; ++t) {
-                const int s = t % G2_STAGES;
-                if (t >= G2_STAGES) mbar_wait(bar_empty + 8 * s, ((t / G2_STAGES) + 1) & 1);
+            for (int t = r0; t < t_end; ++t) {
+                const int lt = t - r0, s = lt % G2_STAGES;
+                if (lt >= G2_STAGES) mbar_wait(bar_empty + 8 * s, ((lt / G2_STAGES) + 1) & 1);
                 const bool has12 = t >= 2 && t - 2 < H12;
                 const uint32_t full = bar_full + 8 * s, dst = base + s * stage_bytes;
                 mbar_expect_tx(full, (uint32_t)(row11 + row21 + (has12 ? row12 : 0)));
@@ -304,9 +313,9 @@ __global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_
     float2* out = reinterpret_cast<float2*>(p.out) + obase;
     __half2* out_hi = p.out_hi ? p.out_hi + obase : nullptr;
     __half2* out_lo = p.out_lo ? p.out_lo + obase : nullptr;
-    if (jn == 9) g2_consume<9, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane);
-    else if (jn == 7) g2_consume<7, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane);
-    else g2_consume<9, true>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane);
+    if (jn == 9) g2_consume<9, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane, r0, t_end);
+    else if (jn == 7) g2_consume<7, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane, r0, t_end);
+    else g2_consume<9, true>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane, r0, t_end);
 }
 
 int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st) {
@@ -336,7 +345,14 @@ int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaS
         const int smem2 = G2_STAGES * (3 * F - 8) * 256 + 55 * 64 * 4 + 2 * G2_STAGES * 8 + 128;
         static SmemAttrCache attr2;
         if (int rc = attr2.ensure(groupdw_ffma2_kernel, smem2)) return rc;
-        groupdw_ffma2_kernel<<<(unsigned)(a.n_out * (a.C / 64)), G2_CONSUMER_WARPS * 32 + 32, smem2, st>>>(p);
+        // Latency mode (small batches): fewer (sample, slab) pairs than SMs -> split the output rows over several CTAs.  Each extra
+        // CTA re-reads 4 warm-up input rows (L2 hits); results are bit-identical to the whole-map CTA (same fma sequence per row).
+        const int pairs = a.n_out * (a.C / 64);
+        p.row_groups = 1;
+        if (g_groupdw_row_split && pairs * 2 <= 148) p.row_groups = std::min(R, 148 / pairs);
+        p.rows_per_group = (R + p.row_groups - 1) / p.row_groups;
+        p.row_groups = (R + p.rows_per_group - 1) / p.rows_per_group;
+        groupdw_ffma2_kernel<<<(unsigned)(pairs * p.row_groups), G2_CONSUMER_WARPS * 32 + 32, smem2, st>>>(p);
         USOT_CUDA_OK(cudaGetLastError());
         return 0;
     }
