@@ -83,6 +83,11 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
+            # USOT_B200_TUNABLES="name=value,name=value": performance knobs (usot_set_tunable) applied once at load
+            for kv in filter(None, os.environ.get("USOT_B200_TUNABLES", "").split(",")):
+                name, _, val = kv.partition("=")
+                if lib.usot_set_tunable(name.strip().encode(), int(val)) != 0:
+                    raise RuntimeError((lib.usot_last_error() or b"usot_b200: bad USOT_B200_TUNABLES entry").decode())
             _lib = lib
     return _lib
 

@@ -105,6 +105,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.pdl) {
+        // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no tensor of
+        // the previous layer, so it may overlap that layer's tail.  Let OUR successor start its own prologue now, then wait until
+        // every grid we depend on has completed and flushed before the first activation / residual byte is read or written.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -515,6 +522,22 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     p.stages = p.tma_res ? (Cfg::STAGES_RES < Cfg::STAGES ? Cfg::STAGES_RES : Cfg::STAGES) : Cfg::STAGES;
     const int smem = Cfg::smem_bytes(p.stages, p.nbuf);
     USOT_REQUIRE(smem <= 227 * 1024, "conv_tc: shared memory plan exceeds 227 KiB");
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        USOT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT>, p));
+        return 0;
+    }
     conv_tc_kernel<BN, SPLIT><<<grid, TC_THREADS, smem, st>>>(p);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
@@ -523,6 +546,7 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
 int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
 int g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
 int g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
+int g_tc_pdl = 0;             // programmatic dependent launch of the conv kernels (prologue overlaps the previous layer's tail)
 int g_tc_latency_split = 1;   // small grids: halve the N tile until at least half of the SMs have a CTA (batch-1 latency; same arithmetic)
 int g_tc_l2_prefetch = 0;     // TMA L2-prefetch hints for the next tile's residual chunks / 1x1 activation boxes (off: measured slower)
 int g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
@@ -601,6 +625,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
 
     p.fuse_cross = g_tc_fuse_cross;
     p.l2_prefetch = g_tc_l2_prefetch;
+    p.pdl = g_tc_pdl;
     p.tma_store = (g_tc_tma_store && p.out_hi && !(split && bn == 256)) ? 1 : 0;
     p.tma_f32 = 0;
     if (g_tc_tma_store && g_tc_tma_f32 && !p.out_hi && p.out_f32 && !p.res_hi && !(split && bn == 256)) {

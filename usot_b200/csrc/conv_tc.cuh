@@ -14,6 +14,7 @@ struct TcParams {
     int tma_res;          // 1: residual arrives by TMA (requires tma_store)
     int stages;           // operand ring depth used by this launch (<= the config's maximum)
     int nbuf;             // staging buffers per epilogue group: 1, or 3 when the residual is prefetched by TMA
+    int pdl;              // 1: launched with programmatic stream serialization; the kernel runs griddepcontrol.launch_dependents / .wait
     int l2_prefetch;      // 1: cp.async.bulk.prefetch.tensor hints for the next tile (residual chunks; A boxes of 1x1 layers)
     int tma_f32;          // 1: fp32-only output through the staging buffers + TMA store (o[0] is then an fp32 map); implies tma_store
     int fuse_cross;       // 1: split mode issues hi*[hi|lo] as one N = 2*BN MMA (main and cross accumulators are adjacent)
@@ -58,7 +59,7 @@ struct TcEpilogue {
 // generic cuTensorMapEncodeTiled wrapper (dtype / swizzle are CUtensorMapDataType / CUtensorMapSwizzle values)
 int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                 const cuuint32_t* box, int swizzle);
-extern int g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split;
+extern int g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st);
 int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
 void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,

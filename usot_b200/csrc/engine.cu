@@ -723,6 +723,7 @@ int usot_set_tunable(const char* name, int value) {
     if (!strcmp(name, "groupdw_tma")) { USOT_REQUIRE(value >= 0 && value <= 2, "groupdw_tma must be 0 (register-staged), 1 (TMA ring, scalar FMA) or 2 (TMA ring, packed FFMA2)"); g_groupdw_tma = value; return 0; }
     if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
+    if (!strcmp(name, "tc_pdl")) { USOT_REQUIRE(value == 0 || value == 1, "tc_pdl must be 0 or 1"); g_tc_pdl = value; return 0; }
     if (!strcmp(name, "tc_latency_split")) { USOT_REQUIRE(value == 0 || value == 1, "tc_latency_split must be 0 or 1"); g_tc_latency_split = value; return 0; }
     if (!strcmp(name, "tc_l2_prefetch")) { USOT_REQUIRE(value == 0 || value == 1, "tc_l2_prefetch must be 0 or 1"); g_tc_l2_prefetch = value; return 0; }
     if (!strcmp(name, "tc_tma_f32")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_f32 must be 0 or 1"); g_tc_tma_f32 = value; return 0; }
