@@ -546,7 +546,7 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
 int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
 int g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
 int g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
-int g_tc_pdl = 0;             // programmatic dependent launch of the conv kernels (prologue overlaps the previous layer's tail)
+int g_tc_pdl = 1;             // programmatic dependent launch of the conv kernels on small grids (prologue overlaps the previous layer's tail)
 int g_tc_latency_split = 1;   // small grids: halve the N tile until at least half of the SMs have a CTA (batch-1 latency; same arithmetic)
 int g_tc_l2_prefetch = 0;     // TMA L2-prefetch hints for the next tile's residual chunks / 1x1 activation boxes (off: measured slower)
 int g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
@@ -625,7 +625,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
 
     p.fuse_cross = g_tc_fuse_cross;
     p.l2_prefetch = g_tc_l2_prefetch;
-    p.pdl = g_tc_pdl;
+    p.pdl = 0;  // decided below, once the tile count is known
     p.tma_store = (g_tc_tma_store && p.out_hi && !(split && bn == 256)) ? 1 : 0;
     p.tma_f32 = 0;
     if (g_tc_tma_store && g_tc_tma_f32 && !p.out_hi && p.out_f32 && !p.res_hi && !(split && bn == 256)) {
@@ -653,6 +653,9 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     }
 
     const int grid = std::min(p.num_tiles, num_sms);
+    // Programmatic dependent launch pays in the latency regime (every tile has its own SM, idle SMs host the successor's prologue):
+    // batch 1: -7 % per track() call.  At batch 256 it measured -1.6 % (within clock noise, no possible gain): not used there.
+    p.pdl = (g_tc_pdl && p.num_tiles <= num_sms) ? 1 : 0;
     if (split) {
         if (bn == 256) return launch_cfg<256, true>(p, grid, st);
         if (bn == 128) return launch_cfg<128, true>(p, grid, st);
