@@ -186,7 +186,8 @@ USOT_API int usot_engine_forward_train(usot_engine* e, const float* zf, const fl
  *   ->  track() with the memory branch  ->  usot_tracker_postprocess  ->  pool_label_search of the winning box  ->  PrPool of
  *   the new memory feature from xf into feat_out ((7,7,256) nhwc, typically the next free row of the queue buffer).
  * zf (1,7,7,256) nhwc; window (R,R) float64; target_w/h already multiplied by scale_z; result[8] as usot_tracker_postprocess.
- * frame, fill (3 bytes), zf, mem_buf, window, result, feat_out are DEVICE pointers. */
+ * frame, fill (3 bytes), zf, mem_buf, window, result, feat_out are DEVICE pointers.  Calls on one engine are serialised on the
+ * host and share one device workspace: issue the frames of one engine on one stream. */
 USOT_API int usot_engine_track_frame(usot_engine* e, const uint8_t* frame, int height, int width, int context_xmin, int context_ymin,
                                      int original_sz, const uint8_t* fill, int instance_size, const float* zf, const float* mem_buf,
                                      const int32_t* mem_rows, int nq, const double* window, double target_w, double target_h, double ratio,

@@ -228,17 +228,19 @@ def tracker_track(state, im):
     return state
 
 
-def synthetic_video(seed=3, n_frames=6, h=240, w=320):
-    """Seeded uint8 frames: smooth-ish random background, a textured bright box drifting by (+4, +3) px per frame.
-    Returns (frames, initial target_pos (cx, cy), target_sz (w, h))."""
+def synthetic_video(seed=3, n_frames=6, h=240, w=320, box=(64, 48)):
+    """Seeded uint8 frames: smooth-ish random background, a textured bright box (w, h) = ``box`` drifting by (+4, +3) px per
+    frame.  Returns (frames, initial target_pos (cx, cy), target_sz (w, h)).  A box below 0.4 % of the frame area makes the
+    tracker choose the 271-pixel search window (usot_tracker.py:43-48)."""
     rng = np.random.default_rng(seed)
+    bw, bh = box
     bg = rng.integers(0, 120, (h // 8 + 1, w // 8 + 1, 3)).astype(np.float64)
     bg = np.kron(bg, np.ones((8, 8, 1)))[:h, :w] + rng.integers(0, 30, (h, w, 3))
-    tex = rng.integers(150, 256, (48, 64, 3)).astype(np.float64)
+    tex = rng.integers(150, 256, (bh, bw, 3)).astype(np.float64)
     frames = []
     for t in range(n_frames):
         f = bg.copy()
         y0, x0 = 90 + 3 * t, 120 + 4 * t
-        f[y0:y0 + 48, x0:x0 + 64] = tex
+        f[y0:y0 + bh, x0:x0 + bw] = tex
         frames.append(np.clip(f, 0, 255).astype(np.uint8))
-    return frames, np.array([120 + 32.0, 90 + 24.0]), np.array([64.0, 48.0])
+    return frames, np.array([120 + bw / 2.0, 90 + bh / 2.0]), np.array([float(bw), float(bh)])

@@ -12,17 +12,21 @@ import tracker_oracle as T
 from helpers import GOLD, load_weights
 
 
-def _fixture():
-    g = np.load(os.path.join(GOLD, "tracker_trace.npz"))
-    frames, pos0, sz0 = T.synthetic_video(seed=int(g["video_seed"]), n_frames=int(g["n_frames"]))
+def _fixture(tag=""):
+    """tag "" = ordinary target (255-pixel search window), "small_" = target below 0.4 % of the frame (271-pixel window, R = 27)."""
+    z = np.load(os.path.join(GOLD, "tracker_trace.npz"))
+    g = {k[len(tag):]: z[k] for k in z.files if k.startswith(tag) and (tag or not k.startswith("small_"))}
+    g["n_frames"] = z["n_frames"]
+    frames, pos0, sz0 = T.synthetic_video(seed=int(g["video_seed"]), n_frames=int(g["n_frames"]), box=tuple(int(v) for v in g["box"]))
     assert np.array_equal(pos0, g["pos0"]) and np.array_equal(sz0, g["sz0"])
     return g, frames, pos0, sz0
 
 
-def test_oracle_tracker_reproduces_reference_trace():
-    g, frames, pos0, sz0 = _fixture()
+@pytest.mark.parametrize("tag,size", [("", 255), ("small_", 271)])
+def test_oracle_tracker_reproduces_reference_trace(tag, size):
+    g, frames, pos0, sz0 = _fixture(tag)
     state = T.tracker_init(frames[0], pos0.copy(), sz0.copy(), T.OracleNet(load_weights("damp025")))
-    assert state['p'].instance_size == 255 and state['p'].score_size == 25 and len(state['init_features']) == 2
+    assert state['p'].instance_size == size and state['p'].score_size == (size - 127) // 8 + 9 and len(state['init_features']) == 2
     rows = []
     for im in frames[1:]:
         state = T.tracker_track(state, im)
@@ -54,18 +58,19 @@ def test_tracker_mirror_host_logic():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision,fused", [("fp16x3", True), ("fp32", True), ("fp16x3", False)])
-def test_gpu_tracker_follows_reference_trace(precision, fused):
+@pytest.mark.parametrize("precision,fused,tag", [("fp16x3", True, ""), ("fp32", True, ""), ("fp16x3", False, ""), ("fp16x3", True, "small_"),
+                                                 ("fp32", False, "small_")])
+def test_gpu_tracker_follows_reference_trace(precision, fused, tag):
     from usot_b200 import USOT
     from usot_b200.tracker import USOTTracker
-    g, frames, pos0, sz0 = _fixture()
+    g, frames, pos0, sz0 = _fixture(tag)
     net = USOT(precision=precision)
     net.load_state_dict(load_weights("damp025"))
     net = net.eval().cuda()
     tracker = USOTTracker(types.SimpleNamespace(arch="USOT"))
     tracker.fused_frame = fused  # one usot_engine_track_frame call per frame vs the op-by-op path
     state = tracker.init(frames[0], pos0.copy(), sz0.copy(), net)
-    assert tuple(net.zf.shape) == (1, 256, 7, 7)
+    assert tuple(net.zf.shape) == (1, 256, 7, 7) and state['p'].instance_size == (271 if tag else 255)
     rows = []
     for im in frames[1:]:
         state = tracker.track(state, im)

@@ -184,6 +184,7 @@ struct usot_engine {
     // scratch of usot_engine_track_frame (crop, gathered memory templates, score / box maps, xf, pool box); grow-only, outside the arena
     char* frame_ws = nullptr;
     size_t frame_ws_cap = 0;
+    std::mutex frame_mu;  // one usot_engine_track_frame at a time per engine (the workspace is shared; use one stream per engine)
 
     ~usot_engine() {
         cudaSetDevice(device);
@@ -1074,6 +1075,7 @@ int usot_engine_track_frame(usot_engine* e, const uint8_t* frame, int height, in
     const int F = usot_feature_size(instance_size), R = F - 6;
     USOT_REQUIRE(F >= 9, "search crop too small");
     cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> frame_lock(e->frame_mu);
     USOT_CUDA_OK(cudaSetDevice(e->device));
     // carve the frame workspace (256-byte aligned pieces)
     size_t off = 0;
