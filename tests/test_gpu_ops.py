@@ -177,6 +177,24 @@ def test_pred_conv_variants_bit_identical(ops, cout, mode, r):
     assert torch.equal(outs[0], outs[1])
 
 
+def test_empty_inputs_are_noops(ops):
+    """Zero rois / crops / maps: every stand-alone op returns an empty tensor of the right shape and leaves no CUDA error behind
+    (the reference's PrRoIPool launches a zero-size grid and exit()s on the resulting launch error, prroi_pooling_gpu_impl.cu:20-27)."""
+    from usot_b200 import tracker_ops
+    feat = torch.randn(2, 8, 9, 9).cuda()
+    out = ops.prroi_pool2d(feat, torch.zeros(0, 5).cuda(), 7, 7, 1.0)
+    assert tuple(out.shape) == (0, 8, 7, 7)
+    y = ops.pred_conv(torch.zeros(0, 25, 25, 256).cuda(), torch.zeros(1, 256, 3, 3).cuda(), torch.zeros(1).cuda())
+    assert tuple(y.shape) == (0, 1, 25, 25)
+    x = ops.xcorr_depthwise(torch.zeros(0, 256, 29, 29).cuda(), torch.zeros(1, 256, 5, 5).cuda())
+    assert tuple(x.shape) == (0, 256, 25, 25)
+    frames = torch.zeros(1, 32, 32, 3, dtype=torch.uint8).cuda()
+    c = tracker_ops.crop_resize(frames, torch.zeros(0, 4, dtype=torch.int32).cuda(), torch.zeros(0, 3, dtype=torch.uint8).cuda(), 127)
+    assert tuple(c.shape) == (0, 3, 127, 127)
+    torch.cuda.synchronize()
+    assert torch.isfinite(ops.prroi_pool2d(feat, torch.tensor([[0.0, 1.0, 1.0, 5.0, 5.0]]).cuda(), 7, 7, 1.0)).all()  # still healthy
+
+
 CONV_CASES = [
     # cin, cout, k, stride, pad, dil, h, w, residual, relu
     (64, 64, 1, 1, (0, 0), (1, 1), 17, 17, False, True),

@@ -765,7 +765,7 @@ int usot_prroi_pool_coor_backward(const float* features, const float* rois, cons
 
 int usot_xcorr_depthwise(const float* x, const float* kernel, float* out, int bx, int bk, int channels, int hx, int wx, int hk, int wk,
                          void* stream) {
-    USOT_REQUIRE(x && kernel && out, "null pointer");
+    USOT_REQUIRE(bx == 0 || (x && kernel && out), "null pointer");
     return launch_xcorr_nchw(x, kernel, out, bx, bk, channels, hx, wx, hk, wk, (cudaStream_t)stream);
 }
 
