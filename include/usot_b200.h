@@ -93,6 +93,12 @@ USOT_API int usot_prroi_pool_coor_backward(const float* features, const float* r
 USOT_API int usot_xcorr_depthwise(const float* x, const float* kernel, float* out, int bx, int bk, int channels, int hx, int wx,
                                   int hk, int wk, void* stream);
 
+/* Backward of usot_xcorr_depthwise (training path; the reference gets it from autograd through F.conv2d, connect.py:147-157).
+ * grad_out (bx,C,hx-hk+1,wx-wk+1); grad_x (bx,C,hx,wx) and grad_kernel (bk,C,hk,wk) are fully overwritten; either may be NULL.
+ * With bk == 1 the kernel gradient is the sum over all bx samples (atomics: summation order is not fixed). */
+USOT_API int usot_xcorr_depthwise_backward(const float* x, const float* kernel, const float* grad_out, float* grad_x, float* grad_kernel,
+                                           int bx, int bk, int channels, int hx, int wx, int hk, int wk, void* stream);
+
 /* Fused GroupDW, nhwc.  x11 (nx,F-2,F-2,C), x12 (nx,F-4,F-2,C), x21 (nx,F-2,F-4,C); z11 (nz,5,5,C), z12 (nz,3,5,C),
  * z21 (nz,5,3,C); weight = the raw 3-vector (softmax is applied inside; read back with one stream sync);
  * out (n_out,F-6,F-6,C).  Sample n uses x[n / (n_out/nx)] and z[n] (or z[0] when nz == 1). */

@@ -195,6 +195,22 @@ def test_empty_inputs_are_noops(ops):
     assert torch.isfinite(ops.prroi_pool2d(feat, torch.tensor([[0.0, 1.0, 1.0, 5.0, 5.0]]).cuda(), 7, 7, 1.0)).all()  # still healthy
 
 
+@pytest.mark.parametrize("bx,bk,hk,wk", [(3, 3, 5, 5), (4, 1, 5, 5), (2, 1, 3, 5), (2, 2, 5, 3)])
+def test_xcorr_depthwise_backward_vs_autograd(ops, bx, bk, hk, wk):
+    """Both gradients of the depth-wise xcorr against torch autograd through the oracle's F.conv2d formulation (float64)."""
+    g = torch.Generator().manual_seed(bx * 10 + bk)
+    c, hx, wx = 64, 29 if hk == 5 else 27, 29 if wk == 5 else 27
+    x = torch.randn(bx, c, hx, wx, generator=g)
+    k = torch.randn(bk, c, hk, wk, generator=g)
+    go = torch.randn(bx, c, hx - hk + 1, wx - wk + 1, generator=g)
+    xr, kr = x.double().requires_grad_(True), k.double().requires_grad_(True)
+    O.xcorr_depthwise(xr, kr).backward(go.double())
+    xc, kc = x.cuda().requires_grad_(True), k.cuda().requires_grad_(True)
+    ops.xcorr_depthwise(xc, kc).backward(go.cuda())
+    assert rel_err(xc.grad.cpu(), xr.grad.float()) <= 5e-6
+    assert rel_err(kc.grad.cpu(), kr.grad.float()) <= 5e-6
+
+
 CONV_CASES = [
     # cin, cout, k, stride, pad, dil, h, w, residual, relu
     (64, 64, 1, 1, (0, 0), (1, 1), 17, 17, False, True),

@@ -36,6 +36,7 @@ SIGNATURES = {
     "usot_prroi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "usot_prroi_pool_coor_backward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
     "usot_xcorr_depthwise": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "usot_xcorr_depthwise_backward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "usot_groupdw_xcorr": (_I, [_P] * 8 + [_I] * 5 + [_P]),
     "usot_conv2d_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P]),
     "usot_pred_conv": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, ctypes.c_float, _P, _P, _P, _P]),

@@ -132,6 +132,8 @@ int launch_crop_resize(const uint8_t* frames, int n_frames, int H, int W, const 
 int launch_crop_resize_one(const uint8_t* frame, int H, int W, int xmin, int ymin, int osz, const uint8_t* fill3, int model_sz, float* out_nchw,
                            cudaStream_t st);
 // kernels_glue.cu: pieces of the one-call tracker frame (usot_engine_track_frame)
+int launch_xcorr_backward(const float* x, const float* k, const float* gout, float* gx /*or null*/, float* gk /*or null*/, int nx, int nk, int C,
+                          int hx, int wx, int hk, int wk, cudaStream_t st);
 int launch_gather_rows(const float* buf, const int* rows_host, int n_rows, size_t row_floats, float* out, cudaStream_t st);
 int launch_pool_box_from_result(const double* result, int score_size, int instance_size, int total_stride, float* box4, cudaStream_t st);
 int launch_center_crop_nhwc(const float* in, int n, int h, int w, int c, int l, float* out, cudaStream_t st);

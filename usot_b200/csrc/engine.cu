@@ -769,6 +769,13 @@ int usot_xcorr_depthwise(const float* x, const float* kernel, float* out, int bx
     return launch_xcorr_nchw(x, kernel, out, bx, bk, channels, hx, wx, hk, wk, (cudaStream_t)stream);
 }
 
+int usot_xcorr_depthwise_backward(const float* x, const float* kernel, const float* grad_out, float* grad_x, float* grad_kernel, int bx, int bk,
+                                  int channels, int hx, int wx, int hk, int wk, void* stream) {
+    USOT_REQUIRE(bx == 0 || (x && kernel && grad_out), "null pointer");
+    USOT_REQUIRE(grad_x || grad_kernel, "nothing to compute: both gradient outputs are NULL");
+    return launch_xcorr_backward(x, kernel, grad_out, grad_x, grad_kernel, bx, bk, channels, hx, wx, hk, wk, (cudaStream_t)stream);
+}
+
 int usot_groupdw_xcorr(const float* x11, const float* x12, const float* x21, const float* z11, const float* z12, const float* z21,
                        const float* weight, float* out, int nx, int nz, int n_out, int channels, int feat_size, void* stream) {
     USOT_REQUIRE(x11 && x12 && x21 && z11 && z12 && z21 && weight && out, "null pointer");

@@ -90,6 +90,84 @@ int launch_tracker_post(const float* cls, const float* cls_mem, const float* bbo
     return 0;
 }
 
+// ---- backward of the depth-wise cross-correlation (training path) -----------------------------------
+// Forward (connect.py:147-157): out[b,c,i,j] = sum_{u,v} x[b,c,i+u,j+v] * k[b',c,u,v], b' = b or 0 (kernel batch 1 broadcast).
+//   grad_x[b,c,y,x] = sum_{u,v} gout[b,c,y-u,x-v] * k[b',c,u,v]                 (full correlation, zero outside gout)
+//   grad_k[b',c,u,v] = sum_{b -> b'} sum_{i,j} gout[b,c,i,j] * x[b,c,i+u,j+v]    (reduced over positions and, when the kernel is
+//                                                                                broadcast, over the samples that share it)
+// One block per (sample, channel) plane, like the forward op: x, gout and the taps are staged in shared memory.
+__global__ void __launch_bounds__(256) xcorr_backward_kernel(const float* __restrict__ x, const float* __restrict__ k, const float* __restrict__ gout,
+                                                             float* __restrict__ gx, float* __restrict__ gk, int nk, int C, int hx, int wx,
+                                                             int hk, int wk) {
+    extern __shared__ float xb_sm[];
+    const int ho = hx - hk + 1, wo = wx - wk + 1;
+    float* xs = xb_sm;
+    float* gs = xs + hx * wx;
+    float* ks = gs + ho * wo;
+    float* red = ks + hk * wk;  // [8] warp partials
+    const int plane = blockIdx.x, b = plane / C, c = plane % C;
+    const int kb = (nk == 1) ? 0 : b;
+    const float* xp = x + (size_t)plane * hx * wx;
+    const float* gp = gout + (size_t)plane * ho * wo;
+    const float* kp = k + ((size_t)kb * C + c) * hk * wk;
+    for (int i = threadIdx.x; i < hx * wx; i += 256) xs[i] = __ldg(xp + i);
+    for (int i = threadIdx.x; i < ho * wo; i += 256) gs[i] = __ldg(gp + i);
+    for (int i = threadIdx.x; i < hk * wk; i += 256) ks[i] = __ldg(kp + i);
+    __syncthreads();
+    if (gx) {
+        for (int o = threadIdx.x; o < hx * wx; o += 256) {
+            const int y = o / wx, xx = o % wx;
+            float s = 0.f;
+            for (int u = 0; u < hk; ++u) {
+                const int i = y - u;
+                if (i < 0 || i >= ho) continue;
+                for (int v = 0; v < wk; ++v) {
+                    const int j = xx - v;
+                    if (j >= 0 && j < wo) s = fmaf(gs[i * wo + j], ks[u * wk + v], s);
+                }
+            }
+            gx[(size_t)plane * hx * wx + o] = s;
+        }
+    }
+    if (gk) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int t = 0; t < hk * wk; ++t) {
+            const int u = t / wk, v = t % wk;
+            float s = 0.f;
+            for (int o = threadIdx.x; o < ho * wo; o += 256) {
+                const int i = o / wo, j = o % wo;
+                s = fmaf(gs[o], xs[(i + u) * wx + j + v], s);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) red[warp] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float tot = 0.f;
+                for (int w8 = 0; w8 < 8; ++w8) tot += red[w8];
+                float* dst = gk + ((size_t)kb * C + c) * hk * wk + t;
+                if (nk == 1) atomicAdd(dst, tot);  // the broadcast kernel collects every sample's contribution
+                else *dst = tot;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+int launch_xcorr_backward(const float* x, const float* k, const float* gout, float* gx, float* gk, int nx, int nk, int C, int hx, int wx,
+                          int hk, int wk, cudaStream_t st) {
+    USOT_REQUIRE(nk == 1 || nk == nx, "xcorr backward: kernel batch must be 1 or equal to the search batch");
+    USOT_REQUIRE(hx >= hk && wx >= wk, "xcorr backward: kernel larger than search map");
+    const int ho = hx - hk + 1, wo = wx - wk + 1;
+    const size_t smem = ((size_t)hx * wx + (size_t)ho * wo + (size_t)hk * wk + 8) * sizeof(float);
+    USOT_REQUIRE(smem <= 48 * 1024, "xcorr backward: plane too large");
+    if (gk && nk == 1) USOT_CUDA_OK(cudaMemsetAsync(gk, 0, (size_t)C * hk * wk * sizeof(float), st));
+    if (nx * C == 0) return 0;
+    xcorr_backward_kernel<<<nx * C, 256, smem, st>>>(x, k, gout, gx, gk, nk, C, hx, wx, hk, wk);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // ---- one-call tracker frame helpers ------------------------------------------------------------------------------
 struct RowList { int r[16]; };
 __global__ void gather_rows_kernel(const float4* __restrict__ buf, RowList rows, size_t row4, float4* __restrict__ out) {

@@ -83,17 +83,41 @@ def prroi_pool2d(features, rois, pooled_height, pooled_width, spatial_scale):
     return PrRoIPool2DFunction.apply(features, rois, pooled_height, pooled_width, spatial_scale)
 
 
+class XCorrDepthwiseFunction(torch.autograd.Function):
+    """Depth-wise cross-correlation with both gradients (lib/models/connect.py:147-157 + the autograd of its F.conv2d)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel):
+        _need_float(x, kernel)
+        _need_cuda(x, kernel)
+        x, kernel = x.contiguous(), kernel.contiguous()
+        bx, c, hx, wx = x.shape
+        bk, ck, hk, wk = kernel.shape
+        assert c == ck, "channel mismatch"
+        out = torch.empty((bx, c, hx - hk + 1, wx - wk + 1), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().usot_xcorr_depthwise(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(out), bx, bk, c, hx, wx, hk, wk, _stream(x)))
+        ctx.save_for_backward(x, kernel)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, kernel = ctx.saved_tensors
+        bx, c, hx, wx = x.shape
+        bk, _, hk, wk = kernel.shape
+        grad_out = grad_out.contiguous().float()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gk = torch.empty_like(kernel) if ctx.needs_input_grad[1] else None
+        if gx is not None or gk is not None:
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().usot_xcorr_depthwise_backward(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(grad_out), _lib.ptr(gx), _lib.ptr(gk),
+                                                                     bx, bk, c, hx, wx, hk, wk, _stream(x)))
+        return gx, gk
+
+
 def xcorr_depthwise(x, kernel):
-    _need_float(x, kernel)
-    _need_cuda(x, kernel)
-    x, kernel = x.contiguous(), kernel.contiguous()
-    bx, c, hx, wx = x.shape
-    bk, ck, hk, wk = kernel.shape
-    assert c == ck, "channel mismatch"
-    out = torch.empty((bx, c, hx - hk + 1, wx - wk + 1), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.load().usot_xcorr_depthwise(_lib.ptr(x), _lib.ptr(kernel), _lib.ptr(out), bx, bk, c, hx, wx, hk, wk, _stream(x)))
-    return out
+    """Drop-in for lib.models.connect.xcorr_depthwise (NCHW; kernel batch 1 or equal to the search batch); differentiable."""
+    return XCorrDepthwiseFunction.apply(x, kernel)
 
 
 def groupdw_xcorr(x, z, weight, n_out=None):
