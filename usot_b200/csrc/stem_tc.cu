@@ -73,16 +73,22 @@ __global__ void __launch_bounds__(256, 1) stem_tc_kernel(const StemParams p) {
         decode(t, b, oy, x0);
         float* dst = reinterpret_cast<float*>(sm + ST_P_OFF + buf * ST_PATCH_BYTES);
         const float* src = p.x + (size_t)b * 3 * p.S * p.S;
-        for (int i = tid; i < ST_PROWS * ST_PW; i += 256) {
-            const int r = i / ST_PW, col = i - r * ST_PW;
+        // one patch row (c, kh) per warp pass, lanes stride over its 261 columns: the address arithmetic is per row, not per element
+        // (the flat-index version spent two integer divisions per 4-byte copy and made this loop the largest instruction consumer
+        // of the kernel)
+        for (int r = warp; r < ST_PROWS; r += 8) {
             const int c = r / 7, kh = r - c * 7;
-            const int gx = 2 * x0 + col, gy = 2 * oy + kh;
-            float* d = dst + r * ST_PWP + col;
-            if (gx < p.S && gy < p.S) {
-                const float* g = src + ((size_t)c * p.S + gy) * p.S + gx;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(d)), "l"(g) : "memory");
-            } else {
-                *d = 0.f;
+            const int gy = 2 * oy + kh;
+            const bool row_ok = gy < p.S;
+            const float* g = src + ((size_t)c * p.S + gy) * p.S + 2 * x0;
+            const uint32_t d = smem_u32(dst + r * ST_PWP);
+            const int ncol = min(ST_PW, p.S - 2 * x0);  // columns of this row that exist in the image
+            for (int col = lane; col < ST_PW; col += 32) {
+                if (row_ok && col < ncol) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u * col), "l"(g + col) : "memory");
+                } else {
+                    dst[r * ST_PWP + col] = 0.f;
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
