@@ -1,9 +1,5 @@
-# GPU job of the current iteration (run as: gpurun --timeout 1500 -- 'bash gpurun_job.sh')
+# GPU job of the current iteration (run as: gpurun --timeout 900 -- 'bash gpurun_job.sh')
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_tunables.py tests/test_gpu_train.py -q -m gpu 2>&1 | tail -20 > gpurun_out/pytest_gpu_stem.log
-timeout 400 python bench.py > gpurun_out/bench_stem.json 2> gpurun_out/bench_stem.err
-timeout 300 python bench.py --no-cpu-baseline --precision fp16 > gpurun_out/bench_stem_fp16.json 2> gpurun_out/bench_stem_fp16.err
-tail -4 gpurun_out/pytest_gpu_stem.log; python -c "
-import json
-for f in ('bench_stem','bench_stem_fp16'):
-    d=json.load(open('gpurun_out/%s.json'%f)); print(f, d['value'], d['e2e']['value'], d['kernel_ms_per_step'], d['clocks'])"
+timeout 400 python -m pytest tests/test_crop.py tests/test_tracker.py tests/test_gpu_ops.py -q -m gpu 2>&1 | tail -8 > gpurun_out/pytest_gpu_crop.log
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:crop_resize -s 2 -c 1 -o gpurun_out/r01b_crop_resize -f python tools/crop_case.py > gpurun_out/ncu_crop.log 2>&1
+tail -4 gpurun_out/pytest_gpu_crop.log; tail -2 gpurun_out/ncu_crop.log
