@@ -121,3 +121,30 @@ def test_gpu_crop_full_batch_properties():
     const = tracker_ops.upload_frame(np.full((120, 160, 3), 201, np.uint8))
     c = tracker_ops.crop_resize(const, torch.tensor([[0, 5, 5, 77]], dtype=torch.int32).cuda(), fill[:1], 255)
     assert float(c.min()) == 201.0 and float(c.max()) == 201.0
+
+
+def test_crop_geometry_property_sweep():
+    """Host bookkeeping of the device crop against the oracle's restatement of track_utils.py:41-55,81-115 over a seeded sweep
+    that includes exact .5 ties (python's round-half-even), windows outside the frame and both need_bbox modes."""
+    from usot_b200.tracker_ops import crop_geometry
+    rng = np.random.default_rng(123)
+    for k in range(400):
+        h, w = int(rng.integers(20, 700)), int(rng.integers(20, 900))
+        osz = int(rng.integers(2, 900))
+        msz = (127, 255, 271)[k % 3]
+        pos = rng.uniform(-100, 1000, 2)
+        if k % 5 == 0:
+            pos = np.floor(pos) + 0.5      # ties
+        if k % 7 == 0:
+            pos = np.floor(pos)
+        tsz = rng.uniform(2, 300, 2)
+        nb = bool(k % 2)
+        im = np.zeros((h, w, 3), np.uint8)
+        _, ref = C.get_subwindow_tracking(im, pos, msz, osz, np.zeros(3), tsz, need_bbox=nb) if osz * osz * 3 < 3e6 else (None, None)
+        xmin, ymin, info = crop_geometry((h, w), pos, msz, osz, tsz, nb)
+        assert (xmin, ymin) == C.context_window(pos, osz)
+        if ref is not None:
+            assert info["crop_cords"] == ref["crop_cords"] and info["pad_info"] == ref["pad_info"]
+            assert info["original_image_bbox"] == ref["original_image_bbox"]
+            if nb:
+                assert info["template_bbox"] == ref["template_bbox"]
