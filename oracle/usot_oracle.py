@@ -286,10 +286,83 @@ def prroi_pool2d(features: torch.Tensor, rois: torch.Tensor, pooled_h: int = 7, 
     return torch.from_numpy(out)
 
 
+def prroi_pool2d_backward(grad_out: torch.Tensor, rois: torch.Tensor, feat_shape, spatial_scale: float = 1.0) -> torch.Tensor:
+    """PrRoIPoolingBackward -- lib/models/prroi_pool/src/prroi_pooling_gpu_impl.cu:214-272 (gradient w.r.t. the features; the
+    transpose of ``prroi_pool2d``, which is linear in the features: every corner of every cell of every bin receives
+    coef * top_diff / bin_area, :108-147).  float32, vectorised over channels."""
+    go = grad_out.detach().cpu().numpy().astype(np.float32)
+    r = rois.detach().cpu().numpy().astype(np.float32)
+    B, C, H, W = feat_shape
+    n_rois, _, pooled_h, pooled_w = go.shape
+    gf = np.zeros((B, C, H, W), np.float32)
+    scale = _f32(spatial_scale)
+
+    def g(lim, a):
+        return lim - _f32(0.5) * lim * lim - a + _f32(0.5) * a * a
+
+    def add(b, h, w, v):  # PrRoIPoolingDistributeDiff: nothing outside the map
+        if 0 <= h < H and 0 <= w < W:
+            gf[b, :, h, w] += v
+
+    for n in range(n_rois):
+        b = int(r[n, 0])
+        sw, sh, ew, eh = (r[n, 1] * scale, r[n, 2] * scale, r[n, 3] * scale, r[n, 4] * scale)
+        roi_w = max(ew - sw, _f32(0.0))
+        roi_h = max(eh - sh, _f32(0.0))
+        bin_h = _f32(roi_h / _f32(pooled_h))
+        bin_w = _f32(roi_w / _f32(pooled_w))
+        win_size = max(_f32(0.0), _f32(bin_w * bin_h))
+        if win_size == 0:
+            continue
+        for ph in range(pooled_h):
+            for pw in range(pooled_w):
+                ws_w = _f32(sw + _f32(bin_w * _f32(pw)))
+                ws_h = _f32(sh + _f32(bin_h * _f32(ph)))
+                we_w = _f32(ws_w + bin_w)
+                we_h = _f32(ws_h + bin_h)
+                s_w, e_w = int(math.floor(ws_w)), int(math.ceil(we_w))
+                s_h, e_h = int(math.floor(ws_h)), int(math.ceil(we_h))
+                top = go[n, :, ph, pw] / win_size
+                for wi in range(s_w, e_w):
+                    for hi in range(s_h, e_h):
+                        y0 = max(ws_h, _f32(hi))
+                        x0 = max(ws_w, _f32(wi))
+                        y1 = min(we_h, _f32(hi + 1))
+                        x1 = min(we_w, _f32(wi + 1))
+                        a, bt = _f32(x0 - _f32(wi)), _f32(y0 - _f32(hi))
+                        la, lb = _f32(x1 - _f32(wi)), _f32(y1 - _f32(hi))
+                        a2, la2 = _f32(_f32(wi + 1) - x1), _f32(_f32(wi + 1) - x0)
+                        b2, lb2 = _f32(_f32(hi + 1) - y1), _f32(_f32(hi + 1) - y0)
+                        add(b, hi, wi, top * _f32(g(la, a) * g(lb, bt)))
+                        add(b, hi, wi + 1, top * _f32(g(la2, a2) * g(lb, bt)))
+                        add(b, hi + 1, wi, top * _f32(g(la, a) * g(lb2, b2)))
+                        add(b, hi + 1, wi + 1, top * _f32(g(la2, a2) * g(lb2, b2)))
+    return torch.from_numpy(gf)
+
+
+class _PrRoIPoolFn(torch.autograd.Function):
+    """Differentiable (w.r.t. the features) wrapper used by the gradient fixtures; the roi coordinates get no gradient, exactly
+    like the detached boxes of the training forward (lib/models/models.py:271-272) and the label boxes."""
+
+    @staticmethod
+    def forward(ctx, features, rois):
+        ctx.save_for_backward(rois)
+        ctx.feat_shape = tuple(features.shape)
+        return prroi_pool2d(features, rois, 7, 7, 1.0)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rois,) = ctx.saved_tensors
+        return prroi_pool2d_backward(grad_out, rois, ctx.feat_shape, 1.0), None
+
+
 def prpool_feature(features: torch.Tensor, bboxs: torch.Tensor) -> torch.Tensor:
     """USOT_.prpool_feature -- lib/models/models.py:164-171."""
     idx = torch.arange(0, features.shape[0]).view(-1, 1).float()
-    return prroi_pool2d(features, torch.cat((idx, bboxs.float().cpu()), dim=1), 7, 7, 1.0)
+    rois = torch.cat((idx, bboxs.detach().float().cpu()), dim=1)
+    if features.requires_grad:
+        return _PrRoIPoolFn.apply(features, rois)
+    return prroi_pool2d(features, rois, 7, 7, 1.0)
 
 
 # ---- head -------------------------------------------------------------------
