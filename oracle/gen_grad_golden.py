@@ -87,7 +87,7 @@ def oracle_grads(sd, train_bn):
     finally:
         O._CAL.on = False
     (losses[0] + losses[1] + losses[2]).backward()
-    return [float(v) for v in losses], {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
+    return [float(v.detach()) for v in losses], {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
 
 
 def reference_grads(sd, train_bn):
@@ -102,7 +102,7 @@ def reference_grads(sd, train_bn):
     losses = net(z, x, label=label, reg_target=reg_target, reg_weight=reg_weight, template_bbox=tb, search_memory=smem, search_bbox=sb,
                  cls_ratio=0.4)
     (losses[0] + losses[1] + losses[2]).backward()
-    return [float(v) for v in losses], {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    return [float(v.detach()) for v in losses], {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
 
 
 def main():
