@@ -211,6 +211,22 @@ def test_xcorr_depthwise_backward_vs_autograd(ops, bx, bk, hk, wk):
     assert rel_err(kc.grad.cpu(), kr.grad.float()) <= 5e-6
 
 
+@pytest.mark.parametrize("cin,cout,k,pad,dil,h", [(256, 256, 3, (2, 2), (2, 2), 13), (256, 1024, 1, (0, 0), (1, 1), 9), (256, 256, 3, (0, 0), (2, 1), 15),
+                                                   (512, 1024, 3, (1, 1), (1, 1), 9)])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+def test_conv_dgrad_on_the_forward_kernel(ops, cin, cout, k, pad, dil, h, precision):
+    """Input gradient of the stride-1 convs computed by the forward conv kernel with transposed, flipped filters."""
+    g = torch.Generator().manual_seed(cin + k)
+    x = torch.randn(2, cin, h, h, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, k, k, generator=g, dtype=torch.float64) / (cin * k * k) ** 0.5
+    y = torch.nn.functional.conv2d(x, w, None, 1, pad, dil)
+    go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(go)
+    ours = ops.conv2d_nhwc_input_grad(go.float().permute(0, 2, 3, 1).contiguous().cuda(), w.float().cuda(), pad, dil, precision)
+    assert tuple(ours.shape) == (2, h, h, cin)
+    assert rel_err(ours.permute(0, 3, 1, 2).cpu(), x.grad.float()) <= (5e-6 if precision == "fp32" else 3e-5)
+
+
 CONV_CASES = [
     # cin, cout, k, stride, pad, dil, h, w, residual, relu
     (64, 64, 1, 1, (0, 0), (1, 1), 17, 17, False, True),

@@ -74,3 +74,22 @@ def test_namespace_shadowing_leaves_the_rest_of_the_reference_visible():
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + ref)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and "shadow-ok" in r.stdout, r.stderr
+
+
+@pytest.mark.parametrize("k,pad,dil", [(1, (0, 0), (1, 1)), (3, (1, 1), (1, 1)), (3, (2, 2), (2, 2)), (3, (0, 0), (2, 1)), (3, (0, 0), (1, 2)),
+                                       (3, (0, 0), (1, 1))])
+def test_dgrad_weight_transform_matches_autograd(k, pad, dil):
+    """ops.dgrad_weights: conv(grad_out, flipped-transposed filter, padding d*(k-1)-p) equals the autograd input gradient of the
+    stride-1 conv (every stride-1 geometry of the network: 1x1, 3x3 p1, dilated p2/d2, the three un-padded encoder dilations)."""
+    from usot_b200.ops import dgrad_weights
+    g = torch.Generator().manual_seed(k * 7 + dil[0])
+    x = torch.randn(2, 8, 13, 11, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(6, 8, k, k, generator=g, dtype=torch.float64)
+    y = torch.nn.functional.conv2d(x, w, None, 1, pad, dil)
+    go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(go)
+    w_t, pad_t = dgrad_weights(w, pad, dil)
+    gx = torch.nn.functional.conv2d(go, w_t, None, 1, pad_t, dil)
+    assert gx.shape == x.shape and float((gx - x.grad).abs().max()) <= 1e-10
+    with pytest.raises(ValueError):
+        dgrad_weights(w, (5, 5), (1, 1))

@@ -175,3 +175,26 @@ def pred_conv(x, weight_oihw, bias, mode=0, mul=0.1, adjust=None, bias4=None):
                                               float(mul), _lib.ptr(None if adjust is None else adjust.contiguous()),
                                               _lib.ptr(None if bias4 is None else bias4.reshape(-1).contiguous()), _lib.ptr(out), _stream(x)))
     return out
+
+
+def dgrad_weights(weight_oihw, padding=(0, 0), dilation=(1, 1)):
+    """Host side of conv dgrad for a STRIDE-1 convolution: the gradient w.r.t. the input is itself a stride-1 convolution of
+    grad_out with the spatially flipped, channel-transposed filter and padding d*(k-1) - p.  Returns (weight' (Cin,Cout,kh,kw),
+    padding').  Pure tensor bookkeeping (checked against torch autograd on the CPU, tests/test_host_logic.py)."""
+    ph, pw = (padding, padding) if isinstance(padding, int) else padding
+    dh, dw = (dilation, dilation) if isinstance(dilation, int) else dilation
+    kh, kw = weight_oihw.shape[2], weight_oihw.shape[3]
+    pad = (dh * (kh - 1) - ph, dw * (kw - 1) - pw)
+    if pad[0] < 0 or pad[1] < 0:
+        raise ValueError("dgrad as a forward conv needs padding <= dilation * (k - 1)")
+    return weight_oihw.flip(2, 3).permute(1, 0, 2, 3).contiguous(), pad
+
+
+def conv2d_nhwc_input_grad(grad_out, weight_oihw, padding=(0, 0), dilation=(1, 1), precision="fp32"):
+    """dgrad of every stride-1 conv of the network (40 of the 43 backbone convs, the neck, encoders, towers, conf/value generators)
+    on the SAME kernel as the forward pass: grad_out NHWC (n,ho,wo,Cout) -> grad_in NHWC (n,h,w,Cin).  Training path groundwork
+    (SURVEY.md §8f-3); wgrad and the two stride-2 layers need their own kernels."""
+    w_t, pad = dgrad_weights(weight_oihw, padding, dilation)
+    cin = w_t.shape[0]
+    one = torch.ones(cin, dtype=torch.float32, device=grad_out.device)
+    return conv2d_nhwc(grad_out, w_t, one, torch.zeros_like(one), stride=1, padding=pad, dilation=dilation, precision=precision)
