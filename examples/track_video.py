@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+sys.path.insert(0, ROOT)
 
 import lib.models.models as models  # noqa: E402  (the shadow in this repo)
 from lib.tracker.usot_tracker import USOTTracker  # noqa: E402
@@ -36,8 +36,15 @@ else:
     net.load_state_dict(synthetic_state_dict("damp025"))
 net = net.eval().cuda()
 
-import tracker_oracle  # noqa: E402  (only for its synthetic video generator)
-frames, target_pos, target_sz = tracker_oracle.synthetic_video(seed=15, n_frames=8)
+rng = np.random.default_rng(15)  # a textured bright box drifting over a noisy background
+bg = np.kron(rng.integers(0, 120, (31, 41, 3)).astype(np.float64), np.ones((8, 8, 1)))[:240, :320] + rng.integers(0, 30, (240, 320, 3))
+tex = rng.integers(150, 256, (48, 64, 3)).astype(np.float64)
+frames = []
+for t in range(8):
+    f = bg.copy()
+    f[90 + 3 * t:138 + 3 * t, 120 + 4 * t:184 + 4 * t] = tex
+    frames.append(np.clip(f, 0, 255).astype(np.uint8))
+target_pos, target_sz = np.array([152.0, 114.0]), np.array([64.0, 48.0])
 tracker = USOTTracker(types.SimpleNamespace(arch="USOT"))
 state = tracker.init(frames[0], target_pos.copy(), target_sz.copy(), net)
 torch.cuda.synchronize()
