@@ -20,6 +20,10 @@
  *   usot_xcorr_depthwise             <- xcorr_depthwise                  lib/models/connect.py:147-157
  *   usot_groupdw_xcorr               <- GroupDW.forward                  lib/models/connect.py:86-102
  *   usot_conv2d_nhwc                 <- nn.Conv2d + BatchNorm2d (+ReLU)  lib/models/modules.py:37-58, connect.py:20-53
+ *   usot_stem_conv / usot_maxpool3x3s2p1_nhwc <- conv1+bn1+relu / maxpool of ResNet_plus2   lib/models/modules.py:70-75,138-141
+ *   usot_conf_fusion                 <- Conf_Fusion.forward (reduction)  lib/models/connect.py:123-144
+ *   usot_cycle_glue                  <- forward-track argmax + box maps  lib/models/models.py:131-162,262-274
+ *   usot_weighted_bce / usot_iou_loss <- _weighted_BCE / add_iouloss    lib/models/models.py:42-100
  *   usot_pred_conv                   <- bbox_pred / cls_pred / cls_memory_pred + their epilogues   lib/models/connect.py:235-241,274-275
  *   usot_engine_template             <- USOT_.template                   lib/models/models.py:173-177
  *   usot_engine_track                <- USOT_.track                      lib/models/models.py:179-198
@@ -129,6 +133,32 @@ USOT_API int usot_pred_conv(const float* in, int n, int r, int channels, const f
  * averages 2x2 blocks (OpenCV's INTER_AREA route), anything else is OpenCV's 11-bit fixed-point bilinear. */
 USOT_API int usot_crop_resize(const uint8_t* frames, int n_frames, int height, int width, const int32_t* crops, const uint8_t* fill,
                               int n, int model_sz, float* out, void* stream);
+
+/* MaxPool 3x3 / stride 2 / pad 1 of the stem (lib/models/modules.py:75,141), nhwc.  in (n,h,w,C), C % 4 == 0; out (n,ho,wo,C) fp32
+ * and/or out_split_sum (n,ho,wo,C): the engine's split-fp16 variant of the same kernel (hi + lo planes, summed back to fp32 by this
+ * test/debug entry; allocates scratch and synchronises `stream`).  Either output may be NULL. */
+USOT_API int usot_maxpool3x3s2p1_nhwc(const float* in, int n, int h, int w, int channels, float* out, float* out_split_sum, void* stream);
+
+/* Stem conv1 7x7 / stride 2 / pad 0 + per-channel affine (folded BN) + ReLU (lib/models/modules.py:70-74,138-140).  x (n,3,size,size)
+ * nchw on the device; host_weight_oihw (64,3,7,7), host_scale / host_shift (64) are HOST pointers (packed + uploaded by this
+ * test/debug entry, which synchronises `stream`); out (n,HO,HO,64) nhwc fp32, HO = (size-7)/2+1.  precision = USOT_PREC_*. */
+USOT_API int usot_stem_conv(const float* x, int n, int size, const float* host_weight_oihw, const float* host_scale, const float* host_shift,
+                            float* out, int precision, void* stream);
+
+/* Conf_Fusion's reduction (lib/models/connect.py:123-144, after the two generator convs): conf / value (batch*nq, per_map) fp32
+ * (any layout, elementwise); out[b] = sum_q exp(clamp(conf[b,q],-6,4)) * value[b,q] / sum_q exp(clamp(conf[b,q],-6,4)). */
+USOT_API int usot_conf_fusion(const float* conf, const float* value, int batch, int nq, int64_t per_map, float* out, void* stream);
+
+/* Forward-tracking glue of the cycle-memory forward (lib/models/models.py:262-274 with :131-162): per memory sample s of n,
+ * res = cls_ratio*off_cls[s] + (1-cls_ratio)*mem_cls[s] over the (R,R) map; idx = first argmax; image box = grid(idx) -/+
+ * off_bbox[s,:,idx] (nchw (n,4,R,R)); pool_box (n,4) = image_bbox_to_prpool_bbox(box).  best_score (n) / best_idx (n) may be NULL. */
+USOT_API int usot_cycle_glue(const float* off_cls, const float* mem_cls, const float* off_bbox, int n, int score_size, int search_size,
+                             int search_feature_size, float cls_ratio, float* pool_box, float* best_score, int32_t* best_idx, void* stream);
+
+/* _weighted_BCE (lib/models/models.py:42-58): 0.5*mean BCEWithLogits over label==1 + 0.5*mean over label==0; loss[1] on the device. */
+USOT_API int usot_weighted_bce(const float* pred, const float* label, int count, float* loss, void* stream);
+/* add_iouloss / _IOULoss (lib/models/models.py:60-100): bbox (n,4,R,R) nchw, reg_target (n,R,R,4), reg_weight (n,R,R); cells = R*R. */
+USOT_API int usot_iou_loss(const float* bbox, const float* reg_target, const float* reg_weight, int n, int cells, float* loss, void* stream);
 
 USOT_API int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream);
 USOT_API int usot_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, void* stream);

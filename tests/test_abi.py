@@ -18,7 +18,7 @@ def test_header_symbols_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.usot_abi_version() == 2
+    assert lib.usot_abi_version() == 3
     assert lib.usot_feature_size(255) == 31 and lib.usot_feature_size(271) == 33 and lib.usot_feature_size(127) == 15
     rc = lib.usot_set_tunable(b"no_such_knob", 1)
     assert rc != 0 and b"unknown tunable" in lib.usot_last_error()
@@ -51,7 +51,7 @@ def test_header_is_plain_c_and_a_c_host_links(lib, tmp_path):
     subprocess.run([gcc, str(tmp_path / "demo.o"), "-o", exe, "-L", libdir, "-lusot_b200", "-L", cudart, "-lcudart", f"-Wl,-rpath,{libdir}",
                     f"-Wl,-rpath,{cudart}"], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
-    assert "ABI version 2" in out and "255 crop: 31" in out
+    assert "ABI version 3" in out and "255 crop: 31" in out
 
 
 def test_no_oracle_import_in_product():

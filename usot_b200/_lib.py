@@ -42,6 +42,12 @@ SIGNATURES = {
     "usot_pred_conv": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, ctypes.c_float, _P, _P, _P, _P]),
     "usot_engine_track_frame": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_double, _I, _P, _P, _P]),
+    "usot_maxpool3x3s2p1_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "usot_stem_conv": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "usot_conf_fusion": (_I, [_P, _P, _I, _I, _I64, _P, _P]),
+    "usot_cycle_glue": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "usot_weighted_bce": (_I, [_P, _P, _I, _P, _P]),
+    "usot_iou_loss": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "usot_crop_resize": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "usot_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "usot_nhwc_to_nchw": (_I, [_P, _I, _I, _I, _I, _P, _P]),

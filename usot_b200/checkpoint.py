@@ -20,11 +20,14 @@ MOCO_EMBED_KEYS = ("encoder_q.layer2.0.downsample.0.weight", "encoder_q.layer3.0
 
 
 def remove_prefix(state_dict, prefix, verbose=True):
-    """lib/utils/train_utils.py:130-137."""
+    """Same contract as lib/utils/train_utils.py:130-137: keys that start with ``prefix`` lose it (once), others are kept."""
     if verbose:
-        print('remove prefix \'{}\''.format(prefix))
-    f = lambda x: x.split(prefix, 1)[-1] if x.startswith(prefix) else x
-    return {f(key): value for key, value in state_dict.items()}
+        print("remove prefix '{}'".format(prefix))
+    n = len(prefix)
+    out = {}
+    for key, value in state_dict.items():
+        out[key[n:] if key[:n] == prefix else key] = value
+    return out
 
 
 def check_keys(model, pretrained_state_dict, print_unuse=True, verbose=True):

@@ -3,9 +3,13 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 namespace usot {
+
+// Process-wide performance knobs (usot_set_tunable) are read by launches on any host thread: atomics, never plain ints.
+typedef std::atomic<int> Tunable;
 
 // ---- error plumbing: kernels never exit(); launchers return cudaError_t-like ints ----------
 void set_error(const std::string& msg);
@@ -40,6 +44,19 @@ struct SmemAttrCache {
         return 0;
     }
 };
+
+// SM count of the current device (cached per device; engines of several devices may live in one process).
+inline int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
 
 // ---- activation storage ------------------------------------------------------------------
 // All internal activations are NHWC.  Two storage formats:
@@ -90,7 +107,7 @@ struct GroupDWArgs {
     __half* out_hi = nullptr;                              // optional: write the split-fp16 planes the tower convs read instead of
     __half* out_lo = nullptr;                              // fp32 `out` (FFMA2 kernel only; out_lo may be null in single-fp16 mode)
 };
-extern int g_groupdw_strips, g_groupdw_tma, g_groupdw_row_split;
+extern Tunable g_groupdw_strips, g_groupdw_tma, g_groupdw_row_split;
 bool groupdw_split_output_supported(int F);  // true when launch_groupdw_w will run the FFMA2 kernel, which can write split-fp16 planes
 int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st);  // xcorr_tma.cu
 int launch_groupdw(const GroupDWArgs& a, cudaStream_t st);  // reads dw_weight back (one stream sync)
@@ -104,7 +121,7 @@ int launch_pred_conv(const float* in, int n, int r, int C, const float* w /*[9][
                      const float* b, int cout, int mode, float mul, const float* adjust, const float* bias4, float* out_nchw, cudaStream_t st);
 int launch_pred_repack(const float* w, int cout, int C, float* w4, cudaStream_t st);
 // TMA-streamed per-image variant for large batches (pred_tma.cu); launch_pred_conv dispatches to it when supported
-extern int g_pred_tma_min_batch;
+extern Tunable g_pred_tma_min_batch;
 bool pred_tma_supported(int n, int r, int C, int cout);
 int launch_pred_tma(const float* in, int n, int r, int C, const float* w, const float* b, int cout, int mode, float mul,
                     const float* adjust, const float* bias4, float* out_nchw, cudaStream_t st);

@@ -29,6 +29,8 @@
 #include <cstring>
 #include <algorithm>
 #include <cmath>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace usot {
@@ -543,15 +545,59 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     return 0;
 }
 
-int g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
-int g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
-int g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
-int g_tc_pdl = 1;             // programmatic dependent launch of the conv kernels on small grids (prologue overlaps the previous layer's tail)
-int g_tc_latency_split = 1;   // small grids: halve the N tile until at least half of the SMs have a CTA (batch-1 latency; same arithmetic)
-int g_tc_l2_prefetch = 0;     // TMA L2-prefetch hints for the next tile's residual chunks / 1x1 activation boxes (off: measured slower)
-int g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
-int g_tc_fuse_cross = 1;       // split mode with two accumulators: a_hi*[w_hi|w_lo] as ONE N = 2*BN MMA (A/B switch; same arithmetic)
-int g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cross-term accumulator (accuracy); 256 trades it for reuse
+Tunable g_tc_bn_max = 256;        // tunable: largest N tile (usot_set_tunable("tc_bn_max", 64|128|256))
+Tunable g_tc_tma_res = 1;         // 1: residual via TMA into the staging buffer (needs tc_tma_store); 0: per-thread ld.global
+Tunable g_tc_tma_store = 1;       // 1: TMA-store epilogue for split-fp16 outputs; 0: per-thread st.global (A/B switch)
+Tunable g_tc_pdl = 1;             // programmatic dependent launch of the conv kernels on small grids (prologue overlaps the previous layer's tail)
+Tunable g_tc_latency_split = 1;   // small grids: halve the N tile until at least half of the SMs have a CTA (batch-1 latency; same arithmetic)
+Tunable g_tc_l2_prefetch = 0;     // TMA L2-prefetch hints for the next tile's residual chunks / 1x1 activation boxes (off: measured slower)
+Tunable g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
+Tunable g_tc_fuse_cross = 1;       // split mode with two accumulators: a_hi*[w_hi|w_lo] as ONE N = 2*BN MMA (A/B switch; same arithmetic)
+Tunable g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cross-term accumulator (accuracy); 256 trades it for reuse
+
+struct PlanKey {  // plain words only (no padding: the key is hashed and compared as raw bytes)
+    const void* ptr[11];
+    int geom[14];
+    int K, relu, split, device, knobs[9], pad_;
+};
+struct Plan { TcParams p; int bn, grid; };
+struct PlanKeyHash {
+    size_t operator()(const PlanKey& k) const {
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (size_t i = 0; i < sizeof(PlanKey) / 8; ++i) { h = (h ^ w[i]) * 0x100000001b3ull; h ^= h >> 29; }
+        return (size_t)h;
+    }
+};
+struct PlanKeyEq { bool operator()(const PlanKey& a, const PlanKey& b) const { return memcmp(&a, &b, sizeof(PlanKey)) == 0; } };
+static_assert(sizeof(PlanKey) % 8 == 0, "PlanKey is hashed as 64-bit words");
+static std::mutex g_plan_mu;
+static std::unordered_map<PlanKey, Plan, PlanKeyHash, PlanKeyEq> g_plans;
+
+// (The key holds every pointer AND every shape field, so an address reused by another tensor of a different shape cannot alias.)
+static bool plan_lookup(const PlanKey& k, Plan* out) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_plans.find(k);
+    if (it == g_plans.end()) return false;
+    *out = it->second;
+    return true;
+}
+static void plan_store(const PlanKey& k, const Plan& pl) {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (g_plans.size() >= 4096) g_plans.clear();  // bounded: a sweep over many shapes simply re-encodes
+    g_plans[k] = pl;
+}
+
+static int launch_plan(Plan& pl, bool split, cudaStream_t st) {
+    if (split) {
+        if (pl.bn == 256) return launch_cfg<256, true>(pl.p, pl.grid, st);
+        if (pl.bn == 128) return launch_cfg<128, true>(pl.p, pl.grid, st);
+        return launch_cfg<64, true>(pl.p, pl.grid, st);
+    }
+    if (pl.bn == 256) return launch_cfg<256, false>(pl.p, pl.grid, st);
+    if (pl.bn == 128) return launch_cfg<128, false>(pl.p, pl.grid, st);
+    return launch_cfg<64, false>(pl.p, pl.grid, st);
+}
 
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st) {
     USOT_REQUIRE(g.cin % TC_BK == 0, "conv_tc needs Cin % 64 == 0");
@@ -562,20 +608,34 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     USOT_REQUIRE(ep.out_hi || ep.out_f32, "conv_tc: no output requested");
     if ((size_t)g.n * g.ho * g.wo == 0) return 0;
 
+    // Launch-plan cache: the tensor maps (up to 14 cuTensorMapEncodeTiled calls), tiling and kernel variant of a launch depend only on
+    // the pointers, the geometry and the knobs.  The engine's arena hands out the same addresses for the same call shape, so in steady
+    // state every layer hits (the eager medium-batch path was host-bound on the encodes).
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    const void* kp[11] = {in.hi, in.lo, w.hi, w.lo, w.scale, ep.shift, ep.res_hi, ep.res_lo, ep.out_hi, ep.out_lo, ep.out_f32};
+    const int kg[14] = {g.n, g.h, g.w, g.cin, g.cout, g.kh, g.kw, g.stride, g.ph, g.pw, g.dh, g.dw, g.ho, g.wo};
+    memcpy(key.ptr, kp, sizeof(kp));
+    memcpy(key.geom, kg, sizeof(kg));
+    key.K = w.K; key.relu = ep.relu; key.split = split ? 1 : 0;
+    key.knobs[0] = g_tc_bn_max; key.knobs[1] = g_tc_split_bn_max; key.knobs[2] = g_tc_tma_store; key.knobs[3] = g_tc_tma_res;
+    key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch; key.knobs[7] = g_tc_latency_split;
+    key.knobs[8] = g_tc_pdl;
+    USOT_CUDA_OK(cudaGetDevice(&key.device));
+    {
+        Plan hit;
+        if (plan_lookup(key, &hit)) return launch_plan(hit, split, st);
+    }
+
     TcParams p;
     memset(&p, 0, sizeof(p));
     int bn = 64;
-    const int bn_cap = split ? std::min(g_tc_bn_max, g_tc_split_bn_max) : g_tc_bn_max;
+    const int bn_cap = split ? std::min(g_tc_bn_max.load(), g_tc_split_bn_max.load()) : g_tc_bn_max.load();
     if (g.cout % 256 == 0 && bn_cap >= 256) bn = 256;
     else if (g.cout % 128 == 0 && bn_cap >= 128) bn = 128;
     choose_tiling(g.ho, g.wo, &p.tiles_w, &p.bw, &p.bh);
     p.tiles_h = (g.ho + p.bh - 1) / p.bh;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        USOT_CUDA_OK(cudaGetDevice(&dev));
-        USOT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = device_sm_count();
     // Latency mode (small batches): while the grid would leave at least half of the SMs idle, halve the N tile -- twice as many CTAs,
     // and every MMA of a tile's K loop is half as wide (half as long).  The accumulation order of each output element does not
     // change, so results stay bit-identical to the wide-tile launch of a large batch (tests: batch independence, graph replay).
@@ -652,18 +712,15 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         }
     }
 
-    const int grid = std::min(p.num_tiles, num_sms);
+    Plan plan;
+    plan.p = p;
+    plan.bn = bn;
+    plan.grid = std::min(p.num_tiles, num_sms);
     // Programmatic dependent launch pays in the latency regime (every tile has its own SM, idle SMs host the successor's prologue):
     // batch 1: -7 % per track() call.  At batch 256 it measured -1.6 % (within clock noise, no possible gain): not used there.
-    p.pdl = (g_tc_pdl && p.num_tiles <= num_sms) ? 1 : 0;
-    if (split) {
-        if (bn == 256) return launch_cfg<256, true>(p, grid, st);
-        if (bn == 128) return launch_cfg<128, true>(p, grid, st);
-        return launch_cfg<64, true>(p, grid, st);
-    }
-    if (bn == 256) return launch_cfg<256, false>(p, grid, st);
-    if (bn == 128) return launch_cfg<128, false>(p, grid, st);
-    return launch_cfg<64, false>(p, grid, st);
+    plan.p.pdl = (g_tc_pdl && p.num_tiles <= num_sms) ? 1 : 0;
+    plan_store(key, plan);
+    return launch_plan(plan, split, st);
 }
 
 // =============================================================================================
@@ -689,6 +746,23 @@ int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaS
     const size_t n4 = n / 4;
     f32_to_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in), n4, reinterpret_cast<uint2*>(hi),
                                                                        reinterpret_cast<uint2*>(lo));
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void split_to_f32_kernel(const __half2* __restrict__ hi, const __half2* __restrict__ lo, size_t n2, float2* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const float2 a = __half22float2(hi[i]);
+    const float2 b = lo ? __half22float2(lo[i]) : make_float2(0.f, 0.f);
+    out[i] = make_float2(a.x + b.x, a.y + b.y);
+}
+
+int launch_split_to_f32(const __half* hi, const __half* lo, size_t n, float* out, cudaStream_t st) {
+    USOT_REQUIRE(n % 2 == 0, "split_to_f32: element count must be even");
+    if (n == 0) return 0;
+    split_to_f32_kernel<<<(unsigned)((n / 2 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half2*>(hi), reinterpret_cast<const __half2*>(lo),
+                                                                         n / 2, reinterpret_cast<float2*>(out));
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }

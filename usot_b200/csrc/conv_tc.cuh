@@ -59,12 +59,14 @@ struct TcEpilogue {
 // generic cuTensorMapEncodeTiled wrapper (dtype / swizzle are CUtensorMapDataType / CUtensorMapSwizzle values)
 int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                 const cuuint32_t* box, int swizzle);
-extern int g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
+extern Tunable g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st);
 int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
+int launch_split_to_f32(const __half* hi, const __half* lo /*or null*/, size_t n, float* out, cudaStream_t st);  // out = hi + lo
 void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,
                           std::vector<float>& scale_out);
 
+size_t stem_tc_image_bytes();  // size of the packed stem weight tile (validated when a packed-weight image is imported)
 void pack_stem_tc_host(const float* w_oihw, const float* scale_in, std::vector<uint8_t>& img, std::vector<float>& scale_out);
 
 }  // namespace usot

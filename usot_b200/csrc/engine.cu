@@ -37,16 +37,29 @@ struct Profiler {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
 };
 static Profiler g_prof;
-static int g_stem_tc = 1;  // tunable "stem_tc": 1 = tensor-core stem in the tcgen05 precision modes, 0 = CUDA-core stem
+static thread_local long long tl_launches[8] = {0};  // this host thread's launches (graph capture takes its per-family counts from here)
+static std::mutex g_prof_mu;  // launches of several engines (DataParallel-style host threads) update the counters concurrently
+static void count_launches(int fam, long long n) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.launches[fam] += n;
+}
+static Tunable g_stem_tc{1};  // tunable "stem_tc": 1 = tensor-core stem in the tcgen05 precision modes, 0 = CUDA-core stem
 struct Scope {
     int fam; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     Scope(int fam_, cudaStream_t st_, double flops = 0, double bytes = 0) : fam(fam_), st(st_) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
         g_prof.launches[fam]++;
+        tl_launches[fam]++;
         g_prof.flops[fam] += flops;
         g_prof.bytes[fam] += bytes;
         if (g_prof.on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
-    ~Scope() { if (g_prof.on) { cudaEventRecord(b, st); g_prof.ev.push_back({fam, {a, b}}); } }
+    ~Scope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.ev.push_back({fam, {a, b}});
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -175,9 +188,11 @@ struct usot_engine {
     float *adjust = nullptr, *bias4 = nullptr;
     Arena arena;
     // CUDA-graph cache of track() for small batches: key = (n, size, nz, nq); valid while the arena has not moved
-    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0; int seen = 0; long long launches[8] = {0}; };
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0, weights_gen = 0; int seen = 0; long long launches[8] = {0}; };
     std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
     uint64_t arena_gen = 0;
+    uint64_t weights_gen = 0;         // bumped by every (re)pack: captured graphs hold weight pointers and weight tensor maps
+    cudaEvent_t ev_done = nullptr;    // end of the last call that used the arena / frame workspace: the next call's stream waits on it
     cudaStream_t gstream = nullptr;   // graphs are captured and replayed on an engine-owned stream (the caller's may be the
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // legacy default stream, which cannot be captured); ordered by events
     std::mutex mu;  // one forward at a time per engine (DataParallel replicas own separate engines)
@@ -192,6 +207,7 @@ struct usot_engine {
         if (gstream) cudaStreamDestroy(gstream);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
+        if (ev_done) cudaEventDestroy(ev_done);
         for (void* p : owned) cudaFree(p);
         if (arena.base) cudaFree(arena.base);
         if (frame_ws) cudaFree(frame_ws);
@@ -298,6 +314,12 @@ static int fold_bn(usot_engine* e, const std::string& conv, const std::string& b
 // imported image instead, in the same order.
 static int finalize_impl(usot_engine* e) {
     USOT_CUDA_OK(cudaSetDevice(e->device));
+    // Captured track() graphs carry the old weight pointers / weight tensor maps as kernel parameters: make every one of them
+    // stale BEFORE the buffers are freed (replay is gated on weights_gen), and drop the executables.
+    ++e->weights_gen;
+    USOT_CUDA_OK(cudaDeviceSynchronize());  // nothing in flight may still read the buffers freed below
+    for (auto& g : e->graphs)
+        if (g.second.exec) { cudaGraphExecDestroy(g.second.exec); g.second.exec = nullptr; }
     for (void* p : e->owned) cudaFree(p);
     e->owned.clear();
     e->convs.clear();
@@ -326,7 +348,7 @@ static int finalize_impl(usot_engine* e) {
         if (upload(e, packed, &e->stem_w, 147 * 64) || upload(e, scale, &e->stem_scale, 64) || upload(e, shift, &e->stem_shift, 64)) return 1;
         if (tc) {
             float* d = nullptr;
-            if (upload(e, as_f, &d) || upload(e, scale_tc, &e->stem_tc_scale, 64)) return 1;
+            if (upload(e, as_f, &d, stem_tc_image_bytes() / sizeof(float)) || upload(e, scale_tc, &e->stem_tc_scale, 64)) return 1;
             e->stem_tc_img = d;
         }
     }
@@ -654,11 +676,26 @@ static int prroi(Ctx& c, const T& feat, const float* boxes, int n_rois, float* o
 
 
 // Two-pass driver: plan (count arena bytes) -> grow arena if needed -> execute.
+// The arena (and the frame workspace) is reused from offset 0 by every call, so calls are ordered ON THE DEVICE as well as on the
+// host: each call's stream first waits for the event recorded at the end of the previous call (a no-op on the same stream) --
+// callers may therefore issue calls of one engine from different streams.
+static int order_begin(usot_engine* e, cudaStream_t st) {
+    if (!e->ev_done) USOT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+    else USOT_CUDA_OK(cudaStreamWaitEvent(st, e->ev_done, 0));
+    return 0;
+}
+static int order_end(usot_engine* e, cudaStream_t st) {
+    USOT_CUDA_OK(cudaEventRecord(e->ev_done, st));
+    return 0;
+}
+
 template <typename Fn>
-static int with_arena(usot_engine* e, Fn&& body) {
+static int with_arena(usot_engine* e, cudaStream_t st, Fn&& body, bool ordered = true) {
     USOT_REQUIRE(e && e->finalized, "engine not finalized (load the state_dict and call usot_engine_finalize)");
     std::lock_guard<std::mutex> lk(e->mu);
     USOT_CUDA_OK(cudaSetDevice(e->device));
+    if (ordered)
+        if (int rc = order_begin(e, st)) return rc;
     Arena& ar = e->arena;
     ar.plan = true;
     ar.off = 0;
@@ -681,10 +718,11 @@ static int with_arena(usot_engine* e, Fn&& body) {
         ++e->arena_gen;  // captured graphs hold arena addresses
     }
     ar.off = 0;
-    return body(ar);
+    if (int rc = body(ar)) return rc;
+    return ordered ? order_end(e, st) : 0;
 }
 
-static int g_graph_max_batch = 8;  // tunable "graph_max_batch": track() with n <= this replays a captured CUDA graph (0 = off)
+static Tunable g_graph_max_batch{8};  // tunable "graph_max_batch": track() with n <= this replays a captured CUDA graph (0 = off)
 
 }  // namespace usot
 
@@ -694,10 +732,11 @@ static int g_graph_max_batch = 8;  // tunable "graph_max_batch": track() with n 
 extern "C" {
 
 const char* usot_last_error(void) { return g_err.c_str(); }
-int usot_abi_version(void) { return 2; }
+int usot_abi_version(void) { return 3; }
 
 /* Profiling: kernel launches are always counted; with on=1 every launch is also bracketed by CUDA events on its stream. */
 int usot_profile_reset(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& e : g_prof.ev) { cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second); }
     g_prof.ev.clear();
     for (int i = 0; i < FAM_COUNT; ++i) { g_prof.launches[i] = 0; g_prof.flops[i] = 0; g_prof.bytes[i] = 0; }
@@ -710,6 +749,7 @@ const char* usot_profile_family_name(int fam) { return (fam >= 0 && fam < FAM_CO
 int usot_profile_read(int fam, double* out) {
     USOT_REQUIRE(fam >= 0 && fam < FAM_COUNT && out, "bad argument");
     USOT_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     double ms = 0;
     for (auto& e : g_prof.ev)
         if (e.first == fam) { float t = 0; cudaEventElapsedTime(&t, e.second.first, e.second.second); ms += t; }
@@ -841,7 +881,7 @@ int usot_pred_conv(const float* in, int n, int r, int channels, const float* wei
     USOT_REQUIRE(n == 0 || (in && weight && bias && out), "null pointer");
     USOT_REQUIRE(n >= 0 && r > 0 && channels > 0, "bad shape");
     USOT_REQUIRE(mode == 0 || (mode == 1 && adjust && bias4), "mode must be 0, or 1 with adjust and bias4");
-    g_prof.launches[FAM_PRED]++;
+    count_launches(FAM_PRED, 1);
     return launch_pred_conv(in, n, r, channels, weight, nullptr, bias, cout, mode, mul, adjust, bias4, out, (cudaStream_t)stream);
 }
 
@@ -849,7 +889,7 @@ int usot_crop_resize(const uint8_t* frames, int n_frames, int height, int width,
                      int model_sz, float* out, void* stream) {
     USOT_REQUIRE(n == 0 || (frames && crops && fill && out), "null pointer");
     USOT_REQUIRE(n >= 0 && n <= 65535 && n_frames > 0 && height > 0 && width > 0 && model_sz > 0 && model_sz <= 4096, "bad shape");
-    g_prof.launches[FAM_OTHER]++;
+    count_launches(FAM_OTHER, 1);
     return launch_crop_resize(frames, n_frames, height, width, crops, fill, n, model_sz, out, (cudaStream_t)stream);
 }
 
@@ -894,12 +934,25 @@ int usot_engine_finalize(usot_engine* e) {
     return finalize_impl(e);
 }
 
-/* Packed-weight image: header {magic, abi, precision, record count} + records [u64 bytes][payload padded to 8]. */
+/* Packed-weight image: header {magic, abi, precision, record count, checksum} + records [u64 bytes][payload padded to 8]. */
 static const uint64_t kPackedMagic = 0x55534f5442323030ull;  // "USOTB200"
+static const int kPackedHeader = 40;
+
+// 64-bit word-wise multiply/xorshift hash of the record area (sizes + payloads; every record is padded to 8 bytes)
+static uint64_t packed_checksum(const uint8_t* p, size_t bytes) {
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    for (size_t i = 0; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0xff51afd7ed558ccdull;
+        h ^= h >> 32;
+    }
+    return h;
+}
 
 int64_t usot_engine_packed_size(const usot_engine* e) {
     if (!e || !e->finalized) return 0;
-    int64_t n = 32;
+    int64_t n = kPackedHeader;
     for (const auto& r : e->records) n += 8 + (int64_t)((r.bytes + 7) & ~size_t(7));
     return n;
 }
@@ -909,10 +962,8 @@ int usot_engine_export_packed(usot_engine* e, void* host_buf, int64_t capacity) 
     USOT_REQUIRE(host_buf && capacity >= usot_engine_packed_size(e), "buffer too small (see usot_engine_packed_size)");
     std::lock_guard<std::mutex> lk(e->mu);
     USOT_CUDA_OK(cudaSetDevice(e->device));
-    uint8_t* p = static_cast<uint8_t*>(host_buf);
-    const uint64_t hdr[4] = {kPackedMagic, (uint64_t)usot_abi_version(), (uint64_t)e->precision, (uint64_t)e->records.size()};
-    memcpy(p, hdr, 32);
-    p += 32;
+    uint8_t* const base = static_cast<uint8_t*>(host_buf);
+    uint8_t* p = base + kPackedHeader;
     for (const auto& r : e->records) {
         const uint64_t n = r.bytes;
         memcpy(p, &n, 8);
@@ -923,19 +974,24 @@ int usot_engine_export_packed(usot_engine* e, void* host_buf, int64_t capacity) 
         memset(p + r.bytes, 0, padded - r.bytes);
         p += padded;
     }
+    const uint64_t hdr[5] = {kPackedMagic, (uint64_t)usot_abi_version(), (uint64_t)e->precision, (uint64_t)e->records.size(),
+                             packed_checksum(base + kPackedHeader, (size_t)(p - base) - kPackedHeader)};
+    memcpy(base, hdr, kPackedHeader);
     return 0;
 }
 
 int usot_engine_import_packed(usot_engine* e, const void* host_buf, int64_t size) {
-    USOT_REQUIRE(e && host_buf && size >= 32, "bad argument");
+    USOT_REQUIRE(e && host_buf && size >= kPackedHeader, "bad argument");
     std::lock_guard<std::mutex> lk(e->mu);
     const uint8_t* p = static_cast<const uint8_t*>(host_buf);
-    uint64_t hdr[4];
-    memcpy(hdr, p, 32);
+    uint64_t hdr[5];
+    memcpy(hdr, p, kPackedHeader);
     USOT_REQUIRE(hdr[0] == kPackedMagic, "not a usot_b200 packed weight image");
     USOT_REQUIRE(hdr[1] == (uint64_t)usot_abi_version(), "packed weight image was written by another ABI version");
     USOT_REQUIRE(hdr[2] == (uint64_t)e->precision, "packed weight image was written for another precision mode");
-    e->replay = p + 32;
+    USOT_REQUIRE((size - kPackedHeader) % 8 == 0 && hdr[4] == packed_checksum(p + kPackedHeader, (size_t)size - kPackedHeader),
+                 "packed weight image is corrupt (checksum mismatch)");
+    e->replay = p + kPackedHeader;
     e->replay_end = p + size;
     int rc = finalize_impl(e);
     if (rc == 0 && e->records.size() != hdr[3]) { set_error("usot_b200: packed weight image has an unexpected record count"); rc = 2; }
@@ -954,7 +1010,7 @@ int usot_feature_size(int s) {
 
 int usot_engine_backbone_neck(usot_engine* e, const float* x, int n, int size, float* xf, void* stream) {
     USOT_REQUIRE(x && xf && n > 0 && size >= 63, "bad argument");
-    return with_arena(e, [&](Arena& ar) {
+    return with_arena(e, (cudaStream_t)stream, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
         T f;
         return backbone_neck(c, x, n, size, xf, &f);
@@ -964,7 +1020,7 @@ int usot_engine_backbone_neck(usot_engine* e, const float* x, int n, int size, f
 int usot_engine_template(usot_engine* e, const float* z, int n, int size, const float* template_bbox, float* zf, float* x_ori,
                          void* stream) {
     USOT_REQUIRE(z && zf && n > 0 && size >= 63, "bad argument");
-    return with_arena(e, [&](Arena& ar) {
+    return with_arena(e, (cudaStream_t)stream, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
         T f;
         if (int rc = backbone_neck(c, z, n, size, x_ori, &f)) return rc;
@@ -1006,15 +1062,17 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
             if (int rc = head_memory(c, cls_x, n, f.h, mi, nq, n * nq, staged ? io.cls_mem : cls_mem)) return rc;
         return 0;
     };
-    if (!want_graph) return with_arena(e, [&](Arena& ar) { return body(ar, false); });
+    if (!want_graph) return with_arena(e, st, [&](Arena& ar) { return body(ar, false); });
 
     usot_engine::GraphEntry* ge = nullptr;
+    bool first = false;
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        ge = &e->graphs[std::make_tuple(n, size, nz, nq)];
+        ge = &e->graphs[std::make_tuple(n, size, nz, nq)];  // (std::map: the entry's address is stable)
+        first = ge->seen++ == 0;
     }
-    if (ge->seen++ == 0)  // first call with this shape runs eagerly (one-time kernel attribute / constant setup must not be captured)
-        return with_arena(e, [&](Arena& ar) { return body(ar, false); });
+    if (first)  // first call with this shape runs eagerly (one-time kernel attribute / constant setup must not be captured)
+        return with_arena(e, st, [&](Arena& ar) { return body(ar, false); });
     USOT_CUDA_OK(cudaSetDevice(e->device));
     if (!e->gstream) {
         USOT_CUDA_OK(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
@@ -1024,19 +1082,23 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
     st = e->gstream;
     USOT_CUDA_OK(cudaEventRecord(e->ev_in, caller));   // everything the caller enqueued (inputs!) precedes the graph
     USOT_CUDA_OK(cudaStreamWaitEvent(st, e->ev_in, 0));
-    if (!ge->exec || ge->arena_gen != e->arena_gen) {
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (int rc = order_begin(e, st)) return rc;   // (outside the capture: the event belongs to no graph)
+    }
+    if (!ge->exec || ge->arena_gen != e->arena_gen || ge->weights_gen != e->weights_gen) {
         // (re)capture: the planning pass of with_arena sizes / grows the arena, the execute pass is recorded into the graph
         if (ge->exec) { cudaGraphExecDestroy(ge->exec); ge->exec = nullptr; }
         long long before[FAM_COUNT];
-        for (int i = 0; i < FAM_COUNT; ++i) before[i] = g_prof.launches[i];
+        for (int i = 0; i < FAM_COUNT; ++i) before[i] = tl_launches[i];
         bool capturing = false;
-        int rc = with_arena(e, [&](Arena& ar) -> int {
+        int rc = with_arena(e, st, [&](Arena& ar) -> int {
             if (!ar.plan) {
                 if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { set_error("usot_b200: cudaStreamBeginCapture failed"); return 1; }
                 capturing = true;
             }
             return body(ar, true);
-        });
+        }, /*ordered=*/false);
         cudaGraph_t graph = nullptr;
         if (capturing) {
             cudaError_t ce = cudaStreamEndCapture(st, &graph);
@@ -1047,7 +1109,8 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
         cudaGraphDestroy(graph);
         if (ie != cudaSuccess) { ge->exec = nullptr; set_error(std::string("usot_b200: cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return 1; }
         ge->arena_gen = e->arena_gen;
-        for (int i = 0; i < FAM_COUNT; ++i) { ge->launches[i] = g_prof.launches[i] - before[i]; g_prof.launches[i] = before[i]; }
+        ge->weights_gen = e->weights_gen;
+        for (int i = 0; i < FAM_COUNT; ++i) { ge->launches[i] = tl_launches[i] - before[i]; count_launches(i, -ge->launches[i]); }  // (capture launched nothing)
     } else {
         // replay: recompute the (deterministic) staging addresses without launching anything
         std::lock_guard<std::mutex> lk(e->mu);
@@ -1060,13 +1123,17 @@ int usot_engine_track(usot_engine* e, const float* x, int n, int size, const flo
     USOT_CUDA_OK(cudaMemcpyAsync(io.zf, zf, n_zf * 4, cudaMemcpyDeviceToDevice, st));
     if (nq) USOT_CUDA_OK(cudaMemcpyAsync(io.mem, template_mem, n_mem * 4, cudaMemcpyDeviceToDevice, st));
     USOT_CUDA_OK(cudaGraphLaunch(ge->exec, st));
-    for (int i = 0; i < FAM_COUNT; ++i) g_prof.launches[i] += ge->launches[i];
+    for (int i = 0; i < FAM_COUNT; ++i) count_launches(i, ge->launches[i]);
     USOT_CUDA_OK(cudaMemcpyAsync(cls, io.cls, n_cls * 4, cudaMemcpyDeviceToDevice, st));
     USOT_CUDA_OK(cudaMemcpyAsync(bbox, io.bbox, 4 * n_cls * 4, cudaMemcpyDeviceToDevice, st));
     if (nq) USOT_CUDA_OK(cudaMemcpyAsync(cls_mem, io.cls_mem, n_cls * 4, cudaMemcpyDeviceToDevice, st));
     if (xf) USOT_CUDA_OK(cudaMemcpyAsync(xf, io.xf, n_xf * 4, cudaMemcpyDeviceToDevice, st));
     USOT_CUDA_OK(cudaEventRecord(e->ev_out, st));
     USOT_CUDA_OK(cudaStreamWaitEvent(caller, e->ev_out, 0));  // the caller's stream sees the outputs in order
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (int rc = order_end(e, st)) return rc;
+    }
     return 0;
 }
 
@@ -1101,11 +1168,15 @@ int usot_engine_track_frame(usot_engine* e, const uint8_t* frame, int height, in
         e->frame_ws = static_cast<char*>(p);
         e->frame_ws_cap = off;
     }
+    {   // the previous call of this engine (possibly issued on another stream) may still be reading the workspace
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (int rc = order_begin(e, st)) return rc;
+    }
     char* ws = e->frame_ws;
     float *x = reinterpret_cast<float*>(ws + o_x), *mem = reinterpret_cast<float*>(ws + o_mem), *cls = reinterpret_cast<float*>(ws + o_cls);
     float *bbox = reinterpret_cast<float*>(ws + o_bbox), *cm = reinterpret_cast<float*>(ws + o_cm), *xf = reinterpret_cast<float*>(ws + o_xf);
     float* box = reinterpret_cast<float*>(ws + o_box);
-    g_prof.launches[FAM_OTHER] += 4;
+    count_launches(FAM_OTHER, 4);
     if (int rc = launch_crop_resize_one(frame, height, width, context_xmin, context_ymin, original_sz, fill, instance_size, x, st)) return rc;
     if (int rc = launch_gather_rows(mem_buf, mem_rows, nq, (size_t)49 * 256, mem, st)) return rc;
     if (int rc = usot_engine_track(e, x, 1, instance_size, zf, 1, mem, nq, cls, bbox, cm, xf, stream)) return rc;
@@ -1119,7 +1190,7 @@ int usot_engine_extract_memory_feature(usot_engine* e, const float* ori_x, int n
                                        const float* search_bbox, float* out, void* stream) {
     USOT_REQUIRE((ori_x != nullptr) != (xf != nullptr), "exactly one of ori_x / xf must be given");
     USOT_REQUIRE(search_bbox && out && n > 0, "bad argument");
-    return with_arena(e, [&](Arena& ar) {
+    return with_arena(e, (cudaStream_t)stream, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
         T f = wrap_f32(xf, n, feat, feat, 256);
         if (ori_x)
@@ -1134,7 +1205,7 @@ int usot_engine_forward_train(usot_engine* e, const float* zf, const float* xf, 
     USOT_REQUIRE(zf && xf && label && reg_target && reg_weight && losses && n > 0 && m >= 0, "bad argument");
     USOT_REQUIRE(m == 0 || (xf_mem && search_bbox), "cycle memory needs xf_mem and search_bbox");
     USOT_REQUIRE(feat >= 9, "feature map too small");
-    return with_arena(e, [&](Arena& ar) {
+    return with_arena(e, (cudaStream_t)stream, [&](Arena& ar) {
         Ctx c{e, ar, (cudaStream_t)stream};
         const int R = feat - 6, cells = R * R;
         T xf_t = wrap_f32(xf, n, feat, feat, 256);
@@ -1173,7 +1244,7 @@ int usot_tracker_postprocess(const float* cls, const float* cls_mem, const float
                              double window_influence, double* result, void* stream) {
     USOT_REQUIRE(cls && cls_mem && bbox && window && result, "null pointer");
     USOT_REQUIRE(target_w > 0 && target_h > 0, "target size must be positive");
-    g_prof.launches[FAM_OTHER]++;
+    count_launches(FAM_OTHER, 1);
     return launch_tracker_post(cls, cls_mem, bbox, window, score_size, instance_size, target_w, target_h, (float)ratio, penalty_k,
                                window_influence, result, (cudaStream_t)stream);
 }

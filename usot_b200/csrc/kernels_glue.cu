@@ -64,11 +64,15 @@ __global__ void __launch_bounds__(256) tracker_post_kernel(const float* __restri
         const double r_c = change((tw / th) / ((x2 - x1) / (y2 - y1)));
         const double pen = exp(-(r_c * s_c - 1.0) * penalty_k);
         const double ps = pen * (double)mix * (1.0 - window_influence) + window[i] * window_influence;
-        if (ps > best) { best = ps; best_i = i; }
+        // a NaN score is the maximum for numpy's argmax (first NaN wins): map it to +inf so the smallest NaN index is returned
+        const double key = ps != ps ? DBL_MAX : ps;
+        if (key > best) { best = key; best_i = i; }
     }
     block_argmax(best, best_i);
     if (threadIdx.x == 0) {
-        const int i = best_i, r = i / R, c = i % R;
+        // No cell compared greater than -DBL_MAX: every penalised score is NaN (non-finite weights / inf boxes).  numpy's argmax
+        // (usot_tracker.py:157) returns the first NaN cell, which is cell 0 when all are NaN: never index out of bounds.
+        const int i = (best_i >= 0 && best_i < cells) ? best_i : 0, r = i / R, c = i % R;
         const float s0 = 1.f / (1.f + expf(-cls[i])), s1 = 1.f / (1.f + expf(-cls_mem[i]));
         const float mix = ratio * s0 + (1.f - ratio) * s1;
         const double gx = (double)(c - R / 2) * 8.0 + half, gy = (double)(r - R / 2) * 8.0 + half;

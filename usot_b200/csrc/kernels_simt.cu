@@ -404,8 +404,8 @@ int launch_groupdw(const GroupDWArgs& a, cudaStream_t st) {
     return launch_groupdw_w(a, e0 / s, e1 / s, e2 / s, st);
 }
 
-int g_groupdw_strips = 3;  // tunable (usot_set_tunable("groupdw_strips", 2|3)) of the register-staged variant
-int g_groupdw_tma = 2;     // tunable: 2 = TMA ring + packed FFMA2 (xcorr_tma.cu, default), 1 = TMA ring + scalar FMA, 0 = register-staged kernel below
+Tunable g_groupdw_strips = 3;  // tunable (usot_set_tunable("groupdw_strips", 2|3)) of the register-staged variant
+Tunable g_groupdw_tma = 2;     // tunable: 2 = TMA ring + packed FFMA2 (xcorr_tma.cu, default), 1 = TMA ring + scalar FMA, 0 = register-staged kernel below
 
 bool groupdw_split_output_supported(int F) { return g_groupdw_tma >= 2 && (F - 6 + 8) / 9 == 3; }
 

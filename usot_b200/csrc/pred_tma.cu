@@ -227,7 +227,7 @@ int launch_pred_repack(const float* w, int cout, int C, float* w4, cudaStream_t 
     return 0;
 }
 
-int g_pred_tma_min_batch = 48;  // tunable "pred_tma_min_batch": batches of at least this many images use the kernel above (0 = never)
+Tunable g_pred_tma_min_batch = 48;  // tunable "pred_tma_min_batch": batches of at least this many images use the kernel above (0 = never)
 
 bool pred_tma_supported(int n, int r, int C, int cout) {
     return g_pred_tma_min_batch > 0 && n >= g_pred_tma_min_batch && C == 256 && (cout == 1 || cout == 4) && r >= 8 && r <= 27;

@@ -210,18 +210,15 @@ int launch_stem_tc(const float* x, int n, int s, const void* w_img, const float*
     p.tiles_per_row = (p.HO + 127) / 128;
     p.num_tiles = n * p.HO * p.tiles_per_row;
     if (p.num_tiles == 0) return 0;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        USOT_CUDA_OK(cudaGetDevice(&dev));
-        USOT_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = device_sm_count();
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (split) stem_tc_kernel<true><<<grid, 256, ST_SMEM, st>>>(p);
     else stem_tc_kernel<false><<<grid, 256, ST_SMEM, st>>>(p);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+size_t stem_tc_image_bytes() { return (size_t)2 * ST_B_PLANE; }
 
 // w: OIHW (64,3,7,7) flattened [64][147].  Produces the shared-memory image of the B tile (hi plane then lo plane, each
 // 3 chunks x 64 rows x 128 B with the 128B swizzle) of w * 2^e[co], and scale_out = scale_in * 2^-e.

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 3) groupdw_tma_kernel(const
 // CTA = (output sample, 64-channel slab): 3 consumer warps (one column strip each, 32 channel pairs) + 1 TMA producer warp.
 // ---------------------------------------------------------------------------------------------
 constexpr int G2_STAGES = 2, G2_CONSUMER_WARPS = 3;
-int g_groupdw_row_split = 1;  // tunable "groupdw_row_split": small batches split the output rows of one map over several CTAs
+Tunable g_groupdw_row_split = 1;  // tunable "groupdw_row_split": small batches split the output rows of one map over several CTAs
 
 static __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;"
@@ -349,7 +349,8 @@ int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaS
         // CTA re-reads 4 warm-up input rows (L2 hits); results are bit-identical to the whole-map CTA (same fma sequence per row).
         const int pairs = a.n_out * (a.C / 64);
         p.row_groups = 1;
-        if (g_groupdw_row_split && pairs * 2 <= 148) p.row_groups = std::min(R, 148 / pairs);
+        const int sms = device_sm_count();
+        if (g_groupdw_row_split && pairs * 2 <= sms) p.row_groups = std::min(R, sms / pairs);
         p.rows_per_group = (R + p.row_groups - 1) / p.row_groups;
         p.row_groups = (R + p.rows_per_group - 1) / p.rows_per_group;
         groupdw_ffma2_kernel<<<(unsigned)(pairs * p.row_groups), G2_CONSUMER_WARPS * 32 + 32, smem2, st>>>(p);

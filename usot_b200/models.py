@@ -138,13 +138,33 @@ class USOT_(nn.Module):
         self._tensors = None  # .cuda() / .to() replace buffer objects and move parameter storage
         return super()._apply(fn, *args, **kwargs)
 
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._tensors = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def invalidate(self):
+        """Force the engines to re-pack the weights on the next call.  Needed after edits that autograd's version counters do
+        not see: writes through ``p.data`` (``p.data.copy_()``, ``m.weight.data.normal_()`` -- the reference's own init idiom,
+        lib/models/modules.py:99-102) and after re-assigning a Parameter / buffer object of a sub-module."""
+        self._tensors = None
+        self._engine_keys = {}
+
+    repack = invalidate
+
     def _weights_key(self):
-        """Changes whenever any parameter / buffer is modified in place (version counters only grow) or re-allocated.  Called on
-        every forward entry point, so it walks a cached tensor list instead of rebuilding state_dict() (1.2 ms -> 0.1 ms)."""
+        """Per-tensor (storage address, version counter) of every parameter / buffer: changes when any of them is modified in place
+        through the tensor API (version counters only grow), re-allocated or moved.  Edits through ``.data`` do not bump the
+        version counter: call ``invalidate()`` after those.  Called on every forward entry point, so it walks a cached tensor list
+        instead of rebuilding state_dict() (1.2 ms -> 0.1 ms)."""
         ts = getattr(self, "_tensors", None)
         if ts is None:
             ts = self._tensors = list(self.state_dict(keep_vars=True).values())
-        return (len(ts), sum(v._version for v in ts), sum(v.data_ptr() for v in ts))
+        return tuple((v.data_ptr(), v._version) for v in ts)
 
     def _engine(self, device=None):
         """The engine of the device the parameters live on, (re)packed if any parameter changed since the last call."""

@@ -5,6 +5,10 @@
     groupdw_xcorr     lib/models/connect.py:86-102 (fused, NHWC)
     conv2d_nhwc       nn.Conv2d + folded BatchNorm2d (+residual)(+ReLU)
     pred_conv         bbox_pred / cls_pred / cls_memory_pred + epilogue, lib/models/connect.py:235-241,274-275
+    stem_conv, maxpool3x3s2p1_nhwc   conv1+bn1+relu / maxpool, lib/models/modules.py:70-75,138-141
+    conf_fusion       reduction of Conf_Fusion.forward, lib/models/connect.py:123-144
+    cycle_glue        forward-tracking argmax / box maps, lib/models/models.py:262-274
+    weighted_bce, iou_loss           lib/models/models.py:42-100
 
 torch is used for device memory and the current stream only.
 """
@@ -198,3 +202,86 @@ def conv2d_nhwc_input_grad(grad_out, weight_oihw, padding=(0, 0), dilation=(1, 1
     cin = w_t.shape[0]
     one = torch.ones(cin, dtype=torch.float32, device=grad_out.device)
     return conv2d_nhwc(grad_out, w_t, one, torch.zeros_like(one), stride=1, padding=pad, dilation=dilation, precision=precision)
+
+
+# ---- small stand-alone operators (each one reference op, exposed for op-level parity tests) ---------------------------------
+def maxpool3x3s2p1_nhwc(x, split=False):
+    """MaxPool2d(3, stride 2, padding 1) of the stem (lib/models/modules.py:75,141).  x NHWC (n,h,w,C) -> NHWC (n,ho,wo,C).
+    ``split=True`` runs the engine's variant that writes split-fp16 planes and returns hi + lo."""
+    _need_float(x)
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().usot_maxpool3x3s2p1_nhwc(_lib.ptr(x.contiguous()), n, h, w, c, None if split else _lib.ptr(out),
+                                                        _lib.ptr(out) if split else None, _stream(x)))
+    return out
+
+
+def stem_conv(x, weight_oihw, scale, shift, precision="fp32"):
+    """conv1 7x7/2 p0 + folded BN + ReLU (lib/models/modules.py:70-74,138-140).  x NCHW (n,3,S,S) on the GPU; weight (64,3,7,7),
+    scale / shift (64) on the host or device (copied to the host: the entry packs them itself).  Returns NHWC (n,HO,HO,64)."""
+    _need_float(x)
+    _need_cuda(x)
+    n, c, s, s2 = x.shape
+    assert c == 3 and s == s2 and tuple(weight_oihw.shape) == (64, 3, 7, 7)
+    ho = (s - 7) // 2 + 1
+    host = [t.detach().to("cpu", torch.float32).contiguous() for t in (weight_oihw, scale, shift)]
+    out = torch.empty((n, ho, ho, 64), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().usot_stem_conv(_lib.ptr(x.contiguous()), n, s, _lib.ptr(host[0]), _lib.ptr(host[1]), _lib.ptr(host[2]),
+                                              _lib.ptr(out), _lib.PRECISIONS[precision], _stream(x)))
+    return out
+
+
+def conf_fusion(conf, value, nq):
+    """Reduction of Conf_Fusion.forward (lib/models/connect.py:123-144): conf / value (B*nq, ...) -> (B, ...)."""
+    _need_float(conf, value)
+    _need_cuda(conf, value)
+    assert conf.shape == value.shape and conf.shape[0] % nq == 0
+    b = conf.shape[0] // nq
+    per_map = conf[0].numel()
+    out = torch.empty((b,) + tuple(conf.shape[1:]), dtype=torch.float32, device=conf.device)
+    with torch.cuda.device(conf.device):
+        _lib.check(_lib.load().usot_conf_fusion(_lib.ptr(conf.contiguous()), _lib.ptr(value.contiguous()), b, nq, per_map, _lib.ptr(out),
+                                                _stream(conf)))
+    return out
+
+
+def cycle_glue(off_cls, mem_cls, off_bbox, cls_ratio, search_size=255, search_feature_size=25):
+    """lib/models/models.py:262-274: returns (pool_box (n,4), best_score (n), best_idx (n) int32)."""
+    _need_float(off_cls, mem_cls, off_bbox)
+    _need_cuda(off_cls, mem_cls, off_bbox)
+    n, r = off_bbox.shape[0], off_bbox.shape[-1]
+    assert tuple(off_bbox.shape) == (n, 4, r, r) and off_cls.numel() == n * r * r == mem_cls.numel()
+    dev = off_cls.device
+    box = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    score = torch.empty((n,), dtype=torch.float32, device=dev)
+    idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().usot_cycle_glue(_lib.ptr(off_cls.contiguous()), _lib.ptr(mem_cls.contiguous()), _lib.ptr(off_bbox.contiguous()), n, r,
+                                               int(search_size), int(search_feature_size), float(cls_ratio), _lib.ptr(box), _lib.ptr(score),
+                                               _lib.ptr(idx), _stream(off_cls)))
+    return box, score, idx
+
+
+def weighted_bce(pred, label):
+    """_weighted_BCE (lib/models/models.py:49-58) -> 0-d tensor."""
+    _need_float(pred, label)
+    _need_cuda(pred, label)
+    out = torch.empty((1,), dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        _lib.check(_lib.load().usot_weighted_bce(_lib.ptr(pred.contiguous()), _lib.ptr(label.contiguous()), pred.numel(), _lib.ptr(out), _stream(pred)))
+    return out[0]
+
+
+def iou_loss(bbox_pred, reg_target, reg_weight):
+    """add_iouloss (lib/models/models.py:85-100): bbox_pred (n,4,R,R), reg_target (n,R,R,4), reg_weight (n,R,R) -> 0-d tensor."""
+    _need_float(bbox_pred, reg_target, reg_weight)
+    _need_cuda(bbox_pred, reg_target, reg_weight)
+    n, _, r, _ = bbox_pred.shape
+    out = torch.empty((1,), dtype=torch.float32, device=bbox_pred.device)
+    with torch.cuda.device(bbox_pred.device):
+        _lib.check(_lib.load().usot_iou_loss(_lib.ptr(bbox_pred.contiguous()), _lib.ptr(reg_target.contiguous()), _lib.ptr(reg_weight.contiguous()),
+                                             n, r * r, _lib.ptr(out), _stream(bbox_pred)))
+    return out[0]
