@@ -35,9 +35,15 @@ def test_export_import_roundtrip(tmp_path, precision):
     other = Engine("cuda:0", "fp16" if precision != "fp16" else "fp32")
     with pytest.raises(RuntimeError, match="precision"):
         other.import_packed(path)
-    with open(path, "r+b") as f:  # truncated image
-        f.truncate(n // 2)
-    with pytest.raises(RuntimeError, match="truncated"):
+    import numpy as np
+    raw = np.fromfile(path, dtype=np.uint8)
+    flipped = raw.copy()
+    flipped[n // 3] ^= 0x40  # one flipped bit in the payload (the image carries a checksum now)
+    flipped.tofile(path)
+    with pytest.raises(RuntimeError, match="corrupt"):
+        Engine("cuda:0", precision).import_packed(path)
+    raw[: n // 2].tofile(path)  # truncated image
+    with pytest.raises(RuntimeError, match="corrupt|truncated"):
         Engine("cuda:0", precision).import_packed(path)
 
 
