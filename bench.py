@@ -163,6 +163,9 @@ def workload_config(args):
     if args.config == 3:
         w = (f"USOT.track(x, template_mem, score_mem): batch={b} synthetic 255x255x3 search crops per GPU with a 7-entry memory queue per crop "
              "(full USOT* head: offline + memory branch, Conf_Fusion over N_q = 7) (BASELINE.json configs[2])")
+    elif args.config == 4 and getattr(args, "train_step", False):
+        w = (f"cycle-memory TRAINING STEP (scripts/train_usot.py:196-236): USOT.forward in train() mode + loss.backward() + gradient all-reduce + SGD, "
+             f"{b} samples per GPU, 3 memory frames (= {b} templates + {4 * b} search-size crops per GPU per step) (BASELINE.json configs[3])")
     elif args.config == 4:
         w = (f"USOT.forward(...): cycle-memory training forward, {b} samples per GPU, 3 memory frames (= {b} templates + {4 * b} search-size crops per "
              "GPU per step), template features all-gathered across ranks over NCCL (BASELINE.json configs[3])")
@@ -266,6 +269,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("USOT_B200_PRECISION", "fp16x3"), choices=["fp32", "fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-collective", action="store_true", help="N > 1: skip the cycle-forward all-gather record")
+    ap.add_argument("--train-step", action="store_true", help="config 4: time the whole training step (forward + backward + gradient all-reduce + SGD), train()-mode BN")
     ap.add_argument("--tunable", action="append", default=[], help="name=value performance knob (usot_set_tunable), repeatable; A/B runs only")
     args = ap.parse_args()
     if args.batch is None:
@@ -415,17 +419,26 @@ def main():
         crops_per_step = B * (1 + M)
         h2d_extra = smem_host.numel() * 4 + z.numel() * 4
         exchange = ZfExchange() if world > 1 else None
+        if args.train_step:   # a REAL training step: train()-mode BatchNorm, backward, bucketed gradient all-reduce, SGD update
+            from usot_b200.dist import GradientReducer
+            net.train()
+            reducer = GradientReducer(net.parameters(), bucket_mb=25.0)
+            optimizer = torch.optim.SGD(net.parameters(), lr=1e-6, momentum=0.9, weight_decay=1e-4)
     else:
         net.template(z.to(dev), tb.to(dev))
 
     def fwd(batch, ex):
-        return net.forward(batch["template"], batch["search"], label=batch["label"], reg_target=batch["reg_target"], reg_weight=batch["reg_weight"],
-                           template_bbox=batch["template_bbox"], search_memory=batch["search_memory"], search_bbox=batch["search_bbox"],
-                           cls_ratio=0.4, zf_exchange=ex)
+        with torch.no_grad():   # forward only: the engine's fused graph (with autograd enabled forward() builds the training graph instead)
+            return net.forward(batch["template"], batch["search"], label=batch["label"], reg_target=batch["reg_target"], reg_weight=batch["reg_weight"],
+                               template_bbox=batch["template_bbox"], search_memory=batch["search_memory"], search_bbox=batch["search_bbox"],
+                               cls_ratio=0.4, zf_exchange=ex)
 
     def run(x):
         if args.config == 4:
             tb_ = dict(train_batch, search=x)
+            if args.train_step:
+                from usot_b200.dist import train_step_sharded
+                return train_step_sharded(net, tb_, reducer, optimizer)
             return fwd(tb_, exchange)
         return net.track(x, mem, score)
 
@@ -501,7 +514,10 @@ def main():
     # ---- N > 1: the one collective of this path (z_f all-gather of the cycle-memory forward), on the same ranks ----
     collective = None
     if world > 1 and not args.no_collective:
-        collective = collective_record(args, dist, dev, rank, world, sd, timed)
+        if args.config == 4 and args.train_step:
+            collective = grad_allreduce_record(dist, net, reducer, dict(train_batch), timed, world)
+        else:
+            collective = collective_record(args, dist, dev, rank, world, sd, timed)
 
     line = None
     if rank == 0:
@@ -569,6 +585,38 @@ def main():
     finish(line)
 
 
+def grad_allreduce_record(dist, net, reducer, batch, timed, world):
+    """The collective that limits the 1 -> N TRAINING curve: the bucketed all-reduce of the fp32 gradients (replaces DataParallel's
+    reduce_add_coalesced, scripts/train_usot.py:318).  Step time with the all-reduce overlapped with backward vs the same step with the
+    all-reduce skipped (= its exposed time), and the all-reduce of all buckets alone (bus bandwidth, ring convention 2(N-1)/N)."""
+    from usot_b200.dist import train_step_sharded
+    steps = 5
+    for _ in range(2):
+        train_step_sharded(net, batch, reducer, None)
+    t_with, _, _ = timed(lambda: train_step_sharded(net, batch, reducer, None), steps)
+    reducer.world = 1                      # same step, no communication
+    for _ in range(2):
+        train_step_sharded(net, batch, reducer, None)
+    t_without, _, _ = timed(lambda: train_step_sharded(net, batch, reducer, None), steps)
+    reducer.world = world
+
+    def allreduce_all():
+        works = [dist.all_reduce(b["flat"], async_op=True) for b in reducer.buckets]
+        for w in works:
+            w.wait()
+
+    for _ in range(3):
+        allreduce_all()
+    t_ar, _, _ = timed(allreduce_all, 10)
+    t_ar /= 10
+    nbytes = reducer.bytes_per_step
+    return {"op": "bucketed all_reduce(mean) of the fp32 parameter gradients over NCCL, overlapped with backward (usot_b200.dist.GradientReducer)",
+            "nranks": world, "bytes_per_rank_per_step": nbytes, "buckets": len(reducer.buckets),
+            "ms_per_step_overlapped": t_with / steps, "ms_per_step_no_collective": t_without / steps,
+            "exposed_ms": (t_with - t_without) / steps, "allreduce_alone_ms": t_ar,
+            "allreduce_bus_gbs": 2.0 * (world - 1) / world * nbytes / (t_ar / 1e3) / 1e9}
+
+
 def collective_record(args, dist, dev, rank, world, sd, timed):
     """BASELINE config 4 on these ranks: cycle-memory forward, 16 samples + 3 memory frames per GPU.  Times the step (a) with the NCCL
     all-gather of z_f overlapped on a side stream (the product path, usot_b200.dist.ZfExchange), (b) with the same all-gather
@@ -601,9 +649,10 @@ def collective_record(args, dist, dev, rank, world, sd, timed):
             return lambda: self.gathered[self.rank * n:(self.rank + 1) * n]
 
     def fwd(ex):
-        return net.forward(batch["template"], batch["search"], label=batch["label"], reg_target=batch["reg_target"], reg_weight=batch["reg_weight"],
-                           template_bbox=batch["template_bbox"], search_memory=batch["search_memory"], search_bbox=batch["search_bbox"],
-                           cls_ratio=0.4, zf_exchange=ex)
+        with torch.no_grad():
+            return net.forward(batch["template"], batch["search"], label=batch["label"], reg_target=batch["reg_target"], reg_weight=batch["reg_weight"],
+                               template_bbox=batch["template_bbox"], search_memory=batch["search_memory"], search_bbox=batch["search_bbox"],
+                               cls_ratio=0.4, zf_exchange=ex)
 
     ov, se = ZfExchange(), SerialExchange()
     steps = 10

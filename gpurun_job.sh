@@ -1,13 +1,8 @@
 # Full validation job on one B200 (run as: gpurun --timeout 2400 -- 'bash gpurun_job.sh'); tools/gpurun_job_2gpu.sh is the 2-GPU one.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x --durations=15 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+timeout 600 python -m pytest tests/test_gpu_train_ops.py tests/test_gpu_train_backward.py -q -m gpu -s 2>&1 | grep -v Warning | tail -60 > gpurun_out/pytest_train.log
+timeout 1500 python -m pytest tests -q -m gpu --durations=10 --deselect tests/test_gpu_train_ops.py --deselect tests/test_gpu_train_backward.py 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
-timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
-timeout 300 python bench.py --config 3 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err
-timeout 300 python bench.py --config 3 --precision fp16 --no-cpu-baseline > gpurun_out/bench_c3_fp16.json 2> gpurun_out/bench_c3_fp16.err
-timeout 300 python bench.py --config 4 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err
-timeout 400 python bench.py --config 5 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
-timeout 300 python bench.py --impl cudnn --steps 5 > gpurun_out/bench_cudnn.json 2> gpurun_out/bench_cudnn.err
-timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-timeout 300 python tools/tracker_fps.py fp16x3 300 > gpurun_out/tracker_fps.json 2> gpurun_out/tracker_fps.err
-tail -25 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log; for f in bench bench_c3 bench_c3_fp16 bench_c4 bench_c5 bench_cudnn bench_reference; do echo "== $f"; cut -c1-400 gpurun_out/$f.json; tail -2 gpurun_out/$f.err; done; cat gpurun_out/tracker_fps.json
+timeout 400 python bench.py --config 4 --train-step --steps 5 > gpurun_out/bench_c4_train.json 2> gpurun_out/bench_c4_train.err
+timeout 400 python bench.py --config 4 --steps 5 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err
+tail -45 gpurun_out/pytest_train.log; tail -15 gpurun_out/pytest_gpu.log; tail -1 gpurun_out/smoke.log; for f in bench_c4_train bench_c4; do echo "== $f"; cut -c1-600 gpurun_out/$f.json; tail -3 gpurun_out/$f.err; done

@@ -24,6 +24,8 @@
  *   usot_conf_fusion                 <- Conf_Fusion.forward (reduction)  lib/models/connect.py:123-144
  *   usot_cycle_glue                  <- forward-track argmax + box maps  lib/models/models.py:131-162,262-274
  *   usot_weighted_bce / usot_iou_loss <- _weighted_BCE / add_iouloss    lib/models/models.py:42-100
+ *   usot_conv2d_wgrad_nhwc / usot_conv2d_dgrad_nhwc / usot_bn_* / usot_*_backward <- torch autograd of the same modules under
+ *                                       loss.backward()                 scripts/train_usot.py:229-236
  *   usot_pred_conv                   <- bbox_pred / cls_pred / cls_memory_pred + their epilogues   lib/models/connect.py:235-241,274-275
  *   usot_engine_template             <- USOT_.template                   lib/models/models.py:173-177
  *   usot_engine_track                <- USOT_.track                      lib/models/models.py:179-198
@@ -145,6 +147,11 @@ USOT_API int usot_maxpool3x3s2p1_nhwc(const float* in, int n, int h, int w, int 
 USOT_API int usot_stem_conv(const float* x, int n, int size, const float* host_weight_oihw, const float* host_scale, const float* host_shift,
                             float* out, int precision, void* stream);
 
+/* The bare stem convolution (7x7 / stride 2 / pad 0, 3 -> 64, no bias, no BN, no ReLU) in fp32 FMA arithmetic: the training path's conv1,
+ * which is followed by train-mode BatchNorm (usot_bn_*).  x (n,3,size,size) nchw; weight_kn (147, 64) DEVICE pointer with
+ * k = (c*7 + kh)*7 + kw (= weight.reshape(64, 147).T); out (n,HO,HO,64) nhwc. */
+USOT_API int usot_stem_conv_raw(const float* x, int n, int size, const float* weight_kn, float* out, void* stream);
+
 /* Conf_Fusion's reduction (lib/models/connect.py:123-144, after the two generator convs): conf / value (batch*nq, per_map) fp32
  * (any layout, elementwise); out[b] = sum_q exp(clamp(conf[b,q],-6,4)) * value[b,q] / sum_q exp(clamp(conf[b,q],-6,4)). */
 USOT_API int usot_conf_fusion(const float* conf, const float* value, int batch, int nq, int64_t per_map, float* out, void* stream);
@@ -159,6 +166,44 @@ USOT_API int usot_cycle_glue(const float* off_cls, const float* mem_cls, const f
 USOT_API int usot_weighted_bce(const float* pred, const float* label, int count, float* loss, void* stream);
 /* add_iouloss / _IOULoss (lib/models/models.py:60-100): bbox (n,4,R,R) nchw, reg_target (n,R,R,4), reg_weight (n,R,R); cells = R*R. */
 USOT_API int usot_iou_loss(const float* bbox, const float* reg_target, const float* reg_weight, int n, int cells, float* loss, void* stream);
+
+/* ------------------------------- training path ---------------------------------------- */
+/* The backward of USOT_.forward (scripts/train_usot.py:229-236 calls loss.backward(); the reference gets every gradient from torch
+ * autograd over cuDNN).  All maps nhwc fp32; weights in the (kh*kw*cin, cout) "kn" layout of usot_conv2d_nhwc. */
+
+/* autograd of nn.Conv2d w.r.t. its weight: grad_weight_kn (kh*kw*cin, cout) is overwritten.  Any stride / dilation / channel count. */
+USOT_API int usot_conv2d_wgrad_nhwc(const float* in, const float* grad_out, int n, int h, int w, int cin, int cout, int kh, int kw, int stride,
+                                    int pad_h, int pad_w, int dil_h, int dil_w, float* grad_weight_kn, void* stream);
+/* autograd of nn.Conv2d w.r.t. its input, generic gather form (the thin 256->1/4 prediction convs; wide layers run their dgrad on the
+ * forward conv kernels: usot_conv2d_nhwc with transposed / flipped filters).  grad_in (n,h,w,cin) is overwritten. */
+USOT_API int usot_conv2d_dgrad_nhwc(const float* grad_out, const float* weight_kn, int n, int h, int w, int cin, int cout, int kh, int kw,
+                                    int stride, int pad_h, int pad_w, int dil_h, int dil_w, float* grad_in, void* stream);
+/* nn.BatchNorm2d in train() mode over an (m, channels) map (m = N*H*W): batch mean and BIASED variance of x + bias (bias = the conv
+ * bias, may be NULL); then y = (x + bias - mean) / sqrt(var + eps) * gamma + beta (+ residual)(ReLU).  With running statistics passed
+ * as mean / var the same call is the eval() forward.  invstd_out (channels, optional) is what usot_bn_backward takes. */
+USOT_API int usot_bn_stats(const float* x, const float* bias, int64_t m, int channels, float* mean, float* var, void* stream);
+USOT_API int usot_bn_apply(const float* x, const float* bias, const float* mean, const float* var, float eps, const float* gamma, const float* beta,
+                           const float* residual, int relu, int64_t m, int channels, float* y, float* invstd_out, void* stream);
+/* Backward of usot_bn_apply.  grad_y is the gradient w.r.t. y; with relu != 0, y (the forward output) masks it first.  train != 0:
+ * batch-statistics backward; train == 0: mean / invstd are constants (running statistics).  grad_x doubles as the gradient of the
+ * conv bias' input; grad_gamma / grad_beta (channels); grad_residual (optional) receives the masked gradient for the shortcut. */
+USOT_API int usot_bn_backward(const float* grad_y, const float* y, const float* x, const float* bias, const float* mean, const float* invstd,
+                              const float* gamma, int train, int relu, int64_t m, int channels, float* grad_x, float* grad_gamma,
+                              float* grad_beta, float* grad_residual, void* stream);
+/* out[c] = sum over the m rows of x (m, channels): bias gradients. */
+USOT_API int usot_channel_sum(const float* x, int64_t m, int channels, float* out, void* stream);
+USOT_API int usot_maxpool3x3s2p1_backward_nhwc(const float* in, const float* grad_out, int n, int h, int w, int channels, float* grad_in,
+                                               void* stream);
+USOT_API int usot_conf_fusion_backward(const float* conf, const float* value, const float* grad_out, int batch, int nq, int64_t per_map,
+                                       float* grad_conf, float* grad_value, void* stream);
+/* GroupDW's weighted sum (lib/models/connect.py:96-102): out = w3[0]*x0 + w3[1]*x1 + w3[2]*x2 (w3 on the device) and its backward. */
+USOT_API int usot_weighted_sum3(const float* x0, const float* x1, const float* x2, const float* w3, int64_t numel, float* out, void* stream);
+USOT_API int usot_weighted_sum3_backward(const float* x0, const float* x1, const float* x2, const float* w3, const float* grad_out, int64_t numel,
+                                         float* grad_x0, float* grad_x1, float* grad_x2, float* grad_w3, void* stream);
+/* Backward of usot_weighted_bce / usot_iou_loss; grad_loss[1] on the device. */
+USOT_API int usot_weighted_bce_backward(const float* pred, const float* label, int count, const float* grad_loss, float* grad_pred, void* stream);
+USOT_API int usot_iou_loss_backward(const float* bbox, const float* reg_target, const float* reg_weight, int n, int cells, const float* grad_loss,
+                                    float* grad_bbox, void* stream);
 
 USOT_API int usot_nchw_to_nhwc(const float* in, int n, int c, int h, int w, float* out, void* stream);
 USOT_API int usot_nhwc_to_nchw(const float* in, int n, int h, int w, int c, float* out, void* stream);

@@ -77,6 +77,39 @@ def grad_summary(named_grads):
     return out
 
 
+def grad_samples64(named_grads):
+    """64 strided samples per tensor (all of it when smaller) + its L2 norm: enough for a sample-based relative-L2 error."""
+    out = {}
+    for k, g in named_grads.items():
+        flat = g.detach().double().flatten()
+        step = max(1, flat.numel() // 64)
+        out["n:" + k] = np.array([float(flat.norm())])
+        out["s:" + k] = flat[::step][:64].numpy()
+    return out
+
+
+def oracle_grads_fp64(sd, train_bn):
+    """The same algorithm in float64 (PrRoIPool stays float32 numpy, cast around): the 'exact arithmetic' gradients.  The distance between
+    these and the float32 reference gradients is the reference's OWN rounding noise -- the floor any float32-class implementation can be
+    held to on this (deliberately ill-conditioned, random-weight) network."""
+    pp = O.prpool_feature
+    O.prpool_feature = lambda f, b: pp(f.float(), b).to(f.dtype)
+    try:
+        params = {k: (v.double() if v.dtype.is_floating_point else v).clone().requires_grad_(
+            v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var"))) for k, v in sd.items()}
+        ins = [t.double() for t in inputs()]
+        z, x, tb, sb, smem, label, reg_target, reg_weight = ins
+        O._CAL.on = train_bn
+        try:
+            losses = O.forward_train(params, z, x, label, reg_target, reg_weight, tb, smem, sb, 0.4)
+        finally:
+            O._CAL.on = False
+        (losses[0] + losses[1] + losses[2]).backward()
+        return [float(v.detach()) for v in losses], {k: v.grad for k, v in params.items() if v.requires_grad and v.grad is not None}
+    finally:
+        O.prpool_feature = pp
+
+
 def oracle_grads(sd, train_bn):
     params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var")))
               for k, v in sd.items()}
@@ -126,6 +159,21 @@ def main():
         out[f"{mode}/losses"] = np.array(rl, np.float64)
     np.savez_compressed(os.path.join(GOLD, "grads_damp025.npz"), **out)
     print("wrote tests/golden/grads_damp025.npz")
+    # second fixture: 64 samples per tensor of (a) the float32 reference gradients and (b) the float64 'exact' gradients
+    out64 = {"B": B, "M": M}
+    for mode, train_bn in (("eval", False), ("train", True)):
+        _, rg = reference_grads(sd, train_bn)
+        l64, g64 = oracle_grads_fp64(sd, train_bn)
+        assert set(rg) == set(g64)
+        out64.update({f"{mode}/ref32/{k}": v for k, v in grad_samples64(rg).items()})
+        out64.update({f"{mode}/exact/{k}": v for k, v in grad_samples64(g64).items()})
+        out64[f"{mode}/exact_losses"] = np.array(l64)
+        num = sum(float(((rg[k].double() - g64[k]) ** 2).sum()) for k in rg)
+        den = sum(float((g64[k] ** 2).sum()) for k in rg)
+        out64[f"{mode}/ref32_vs_exact_global_rel_l2"] = np.array([np.sqrt(num / den)])
+        print(f"{mode}: float32 reference vs float64 arithmetic: global relative L2 of the gradient = {np.sqrt(num / den):.3e}")
+    np.savez_compressed(os.path.join(GOLD, "grads64_damp025.npz"), **out64)
+    print("wrote tests/golden/grads64_damp025.npz")
 
 
 if __name__ == "__main__":

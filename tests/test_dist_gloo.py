@@ -64,3 +64,47 @@ def test_world2_gloo_allgather_and_loss_average():
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, 16), nprocs=2, join=True)
+
+
+# ---- gradient all-reduce (replaces DataParallel's reduce_add_coalesced, scripts/train_usot.py:318) ------------------------------
+def _grad_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from usot_b200.dist import GradientReducer
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64), torch.nn.ReLU(), torch.nn.Linear(64, 3))
+        net[2].bias.requires_grad_(False)                                   # a frozen parameter must simply be skipped
+        red = GradientReducer(net.parameters(), bucket_mb=0.01)             # ~2.6k floats per bucket -> several buckets
+        assert len(red.buckets) >= 3
+        g = torch.Generator().manual_seed(1)
+        x_all, y_all = torch.randn(8, 16, generator=g), torch.randn(8, 3, generator=g)
+        lo, hi = rank * 4, rank * 4 + 4
+        for step in range(2):                                               # second step: buckets are re-zeroed, views survive
+            red.zero_grad()
+            loss = ((net(x_all[lo:hi]) - y_all[lo:hi]) ** 2).mean()
+            loss.backward()
+            assert red.launch_order[0] == 0 and sorted(red.launch_order) == list(range(len(red.buckets)))   # heads-first, every bucket once
+            red.finish()
+            # reference: mean over ranks of the per-rank gradients == gradient of the mean of the per-rank losses
+            ref_net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64), torch.nn.ReLU(), torch.nn.Linear(64, 3))
+            ref_net.load_state_dict(net.state_dict())
+            full = sum(((ref_net(x_all[r * 4:r * 4 + 4]) - y_all[r * 4:r * 4 + 4]) ** 2).mean() for r in range(world)) / world
+            full.backward()
+            for (k, p), (_, q) in zip(net.named_parameters(), ref_net.named_parameters()):
+                if not p.requires_grad:
+                    assert p.grad is None
+                    continue
+                assert torch.allclose(p.grad, q.grad, atol=1e-6), k
+                assert p.grad.data_ptr() >= red.buckets[red._of[p]]["flat"].data_ptr()   # still a view into its bucket
+        red.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_bucketed_gradient_allreduce():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_grad_worker, args=(2, port), nprocs=2, join=True)

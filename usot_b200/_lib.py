@@ -44,10 +44,23 @@ SIGNATURES = {
                                      ctypes.c_double, ctypes.c_double, _I, _P, _P, _P]),
     "usot_maxpool3x3s2p1_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "usot_stem_conv": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "usot_stem_conv_raw": (_I, [_P, _I, _I, _P, _P, _P]),
     "usot_conf_fusion": (_I, [_P, _P, _I, _I, _I64, _P, _P]),
     "usot_cycle_glue": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
     "usot_weighted_bce": (_I, [_P, _P, _I, _P, _P]),
     "usot_iou_loss": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "usot_conv2d_wgrad_nhwc": (_I, [_P, _P] + [_I] * 12 + [_P, _P]),
+    "usot_conv2d_dgrad_nhwc": (_I, [_P, _P] + [_I] * 12 + [_P, _P]),
+    "usot_bn_stats": (_I, [_P, _P, _I64, _I, _P, _P, _P]),
+    "usot_bn_apply": (_I, [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I64, _I, _P, _P, _P]),
+    "usot_bn_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I64, _I, _P, _P, _P, _P, _P]),
+    "usot_channel_sum": (_I, [_P, _I64, _I, _P, _P]),
+    "usot_maxpool3x3s2p1_backward_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "usot_conf_fusion_backward": (_I, [_P, _P, _P, _I, _I, _I64, _P, _P, _P]),
+    "usot_weighted_sum3": (_I, [_P, _P, _P, _P, _I64, _P, _P]),
+    "usot_weighted_sum3_backward": (_I, [_P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "usot_weighted_bce_backward": (_I, [_P, _P, _I, _P, _P, _P]),
+    "usot_iou_loss_backward": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "usot_crop_resize": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "usot_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "usot_nhwc_to_nchw": (_I, [_P, _I, _I, _I, _I, _P, _P]),

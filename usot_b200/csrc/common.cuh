@@ -13,6 +13,9 @@ typedef std::atomic<int> Tunable;
 
 // ---- error plumbing: kernels never exit(); launchers return cudaError_t-like ints ----------
 void set_error(const std::string& msg);
+// per-family launch accounting (engine.cu; usot_profile_read): families 8 = conv_wgrad, 9 = train_other, 7 = other, 2 = maxpool, 1 = stem
+void count_op_launch(int family, int n);
+enum { OPFAM_STEM = 1, OPFAM_POOL = 2, OPFAM_FUSION = 5, OPFAM_OTHER = 7, OPFAM_WGRAD = 8, OPFAM_TRAIN = 9 };
 #define USOT_CUDA_OK(expr)                                                                      \
     do {                                                                                        \
         cudaError_t _e = (expr);                                                                \
@@ -58,6 +61,20 @@ inline int device_sm_count() {
     return cached[dev];
 }
 
+// Scratch buffers of the stand-alone / training ops come from the stream-ordered allocator (cudaMallocAsync: no host sync).  Keep freed
+// blocks cached in the device's default pool instead of returning them to the driver at every synchronisation point.
+inline void ensure_async_pool() {
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done[dev] = true;
+}
+
 // ---- activation storage ------------------------------------------------------------------
 // All internal activations are NHWC.  Two storage formats:
 //   F32   : one fp32 plane (SIMT path, bandwidth kernels)
@@ -89,7 +106,7 @@ struct Epilogue {
 
 // ---- launchers (kernels_simt.cu) -----------------------------------------------------------
 int launch_stem(const float* x_nchw, int n, int s, const float* w_packed /*[147][64]*/, const float* scale,
-                const float* shift, float* out_nhwc /*[n][ho][ho][64]*/, cudaStream_t st);
+                const float* shift, float* out_nhwc /*[n][ho][ho][64]*/, cudaStream_t st, int relu = 1);  // scale / shift may be null (1 / 0)
 // tensor-core stem (stem_tc.cu): w_img = packed shared-memory image of the weight tile, see pack_stem_tc_host
 int launch_stem_tc(const float* x_nchw, int n, int s, const void* w_img, const float* scale_tc, const float* shift, float* out_nhwc,
                    bool split, cudaStream_t st);

@@ -767,6 +767,41 @@ int launch_split_to_f32(const __half* hi, const __half* lo, size_t n, float* out
     return 0;
 }
 
+// Device-side twin of pack_tc_weights_host (bit-identical results): one block per output channel.  Used where the weights change
+// between calls (training, stand-alone op): w_kn [K][cout] fp32 -> [cout][K] fp16 hi / lo planes of w * 2^e[co], scale_out = scale_in * 2^-e.
+__global__ void __launch_bounds__(256) pack_tc_weights_kernel(const float* __restrict__ w_kn, int K, int cout, const float* __restrict__ scale_in,
+                                                              __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ scale_out) {
+    __shared__ float red[8];
+    const int co = blockIdx.x;
+    float mx = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, fabsf(__ldg(w_kn + (size_t)k * cout + co)));
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    int e = 0;
+    if (mx > 0.f && isfinite(mx)) {
+        int ex;
+        frexpf(mx, &ex);
+        e = 8 - ex;
+    }
+    const float s = ldexpf(1.0f, e);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float v = __ldg(w_kn + (size_t)k * cout + co) * s;
+        const __half h = __float2half_rn(v);
+        hi[(size_t)co * K + k] = h;
+        if (lo) lo[(size_t)co * K + k] = __float2half_rn(v - __half2float(h));
+    }
+    if (threadIdx.x == 0) scale_out[co] = __ldg(scale_in + co) * ldexpf(1.0f, -e);
+}
+
+int launch_pack_tc_weights(const float* w_kn, int K, int cout, const float* scale_in, __half* hi, __half* lo, float* scale_out, cudaStream_t st) {
+    pack_tc_weights_kernel<<<cout, 256, 0, st>>>(w_kn, K, cout, scale_in, hi, lo, scale_out);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // w_kn: [K][cout] fp32 (k = tap*cin + c).  Produces [cout][K] fp16 hi/lo planes of w * 2^e[co] and scale_out = scale_in * 2^-e.
 void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,
                           std::vector<float>& scale_out) {

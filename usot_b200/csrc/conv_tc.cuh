@@ -63,6 +63,8 @@ extern Tunable g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_t
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st);
 int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
 int launch_split_to_f32(const __half* hi, const __half* lo /*or null*/, size_t n, float* out, cudaStream_t st);  // out = hi + lo
+int launch_pack_tc_weights(const float* w_kn, int K, int cout, const float* scale_in, __half* hi, __half* lo /*or null*/, float* scale_out,
+                           cudaStream_t st);  // device-side twin of pack_tc_weights_host
 void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,
                           std::vector<float>& scale_out);
 

@@ -27,8 +27,10 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 
 // ---- optional per-kernel-family profiling (CUDA events on the launching stream) + launch counting ----
-enum { FAM_CONV = 0, FAM_STEM, FAM_POOL, FAM_XCORR, FAM_PRED, FAM_FUSION, FAM_PRROI, FAM_OTHER, FAM_COUNT };
-static const char* kFamNames[FAM_COUNT] = {"conv", "stem", "maxpool", "groupdw_xcorr", "pred_conv", "conf_fusion", "prroi_pool", "other"};
+enum { FAM_CONV = 0, FAM_STEM, FAM_POOL, FAM_XCORR, FAM_PRED, FAM_FUSION, FAM_PRROI, FAM_OTHER, FAM_WGRAD, FAM_TRAIN, FAM_COUNT };
+static const char* kFamNames[FAM_COUNT] = {"conv", "stem", "maxpool", "groupdw_xcorr", "pred_conv", "conf_fusion", "prroi_pool", "other",
+                                           "conv_wgrad", "train_other"};
+static_assert(FAM_COUNT <= 16, "launch-count arrays hold 16 families");
 struct Profiler {
     bool on = false;
     long long launches[FAM_COUNT] = {0};
@@ -37,12 +39,14 @@ struct Profiler {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev;
 };
 static Profiler g_prof;
-static thread_local long long tl_launches[8] = {0};  // this host thread's launches (graph capture takes its per-family counts from here)
+static thread_local long long tl_launches[16] = {0};  // this host thread's launches (graph capture takes its per-family counts from here)
 static std::mutex g_prof_mu;  // launches of several engines (DataParallel-style host threads) update the counters concurrently
 static void count_launches(int fam, long long n) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.launches[fam] += n;
 }
+// launch accounting for the operators that live in other translation units (ops_abi.cu, train_kernels.cu)
+void count_op_launch(int family, int n) { if (family >= 0 && family < FAM_COUNT) count_launches(family, n); }
 static Tunable g_stem_tc{1};  // tunable "stem_tc": 1 = tensor-core stem in the tcgen05 precision modes, 0 = CUDA-core stem
 struct Scope {
     int fam; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
@@ -188,7 +192,7 @@ struct usot_engine {
     float *adjust = nullptr, *bias4 = nullptr;
     Arena arena;
     // CUDA-graph cache of track() for small batches: key = (n, size, nz, nq); valid while the arena has not moved
-    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0, weights_gen = 0; int seen = 0; long long launches[8] = {0}; };
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t arena_gen = 0, weights_gen = 0; int seen = 0; long long launches[16] = {0}; };
     std::map<std::tuple<int, int, int, int>, GraphEntry> graphs;
     uint64_t arena_gen = 0;
     uint64_t weights_gen = 0;         // bumped by every (re)pack: captured graphs hold weight pointers and weight tensor maps
@@ -832,47 +836,54 @@ int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float*
                conv_out(w, kw, stride, pad_w, dil_w)};
     USOT_REQUIRE(g.ho > 0 && g.wo > 0, "conv output is empty");
     cudaStream_t st = (cudaStream_t)stream;
+    Scope sc(FAM_CONV, st, 2.0 * n * g.ho * g.wo * (double)cout * kh * kw * cin);   // (the training path runs every dense conv through this entry)
     if (precision == USOT_PREC_FP32_SIMT) {
         Epilogue ep{scale, shift, residual, relu};
         return launch_conv_simt(in, g, weight_kn, ep, out, st);
     }
-    // Tensor-core path of the stand-alone op (test/debug entry: packs the weights on the host and synchronises).
+    // Tensor-core path of the stand-alone op: weights are split / packed ON THE DEVICE and the scratch planes come from the stream-ordered
+    // allocator, so the call enqueues without any host synchronisation (the training path issues one such call per layer and step).
     const bool split = precision == USOT_PREC_FP16X3_TC;
     const int K = kh * kw * cin;
     const size_t n_in = (size_t)n * h * w * cin, n_out = (size_t)n * g.ho * g.wo * cout;
-    std::vector<float> hw((size_t)K * cout), hs(cout), scale_tc;
-    USOT_CUDA_OK(cudaMemcpyAsync(hw.data(), weight_kn, hw.size() * 4, cudaMemcpyDeviceToHost, st));
-    USOT_CUDA_OK(cudaMemcpyAsync(hs.data(), scale, cout * 4, cudaMemcpyDeviceToHost, st));
-    USOT_CUDA_OK(cudaStreamSynchronize(st));
-    std::vector<__half> whi, wlo;
-    pack_tc_weights_host(hw.data(), K, cout, hs.data(), whi, wlo, scale_tc);
-    __half *d_whi = nullptr, *d_wlo = nullptr, *d_ihi = nullptr, *d_ilo = nullptr, *d_rhi = nullptr, *d_rlo = nullptr, *d_ohi = nullptr, *d_olo = nullptr;
-    float* d_scale = nullptr;
+    const size_t n_w = (size_t)K * cout;
+    const bool dbg_split_out = getenv("USOT_DEBUG_SPLIT_OUT") != nullptr;  // profiling aid: exercise the split-fp16 output path as the engine does
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t planes = split ? 2 : 1;
+    size_t bytes = planes * al(n_w * 2) + al((size_t)cout * 4) + planes * al(n_in * 2) + (residual ? planes * al(n_out * 2) : 0) +
+                   (dbg_split_out ? 2 * al(n_out * 2) : 0);
+    ensure_async_pool();
+    char* ws = nullptr;
+    USOT_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, st));
+    char* cur = ws;
+    auto take = [&](size_t b) { char* p = cur; cur += al(b); return p; };
+    __half* d_whi = reinterpret_cast<__half*>(take(n_w * 2));
+    __half* d_wlo = split ? reinterpret_cast<__half*>(take(n_w * 2)) : nullptr;
+    float* d_scale = reinterpret_cast<float*>(take((size_t)cout * 4));
+    __half* d_ihi = reinterpret_cast<__half*>(take(n_in * 2));
+    __half* d_ilo = split ? reinterpret_cast<__half*>(take(n_in * 2)) : nullptr;
+    __half *d_rhi = nullptr, *d_rlo = nullptr, *d_ohi = nullptr, *d_olo = nullptr;
     int rc = 0;
-    auto fail = [&](int code) { rc = code; };
     do {
-        if (cudaMalloc(&d_whi, whi.size() * 2) || cudaMalloc(&d_wlo, wlo.size() * 2) || cudaMalloc(&d_scale, cout * 4) ||
-            cudaMalloc(&d_ihi, n_in * 2) || cudaMalloc(&d_ilo, n_in * 2)) { set_error("usot_conv2d_nhwc: cudaMalloc failed"); fail(1); break; }
-        cudaMemcpyAsync(d_whi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_wlo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_scale, scale_tc.data(), cout * 4, cudaMemcpyHostToDevice, st);
+        if ((rc = launch_pack_tc_weights(weight_kn, K, cout, scale, d_whi, d_wlo, d_scale, st))) break;
         if ((rc = launch_f32_to_split(in, n_in, d_ihi, d_ilo, st))) break;
         if (residual) {
-            if (cudaMalloc(&d_rhi, n_out * 2) || cudaMalloc(&d_rlo, n_out * 2)) { set_error("usot_conv2d_nhwc: cudaMalloc failed"); fail(1); break; }
+            d_rhi = reinterpret_cast<__half*>(take(n_out * 2));
+            d_rlo = split ? reinterpret_cast<__half*>(take(n_out * 2)) : nullptr;
             if ((rc = launch_f32_to_split(residual, n_out, d_rhi, d_rlo, st))) break;
         }
-        TcTensor ti{d_ihi, split ? d_ilo : nullptr};
-        TcWeights tw{d_whi, split ? d_wlo : nullptr, d_scale, K};
+        TcTensor ti{d_ihi, d_ilo};
+        TcWeights tw{d_whi, d_wlo, d_scale, K};
         TcEpilogue ep{shift, d_rhi, d_rlo, nullptr, nullptr, out, relu};
-        if (const char* dbg = getenv("USOT_DEBUG_SPLIT_OUT")) {  // profiling aid: exercise the split-fp16 output path as the engine does
-            if (cudaMalloc(&d_ohi, n_out * 2) || cudaMalloc(&d_olo, n_out * 2)) { set_error("usot_conv2d_nhwc: cudaMalloc failed"); fail(1); break; }
-            ep.out_hi = d_ohi; ep.out_lo = d_olo;
-            if (dbg[0] == '2') ep.out_f32 = nullptr;  // split output only
+        if (dbg_split_out) {
+            d_ohi = reinterpret_cast<__half*>(take(n_out * 2));
+            d_olo = reinterpret_cast<__half*>(take(n_out * 2));
+            ep.out_hi = d_ohi; ep.out_lo = split ? d_olo : nullptr;
+            if (getenv("USOT_DEBUG_SPLIT_OUT")[0] == '2') ep.out_f32 = nullptr;  // split output only
         }
-        if ((rc = launch_conv_tc(ti, g, tw, ep, split, st))) break;
-        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("usot_conv2d_nhwc: ") + cudaGetErrorString(cudaGetLastError())); fail(1); }
+        rc = launch_conv_tc(ti, g, tw, ep, split, st);
     } while (0);
-    cudaFree(d_whi); cudaFree(d_wlo); cudaFree(d_scale); cudaFree(d_ihi); cudaFree(d_ilo); cudaFree(d_rhi); cudaFree(d_rlo); cudaFree(d_ohi); cudaFree(d_olo);
+    cudaFreeAsync(ws, st);
     return rc;
 }
 

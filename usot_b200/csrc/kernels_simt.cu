@@ -27,7 +27,7 @@ constexpr int STEM_P = STEM_T * 2 + 5;  // 37 input rows/cols per tile
 
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int S, int HO, const float* __restrict__ wk,
                                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                                   float* __restrict__ out) {
+                                                   float* __restrict__ out, int relu) {
     extern __shared__ float smem[];
     float* ws = smem;                   // [147][64]
     float* ps = smem + 147 * 64;        // [3][37][37]
@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     if (oy >= HO) return;
     float sc[16], sh[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { sc[j] = __ldg(scale + cg * 16 + j); sh[j] = __ldg(shift + cg * 16 + j); }
+    for (int j = 0; j < 16; ++j) { sc[j] = scale ? __ldg(scale + cg * 16 + j) : 1.f; sh[j] = shift ? __ldg(shift + cg * 16 + j) : 0.f; }
+    const float lo = relu ? 0.f : -FLT_MAX;  // (raw conv output for the training path: no ReLU, identity affine)
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         int ox = tx0 + colq * 4 + p;
@@ -83,23 +84,23 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float4 v;
-            v.x = fmaxf(fmaf(acc[p][4 * j], sc[4 * j], sh[4 * j]), 0.f);
-            v.y = fmaxf(fmaf(acc[p][4 * j + 1], sc[4 * j + 1], sh[4 * j + 1]), 0.f);
-            v.z = fmaxf(fmaf(acc[p][4 * j + 2], sc[4 * j + 2], sh[4 * j + 2]), 0.f);
-            v.w = fmaxf(fmaf(acc[p][4 * j + 3], sc[4 * j + 3], sh[4 * j + 3]), 0.f);
+            v.x = fmaxf(fmaf(acc[p][4 * j], sc[4 * j], sh[4 * j]), lo);
+            v.y = fmaxf(fmaf(acc[p][4 * j + 1], sc[4 * j + 1], sh[4 * j + 1]), lo);
+            v.z = fmaxf(fmaf(acc[p][4 * j + 2], sc[4 * j + 2], sh[4 * j + 2]), lo);
+            v.w = fmaxf(fmaf(acc[p][4 * j + 3], sc[4 * j + 3], sh[4 * j + 3]), lo);
             o[j] = v;
         }
     }
 }
 
 int launch_stem(const float* x, int n, int s, const float* wk, const float* scale, const float* shift, float* out,
-                cudaStream_t st) {
+                cudaStream_t st, int relu) {
     const int ho = (s - 7) / 2 + 1;
     const size_t smem = (147 * 64 + 3 * STEM_P * STEM_P) * sizeof(float);
     static SmemAttrCache attr;
     if (int rc = attr.ensure(stem_kernel, (int)smem)) return rc;
     dim3 grid((ho + STEM_T - 1) / STEM_T, (ho + STEM_T - 1) / STEM_T, n);
-    stem_kernel<<<grid, 256, smem, st>>>(x, s, ho, wk, scale, shift, out);
+    stem_kernel<<<grid, 256, smem, st>>>(x, s, ho, wk, scale, shift, out, relu);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -15,6 +15,7 @@ int usot_maxpool3x3s2p1_nhwc(const float* in, int n, int h, int w, int channels,
     USOT_REQUIRE(n >= 0 && h > 0 && w > 0 && channels > 0 && channels % 4 == 0, "bad shape");
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    count_op_launch(OPFAM_POOL, 1);
     if (out)
         if (int rc = launch_maxpool3x3s2p1(in, n, h, w, channels, out, nullptr, nullptr, st)) return rc;
     if (out_split_sum) {
@@ -69,9 +70,18 @@ int usot_stem_conv(const float* x, int n, int size, const float* host_weight_oih
     return rc;
 }
 
+int usot_stem_conv_raw(const float* x, int n, int size, const float* weight_kn, float* out, void* stream) {
+    USOT_REQUIRE(n == 0 || (x && weight_kn && out), "null pointer");
+    USOT_REQUIRE(n >= 0 && size >= 7, "bad shape");
+    if (n == 0) return 0;
+    count_op_launch(OPFAM_STEM, 1);
+    return launch_stem(x, n, size, weight_kn, nullptr, nullptr, out, (cudaStream_t)stream, /*relu=*/0);
+}
+
 int usot_conf_fusion(const float* conf, const float* value, int batch, int nq, int64_t per_map, float* out, void* stream) {
     USOT_REQUIRE(batch == 0 || (conf && value && out), "null pointer");
     USOT_REQUIRE(batch >= 0 && nq > 0 && per_map > 0 && per_map % 4 == 0, "bad shape");
+    count_op_launch(OPFAM_FUSION, 1);
     return launch_conf_fusion(conf, value, batch, nq, (size_t)per_map, out, (cudaStream_t)stream);
 }
 

@@ -227,6 +227,7 @@ static int chan_reduce(RedArgs a, float* out0, float* out1, cudaStream_t st) {
     a.slab = (a.M + slabs - 1) / slabs;
     slabs = (a.M + a.slab - 1) / a.slab;
     double* part = nullptr;
+    ensure_async_pool();
     USOT_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)slabs * 2 * a.C * sizeof(double), st));
     chan_reduce_kernel<<<dim3(groups, slabs), 256, 0, st>>>(a, part);
     chan_finalize_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(part, slabs, a.C, a.M, a.mode, out0, out1);
@@ -478,6 +479,7 @@ int usot_conv2d_wgrad_nhwc(const float* in, const float* grad_out, int n, int h,
     USOT_REQUIRE(grad_weight_kn && (n == 0 || (in && grad_out)), "null pointer");
     ConvGeom g;
     if (int rc = make_geom(&g, n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w)) return rc;
+    count_op_launch(OPFAM_WGRAD, 1);
     return launch_conv_wgrad(in, grad_out, g, grad_weight_kn, (cudaStream_t)stream);
 }
 
@@ -486,11 +488,13 @@ int usot_conv2d_dgrad_nhwc(const float* grad_out, const float* weight_kn, int n,
     USOT_REQUIRE(n == 0 || (grad_out && weight_kn && grad_in), "null pointer");
     ConvGeom g;
     if (int rc = make_geom(&g, n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w)) return rc;
+    count_op_launch(OPFAM_TRAIN, 1);
     return launch_conv_dgrad_gather(grad_out, weight_kn, g, grad_in, (cudaStream_t)stream);
 }
 
 int usot_bn_stats(const float* x, const float* bias, int64_t m, int channels, float* mean, float* var, void* stream) {
     USOT_REQUIRE(x && mean && var && m > 0 && m < (1ll << 31) && channels > 0, "bad argument");
+    count_op_launch(OPFAM_TRAIN, 2);
     RedArgs a{x, bias, nullptr, nullptr, nullptr, nullptr, (int)m, channels, 0, 0, 0};
     return chan_reduce(a, mean, var, (cudaStream_t)stream);
 }
@@ -498,6 +502,7 @@ int usot_bn_stats(const float* x, const float* bias, int64_t m, int channels, fl
 int usot_bn_apply(const float* x, const float* bias, const float* mean, const float* var, float eps, const float* gamma, const float* beta,
                   const float* residual, int relu, int64_t m, int channels, float* y, float* invstd_out, void* stream) {
     USOT_REQUIRE(x && mean && var && gamma && beta && y && m > 0 && channels > 0 && channels % 4 == 0, "bad argument");
+    count_op_launch(OPFAM_TRAIN, 1);
     const size_t total4 = (size_t)m * channels / 4;
     bn_apply_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(x), bias, mean, var, eps, gamma, beta, reinterpret_cast<const float4*>(residual), relu, total4, channels / 4,
@@ -510,6 +515,7 @@ int usot_bn_backward(const float* grad_y, const float* y, const float* x, const 
                      const float* gamma, int train, int relu, int64_t m, int channels, float* grad_x, float* grad_gamma, float* grad_beta,
                      float* grad_residual, void* stream) {
     USOT_REQUIRE(grad_y && x && mean && invstd && gamma && grad_x && grad_gamma && grad_beta && (!relu || y), "null pointer");
+    count_op_launch(OPFAM_TRAIN, 3);
     USOT_REQUIRE(m > 0 && m < (1ll << 31) && channels > 0 && channels % 4 == 0, "bad shape");
     cudaStream_t st = (cudaStream_t)stream;
     RedArgs a{x, bias, grad_y, y, mean, invstd, (int)m, channels, 1, relu, 0};
@@ -525,12 +531,14 @@ int usot_bn_backward(const float* grad_y, const float* y, const float* x, const 
 
 int usot_channel_sum(const float* x, int64_t m, int channels, float* out, void* stream) {
     USOT_REQUIRE(x && out && m > 0 && m < (1ll << 31) && channels > 0, "bad argument");
+    count_op_launch(OPFAM_TRAIN, 2);
     RedArgs a{x, nullptr, nullptr, nullptr, nullptr, nullptr, (int)m, channels, 2, 0, 0};
     return chan_reduce(a, out, nullptr, (cudaStream_t)stream);
 }
 
 int usot_maxpool3x3s2p1_backward_nhwc(const float* in, const float* grad_out, int n, int h, int w, int channels, float* grad_in, void* stream) {
     USOT_REQUIRE(n == 0 || (in && grad_out && grad_in), "null pointer");
+    count_op_launch(OPFAM_TRAIN, 1);
     USOT_REQUIRE(n >= 0 && h > 0 && w > 0 && channels > 0, "bad shape");
     const size_t total = (size_t)n * h * w * channels;
     if (total == 0) return 0;
@@ -543,6 +551,7 @@ int usot_maxpool3x3s2p1_backward_nhwc(const float* in, const float* grad_out, in
 int usot_conf_fusion_backward(const float* conf, const float* value, const float* grad_out, int batch, int nq, int64_t per_map, float* grad_conf,
                               float* grad_value, void* stream) {
     USOT_REQUIRE(batch == 0 || (conf && value && grad_out && grad_conf && grad_value), "null pointer");
+    count_op_launch(OPFAM_TRAIN, 1);
     USOT_REQUIRE(batch >= 0 && nq > 0 && per_map > 0, "bad shape");
     const size_t total = (size_t)batch * per_map;
     if (total == 0) return 0;
@@ -554,6 +563,7 @@ int usot_conf_fusion_backward(const float* conf, const float* value, const float
 
 int usot_weighted_sum3(const float* x0, const float* x1, const float* x2, const float* w3, int64_t numel, float* out, void* stream) {
     USOT_REQUIRE(x0 && x1 && x2 && w3 && out && numel > 0, "bad argument");
+    count_op_launch(OPFAM_TRAIN, 1);
     wsum3_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x0, x1, x2, w3, (size_t)numel, out);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
@@ -562,8 +572,10 @@ int usot_weighted_sum3(const float* x0, const float* x1, const float* x2, const 
 int usot_weighted_sum3_backward(const float* x0, const float* x1, const float* x2, const float* w3, const float* grad_out, int64_t numel,
                                 float* grad_x0, float* grad_x1, float* grad_x2, float* grad_w3, void* stream) {
     USOT_REQUIRE(x0 && x1 && x2 && w3 && grad_out && grad_x0 && grad_x1 && grad_x2 && grad_w3 && numel > 0, "bad argument");
+    count_op_launch(OPFAM_TRAIN, 2);
     cudaStream_t st = (cudaStream_t)stream;
     double* acc = nullptr;
+    ensure_async_pool();
     USOT_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&acc), 3 * sizeof(double), st));
     USOT_CUDA_OK(cudaMemsetAsync(acc, 0, 3 * sizeof(double), st));
     const unsigned blocks = (unsigned)std::min<int64_t>((numel + 255) / 256, (int64_t)device_sm_count() * 8);
@@ -576,6 +588,7 @@ int usot_weighted_sum3_backward(const float* x0, const float* x1, const float* x
 
 int usot_weighted_bce_backward(const float* pred, const float* label, int count, const float* grad_loss, float* grad_pred, void* stream) {
     USOT_REQUIRE(pred && label && grad_loss && grad_pred && count > 0, "bad argument");
+    count_op_launch(OPFAM_TRAIN, 1);
     bce_backward_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, label, count, grad_loss, grad_pred);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
@@ -584,6 +597,7 @@ int usot_weighted_bce_backward(const float* pred, const float* label, int count,
 int usot_iou_loss_backward(const float* bbox, const float* reg_target, const float* reg_weight, int n, int cells, const float* grad_loss,
                            float* grad_bbox, void* stream) {
     USOT_REQUIRE(bbox && reg_target && reg_weight && grad_loss && grad_bbox && n > 0 && cells > 0, "bad argument");
+    count_op_launch(OPFAM_TRAIN, 1);
     iou_backward_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(bbox, reg_target, reg_weight, n, cells, grad_loss, grad_bbox);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;

@@ -60,12 +60,14 @@ class ZfExchange:
 
 
 def cycle_forward_sharded(net, batch, group=None, cls_ratio=0.40):
-    """BASELINE config 4: `batch` holds THIS rank's shard (template, search, search_memory, label, reg_target, reg_weight,
-    template_bbox, search_bbox).  Returns the three losses averaged over ranks (0-d tensors)."""
+    """BASELINE config 4, forward only: `batch` holds THIS rank's shard (template, search, search_memory, label, reg_target,
+    reg_weight, template_bbox, search_bbox).  Returns the three losses averaged over ranks (0-d tensors, no autograd graph: the
+    engine's fused forward with running-statistics BatchNorm; for a training step use ``train_step_sharded``)."""
     ex = ZfExchange(group)
-    losses = net.forward(batch["template"], batch["search"], label=batch["label"], reg_target=batch["reg_target"],
-                         reg_weight=batch["reg_weight"], template_bbox=batch["template_bbox"], search_memory=batch["search_memory"],
-                         search_bbox=batch["search_bbox"], cls_ratio=cls_ratio, zf_exchange=ex)
+    with torch.no_grad():
+        losses = net.forward(batch["template"], batch["search"], label=batch["label"], reg_target=batch["reg_target"],
+                             reg_weight=batch["reg_weight"], template_bbox=batch["template_bbox"], search_memory=batch["search_memory"],
+                             search_bbox=batch["search_bbox"], cls_ratio=cls_ratio, zf_exchange=ex)
     out = torch.stack([losses[0], losses[1] if losses[1] is not None else torch.zeros_like(losses[0]), losses[2]]).float()
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
     out = out / ex.world
@@ -87,3 +89,120 @@ def track_sharded(net, x_local, template_mem_local=None, score_mem_local=None, g
         return out
 
     return ag(cls), ag(bbox), ag(cls_mem), xf
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Training: gradient all-reduce (replaces nn.DataParallel's reduce_add_coalesced, scripts/train_usot.py:318)
+# ---------------------------------------------------------------------------------------------------------------------------------
+class GradientReducer:
+    """Bucketed all-reduce of the parameter gradients, overlapped with the backward pass.
+
+    The reference trains under ``nn.DataParallel``: every iteration the replicas' gradients are summed onto device 0 over PCIe /
+    NVLink by ``reduce_add_coalesced`` AFTER backward has finished, and the parameters are re-broadcast before the next forward.
+    Here every rank owns a full replica (one process per GPU) and the ~118 MB of fp32 gradients are averaged with NCCL all-reduces
+    over NVLink / NVSwitch while backward is still running:
+
+      * parameters are packed, in REVERSE registration order (roughly the order backward produces their gradients: heads first,
+        stem last), into flat fp32 buckets of ``bucket_mb``; ``p.grad`` of every parameter is a VIEW into its bucket, so autograd
+        accumulates straight into the communication buffer (no gather / scatter copies);
+      * a post-accumulate hook per parameter counts ready gradients; when the last one of a bucket lands, ``all_reduce(AVG)`` of that
+        bucket is issued asynchronously (NCCL runs it on its own stream, ordered after the kernels that produced the gradients);
+      * ``finish()`` (after ``loss.backward()``) waits for the outstanding work, so the optimizer sees averaged gradients.
+
+    Averaging (not summing) matches the reference's ``loss = torch.mean(loss)`` over the per-replica losses (scripts/train_usot.py:
+    201-227).  BatchNorm statistics stay per rank, like DataParallel's per-replica statistics; ``broadcast_buffers`` copies rank 0's
+    running statistics to everyone (what DataParallel keeps: the module on device 0) before a checkpoint is written."""
+
+    def __init__(self, params, bucket_mb=25.0, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []       # dicts: flat, params, pending, work
+        self._of = {}
+        cap = int(bucket_mb * (1 << 20)) // 4
+        cur, cur_n = [], 0
+        for p in reversed(self.params):
+            if cur and cur_n + p.numel() > cap:
+                self._make_bucket(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self._make_bucket(cur)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.launch_order = []   # bucket indices in the order their all-reduce was issued (diagnostics / tests)
+        self.bytes_per_step = sum(b["flat"].numel() for b in self.buckets) * 4
+
+    def _make_bucket(self, plist):
+        dev, n = plist[0].device, sum(p.numel() for p in plist)
+        flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in plist:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            self._of[p] = len(self.buckets)
+            off += p.numel()
+        self.buckets.append({"flat": flat, "params": plist, "pending": len(plist), "work": None})
+
+    def zero_grad(self):
+        """Zero the buckets (instead of ``optimizer.zero_grad()``, which would drop the views with set_to_none=True)."""
+        for i, b in enumerate(self.buckets):
+            b["flat"].zero_()
+            b["pending"], b["work"] = len(b["params"]), None
+            off = 0
+            for p in b["params"]:   # re-attach the views if someone replaced .grad
+                if p.grad is None or p.grad.data_ptr() != b["flat"].data_ptr() + off * 4:
+                    p.grad = b["flat"][off:off + p.numel()].view_as(p)
+                off += p.numel()
+        self.launch_order = []
+
+    def _on_grad(self, p):
+        b = self.buckets[self._of[p]]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(self._of[p])
+
+    def _launch(self, i):
+        b = self.buckets[i]
+        self.launch_order.append(i)
+        if self.world > 1:
+            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """Wait for every bucket (issuing the all-reduce of buckets whose parameters got no gradient this step), then scale to the mean."""
+        for i, b in enumerate(self.buckets):
+            if b["work"] is None and b["pending"] > 0 and i not in self.launch_order:
+                self._launch(i)
+        for b in self.buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+                b["flat"].div_(self.world)
+                b["work"] = None
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def broadcast_buffers(net, src=0, group=None):
+    """Rank ``src``'s BatchNorm running statistics to every rank (DataParallel keeps device 0's)."""
+    for b in net.buffers():
+        dist.broadcast(b, src=src, group=group)
+
+
+def train_step_sharded(net, batch, reducer, optimizer=None, loss_weights=(1.0, 1.0, 1.0), cls_ratio=0.40):
+    """One data-parallel training step on this rank's shard: forward with an autograd graph (usot_b200/train.py), backward with the
+    gradient all-reduce overlapped (``reducer``), optional optimizer step.  ``loss_weights`` = (lambda_1, lambda_total - lambda_1, 1.0)
+    of scripts/train_usot.py:215-227.  Returns the three local losses (detached)."""
+    reducer.zero_grad()
+    losses = net.forward(batch["template"], batch["search"], label=batch["label"], reg_target=batch["reg_target"],
+                         reg_weight=batch["reg_weight"], template_bbox=batch["template_bbox"], search_memory=batch.get("search_memory"),
+                         search_bbox=batch.get("search_bbox"), cls_ratio=cls_ratio)
+    loss = loss_weights[0] * losses[0] + loss_weights[2] * losses[2]
+    if losses[1] is not None:
+        loss = loss + loss_weights[1] * losses[1]
+    loss.backward()
+    reducer.finish()
+    if optimizer is not None:
+        optimizer.step()
+    return tuple(None if v is None else v.detach() for v in losses)

@@ -221,15 +221,26 @@ class USOT_(nn.Module):
 
     def forward(self, template, search, label=None, reg_target=None, reg_weight=None, template_bbox=None, search_memory=None,
                 search_bbox=None, cls_ratio=0.40, zf_exchange=None):
-        """Training forward of lib/models/models.py:208-295 with eval-mode BN (running statistics; the reference's train()-mode
-        batch statistics are per-replica and shard-size dependent).  Returns the reference's triple
-        (cls_loss, cls_memory_loss or None, reg_loss) as 0-d CUDA tensors (forward only: no autograd graph).
+        """Training forward of lib/models/models.py:208-295.  Returns the reference's triple (cls_loss, cls_memory_loss or None,
+        reg_loss) as 0-d CUDA tensors.
 
-        ``zf_exchange``: optional callable ``zf_local (n,7,7,256) -> (handle_with_wait, zf_rows_for_this_rank)`` used by
-        usot_b200.dist to all-gather the template features across ranks while the search / memory backbones run."""
-        eng = self._engine(search.device)
+        * With autograd enabled (the reference's training loop, scripts/train_usot.py:196-233) or in ``train()`` mode the call runs the
+          TRAINING path (usot_b200/train.py): the losses carry an autograd graph whose backward runs this library's dgrad / wgrad /
+          BatchNorm / pooling / correlation / loss gradient kernels, and BatchNorm follows ``self.training`` exactly like the reference
+          (batch statistics + running-statistics update in train(), running statistics in eval()).
+        * Under ``torch.no_grad()`` in ``eval()`` mode it runs the engine's fused forward-only graph (running statistics).
+
+        ``zf_exchange``: optional callable ``zf_local (n,7,7,256) -> closure returning this rank's rows`` used by usot_b200.dist to
+        all-gather the template features across ranks while the search / memory backbones run (forward-only path)."""
         if self.pr_pool and template_bbox is None:
             raise ValueError("pr_pool=True needs template_bbox")
+        if self.training or torch.is_grad_enabled():
+            if not next(self.parameters()).is_cuda:
+                raise RuntimeError("usot_b200.USOT runs on CUDA only (call .cuda() first); there is no CPU fallback")
+            from . import train
+            return train.forward_train(self, template, search, label, reg_target, reg_weight, template_bbox, search_memory, search_bbox,
+                                       cls_ratio, train=self.training)
+        eng = self._engine(search.device)
         zf, _ = eng.template(template, template_bbox if self.pr_pool else None)
         pending = zf_exchange(zf) if zf_exchange is not None else None
         xf = eng.backbone_neck(search)
