@@ -119,7 +119,10 @@ def test_groupdw_variants_bit_identical(ops, F_):
         _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", mode))
         outs.append(ops.groupdw_xcorr(xs, zs, w, nx).clone())
     _lib.check(_lib.load().usot_set_tunable(b"groupdw_tma", 2))
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_warps4", 0))   # r02: the default FFMA2 kernel runs four consumer warps at F = 31 / 33
+    outs.append(ops.groupdw_xcorr(xs, zs, w, nx).clone())
+    _lib.check(_lib.load().usot_set_tunable(b"groupdw_warps4", 1))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]) and torch.equal(outs[0], outs[3])
 
 
 def test_groupdw_linearity_full_size(ops):

@@ -62,7 +62,7 @@ def test_cache_keyed_by_state_dict_hash(tmp_path, monkeypatch):
 
     first = run(sd)                      # miss: packs and writes the image
     files = sorted(os.listdir(tmp_path))
-    assert len(files) == 1 and files[0].endswith("_fp16x3_abi2.usotw")
+    assert len(files) == 1 and files[0].endswith("_fp16x3_abi3.usotw")
     second = run(sd)                     # hit: restored from the image
     assert sorted(os.listdir(tmp_path)) == files
     for u, v in zip(first, second):

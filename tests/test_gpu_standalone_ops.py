@@ -112,3 +112,19 @@ def test_iou_loss_vs_oracle(n):
     ref = O.iou_loss(bbox, target, weight)
     out = ops.iou_loss(bbox.cuda(), target.cuda(), weight.cuda())
     assert abs(float(out) - float(ref)) <= 3e-6 * abs(float(ref))
+
+
+def test_torch_ops_dispatch_to_the_c_abi():
+    """torch.ops.usot_b200.* (usot_b200/torch_ops.py): same results as the ctypes wrappers / the oracle."""
+    import usot_b200.torch_ops  # noqa: F401
+    from usot_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    f = torch.randn(2, 8, 9, 9, generator=g)
+    rois = torch.tensor([[0, 1.3, 0.7, 6.9, 7.2], [1, -1.0, 2.0, 4.5, 10.5]])
+    out = torch.ops.usot_b200.prroi_pooling_forward(f.cuda(), rois.cuda(), 7, 7, 1.0)
+    assert rel_err(out, O.prroi_pool2d(f, rois, 7, 7, 1.0)) <= 5e-6
+    gout = torch.randn(2, 8, 7, 7, generator=g)
+    gin = torch.ops.usot_b200.prroi_pooling_backward(f.cuda(), rois.cuda(), out, gout.cuda(), 7, 7, 1.0)
+    assert rel_err(gin, O.prroi_pool2d_backward(gout, rois, f.shape)) <= 5e-6
+    x, k = torch.randn(2, 8, 11, 11, generator=g), torch.randn(2, 8, 3, 3, generator=g)
+    assert rel_err(torch.ops.usot_b200.xcorr_depthwise(x.cuda(), k.cuda()), O.xcorr_depthwise(x, k)) <= 2e-6

@@ -93,3 +93,15 @@ def test_dgrad_weight_transform_matches_autograd(k, pad, dil):
     assert gx.shape == x.shape and float((gx - x.grad).abs().max()) <= 1e-10
     with pytest.raises(ValueError):
         dgrad_weights(w, (5, 5), (1, 1))
+
+
+def test_torch_ops_namespace_is_registered_and_has_no_cpu_kernel():
+    """torch.ops.usot_b200.* exists (dispatcher registration, CUDA key only): CPU tensors are rejected by the dispatcher itself."""
+    import torch
+    import usot_b200.torch_ops as T
+    for name in T.OPS:
+        assert hasattr(torch.ops.usot_b200, name)
+    with pytest.raises(NotImplementedError):
+        torch.ops.usot_b200.prroi_pooling_forward(torch.zeros(1, 4, 5, 5), torch.zeros(1, 5), 7, 7, 1.0)
+    with pytest.raises(NotImplementedError):
+        torch.ops.usot_b200.xcorr_depthwise(torch.zeros(1, 4, 9, 9), torch.zeros(1, 4, 3, 3))

@@ -124,7 +124,7 @@ struct GroupDWArgs {
     __half* out_hi = nullptr;                              // optional: write the split-fp16 planes the tower convs read instead of
     __half* out_lo = nullptr;                              // fp32 `out` (FFMA2 kernel only; out_lo may be null in single-fp16 mode)
 };
-extern Tunable g_groupdw_strips, g_groupdw_tma, g_groupdw_row_split;
+extern Tunable g_groupdw_strips, g_groupdw_tma, g_groupdw_row_split, g_groupdw_warps4;
 bool groupdw_split_output_supported(int F);  // true when launch_groupdw_w will run the FFMA2 kernel, which can write split-fp16 planes
 int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaStream_t st);  // xcorr_tma.cu
 int launch_groupdw(const GroupDWArgs& a, cudaStream_t st);  // reads dw_weight back (one stream sync)

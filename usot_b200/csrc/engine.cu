@@ -777,6 +777,7 @@ int usot_set_tunable(const char* name, int value) {
     if (!strcmp(name, "tc_split_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_split_bn_max must be 64, 128 or 256"); g_tc_split_bn_max = value; return 0; }
     if (!strcmp(name, "pred_tma_min_batch")) { USOT_REQUIRE(value >= 0, "pred_tma_min_batch must be >= 0 (0 = never use the TMA-streamed pred kernel)"); g_pred_tma_min_batch = value; return 0; }
     if (!strcmp(name, "groupdw_row_split")) { USOT_REQUIRE(value == 0 || value == 1, "groupdw_row_split must be 0 or 1"); g_groupdw_row_split = value; return 0; }
+    if (!strcmp(name, "groupdw_warps4")) { USOT_REQUIRE(value == 0 || value == 1, "groupdw_warps4 must be 0 or 1"); g_groupdw_warps4 = value; return 0; }
     if (!strcmp(name, "groupdw_strips")) { USOT_REQUIRE(value == 2 || value == 3, "groupdw_strips must be 2 or 3"); g_groupdw_strips = value; return 0; }
     USOT_REQUIRE(false, "unknown tunable");
 }

@@ -159,6 +159,11 @@ __global__ void __launch_bounds__(GD_CONSUMERS + 32, 3) groupdw_tma_kernel(const
 // CTA = (output sample, 64-channel slab): 3 consumer warps (one column strip each, 32 channel pairs) + 1 TMA producer warp.
 // ---------------------------------------------------------------------------------------------
 constexpr int G2_STAGES = 2, G2_CONSUMER_WARPS = 3;
+// r02: FOUR consumer warps (column strips of 7 / 6) instead of three (9 / 9 / 7): one consumer warp per SM sub-partition.  The kernel is
+// FFMA2-issue bound once the step's power cap has pulled the SM clock down (a 3-register FFMA2 issues every other cycle), and with 3 CTAs
+// of 3 consumer warps per SM one scheduler carried 3 warps while the others carried 2.  Same fma sequence per output element: bit-identical.
+constexpr int G2_CONSUMER_WARPS4 = 4;
+Tunable g_groupdw_warps4 = 1;     // tunable "groupdw_warps4": 1 = four-strip variant for response sizes 25 / 27 (default), 0 = three strips
 Tunable g_groupdw_row_split = 1;  // tunable "groupdw_row_split": small batches split the output rows of one map over several CTAs
 
 static __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
@@ -257,7 +262,8 @@ static __device__ __forceinline__ void g2_consume(const GdwParams& p, const uint
     }
 }
 
-__global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_kernel(const __grid_constant__ GdwParams p) {
+template <int NCW>
+__global__ void __launch_bounds__(NCW * 32 + 32, 3) groupdw_ffma2_kernel(const __grid_constant__ GdwParams p) {
     extern __shared__ __align__(128) uint8_t gsm_raw[];
     const uint32_t base = (smem_u32(gsm_raw) + 127u) & ~127u;
     uint8_t* sm = gsm_raw + (base - smem_u32(gsm_raw));
@@ -276,7 +282,7 @@ __global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_
     const int t_end = min(H11, min(R, r0 + p.rows_per_group) + 4);  // one past the last input row it needs
 
     if (tid == 0) {
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, G2_CONSUMER_WARPS); }
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, NCW); }
         fence_barrier_init();
     }
     if (tid < 64) {
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_
     }
     __syncthreads();
 
-    if (warp == G2_CONSUMER_WARPS) {
+    if (warp == NCW) {
         // ------------------------------- producer -------------------------------
         if (lane == 0) {
             tma_prefetch_desc(&p.m11); tma_prefetch_desc(&p.m12); tma_prefetch_desc(&p.m21);
@@ -306,13 +312,20 @@ __global__ void __launch_bounds__(G2_CONSUMER_WARPS * 32 + 32, 3) groupdw_ffma2_
     }
 
     // ------------------------------- consumers: warp = column strip, lane = channel pair -------------------------------
-    const int j0 = warp * 9;
-    const int jn = min(9, R - j0);
     const float2* z = reinterpret_cast<const float2*>(zs) + lane;                           // tap t of this pair: z[t * 32]
     const size_t obase = ((size_t)n * R * R * C + cblk * 64) / 2 + lane;  // in channel pairs
     float2* out = reinterpret_cast<float2*>(p.out) + obase;
     __half2* out_hi = p.out_hi ? p.out_hi + obase : nullptr;
     __half2* out_lo = p.out_lo ? p.out_lo + obase : nullptr;
+    if (NCW == 4) {   // R = 25: strips 7 | 6 | 6 | 6;  R = 27: 7 | 7 | 7 | 6   (the launcher admits only these two sizes)
+        const int wide = R - 24;                       // number of 7-wide strips (1 or 3)
+        const int j4 = warp <= wide ? warp * 7 : wide * 7 + (warp - wide) * 6;
+        if (warp < wide) g2_consume<7, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j4, 7, lane, r0, t_end);
+        else g2_consume<6, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j4, 6, lane, r0, t_end);
+        return;
+    }
+    const int j0 = warp * 9;
+    const int jn = min(9, R - j0);
     if (jn == 9) g2_consume<9, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane, r0, t_end);
     else if (jn == 7) g2_consume<7, false>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane, r0, t_end);
     else g2_consume<9, true>(p, sm, bar_full, bar_empty, stage_bytes, z, out, out_hi, out_lo, j0, jn, lane, r0, t_end);
@@ -343,8 +356,9 @@ int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaS
     const int smem = GD_STAGES * (3 * F - 8) * 256 + 55 * 64 * 4 + 2 * GD_STAGES * 8 + 128;
     if (g_groupdw_tma >= 2) {
         const int smem2 = G2_STAGES * (3 * F - 8) * 256 + 55 * 64 * 4 + 2 * G2_STAGES * 8 + 128;
-        static SmemAttrCache attr2;
-        if (int rc = attr2.ensure(groupdw_ffma2_kernel, smem2)) return rc;
+        static SmemAttrCache attr2, attr4;
+        const bool four = g_groupdw_warps4 && (R == 25 || R == 27);
+        if (int rc = four ? attr4.ensure(groupdw_ffma2_kernel<G2_CONSUMER_WARPS4>, smem2) : attr2.ensure(groupdw_ffma2_kernel<G2_CONSUMER_WARPS>, smem2)) return rc;
         // Latency mode (small batches): fewer (sample, slab) pairs than SMs -> split the output rows over several CTAs.  Each extra
         // CTA re-reads 4 warm-up input rows (L2 hits); results are bit-identical to the whole-map CTA (same fma sequence per row).
         const int pairs = a.n_out * (a.C / 64);
@@ -353,7 +367,8 @@ int launch_groupdw_tma(const GroupDWArgs& a, float w0, float w1, float w2, cudaS
         if (g_groupdw_row_split && pairs * 2 <= sms) p.row_groups = std::min(R, sms / pairs);
         p.rows_per_group = (R + p.row_groups - 1) / p.row_groups;
         p.row_groups = (R + p.rows_per_group - 1) / p.rows_per_group;
-        groupdw_ffma2_kernel<<<(unsigned)(pairs * p.row_groups), G2_CONSUMER_WARPS * 32 + 32, smem2, st>>>(p);
+        if (four) groupdw_ffma2_kernel<G2_CONSUMER_WARPS4><<<(unsigned)(pairs * p.row_groups), G2_CONSUMER_WARPS4 * 32 + 32, smem2, st>>>(p);
+        else groupdw_ffma2_kernel<G2_CONSUMER_WARPS><<<(unsigned)(pairs * p.row_groups), G2_CONSUMER_WARPS * 32 + 32, smem2, st>>>(p);
         USOT_CUDA_OK(cudaGetLastError());
         return 0;
     }
