@@ -172,9 +172,14 @@ USOT_API int usot_iou_loss(const float* bbox, const float* reg_target, const flo
 /* The backward of USOT_.forward (scripts/train_usot.py:229-236 calls loss.backward(); the reference gets every gradient from torch
  * autograd over cuDNN).  All maps nhwc fp32; weights in the (kh*kw*cin, cout) "kn" layout of usot_conv2d_nhwc. */
 
-/* autograd of nn.Conv2d w.r.t. its weight: grad_weight_kn (kh*kw*cin, cout) is overwritten.  Any stride / dilation / channel count. */
+/* autograd of nn.Conv2d w.r.t. its weight: grad_weight_kn (kh*kw*cin, cout) is overwritten.  Any stride / dilation / channel count.
+ * precision = USOT_PREC_*: the tcgen05 modes run the tensor-core kernel (MN-major operands straight from the nhwc maps, fp16x3 split,
+ * gradients pre-scaled by a power of two on the device) when Cin % 64 == 0 and Cout % 64 == 0; otherwise / fp32: fp32 FMA kernel. */
 USOT_API int usot_conv2d_wgrad_nhwc(const float* in, const float* grad_out, int n, int h, int w, int cin, int cout, int kh, int kw, int stride,
-                                    int pad_h, int pad_w, int dil_h, int dil_w, float* grad_weight_kn, void* stream);
+                                    int pad_h, int pad_w, int dil_h, int dil_w, float* grad_weight_kn, int precision, void* stream);
+/* Power-of-two pre-scaling of a gradient map for the split-fp16 tensor-core kernels: s = 2^e with s * max|x| in [2^target_log2,
+ * 2^(target_log2+1)) (s = 1 for an all-zero map); scale2[2] (device) = {s, 1/s}; y (optional, may alias nothing) = s * x.  No host sync. */
+USOT_API int usot_pow2_scale(const float* x, int64_t numel, int target_log2, float* y, float* scale2, void* stream);
 /* autograd of nn.Conv2d w.r.t. its input, generic gather form (the thin 256->1/4 prediction convs; wide layers run their dgrad on the
  * forward conv kernels: usot_conv2d_nhwc with transposed / flipped filters).  grad_in (n,h,w,cin) is overwritten. */
 USOT_API int usot_conv2d_dgrad_nhwc(const float* grad_out, const float* weight_kn, int n, int h, int w, int cin, int cout, int kh, int kw,

@@ -32,37 +32,59 @@ CONVS = [  # n, h, w, cin, cout, k, stride, pad, dil
 ]
 
 
+PREC_TOL = {"fp32": 2e-5, "fp16x3": 5e-5, "fp16": 6e-3}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3", "fp16"])
 @pytest.mark.parametrize("cfg", CONVS, ids=[f"{c[3]}to{c[4]}k{c[5]}s{c[6]}" + (f"d{c[8][0]}{c[8][1]}" if c[8] != (1, 1) else "") + f"_{c[1]}x{c[2]}" for c in CONVS])
-def test_conv_wgrad_vs_autograd(cfg):
+def test_conv_wgrad_vs_autograd(cfg, precision):
+    """fp32: the FMA kernel.  fp16x3 / fp16: the tcgen05 kernel (MN-major operands) for the wide layers -- with gradients of magnitude 1e-6,
+    far below fp16's normal range, so the device-side power-of-two scaling is exercised -- and the FMA kernel for the thin ones."""
     from usot_b200 import train
     n, h, w, cin, cout, k, stride, pad, dil = cfg
     g = torch.Generator().manual_seed(h * 100 + cin)
-    x = torch.randn(n, h, w, cin, generator=g)
+    x = torch.randn(n, h, w, cin, generator=g) * 3.0
     ho = (h + 2 * pad[0] - dil[0] * (k - 1) - 1) // stride + 1
     wo = (w + 2 * pad[1] - dil[1] * (k - 1) - 1) // stride + 1
-    gy = torch.randn(n, ho, wo, cout, generator=g)
+    gy = torch.randn(n, ho, wo, cout, generator=g) * 1e-6
     ref = torch.empty(k * k * cin, cout)
-    R.usot_conv2d_wgrad_nhwc(x, gy, n, h, w, cin, cout, k, k, stride, pad[0], pad[1], dil[0], dil[1], ref, 0)
-    out = train.conv_wgrad(x.cuda(), gy.cuda(), (cout, cin, k, k), stride, pad, dil)      # OIHW
+    R.usot_conv2d_wgrad_nhwc(x, gy, n, h, w, cin, cout, k, k, stride, pad[0], pad[1], dil[0], dil[1], ref, 0, 0)
+    out = train.conv_wgrad(x.cuda(), gy.cuda(), (cout, cin, k, k), stride, pad, dil, precision)      # OIHW
     ref_oihw = ref.view(k, k, cin, cout).permute(3, 2, 0, 1)
-    assert rel_err(out, ref_oihw) <= 2e-5
+    err = rel_err(out, ref_oihw)
+    print("wgrad", cfg, precision, f"{err:.2e}")
+    assert err <= PREC_TOL[precision]
 
 
 @pytest.mark.parametrize("cfg", [c for c in CONVS if c[3] != 3], ids=lambda c: f"{c[3]}to{c[4]}k{c[5]}s{c[6]}_{c[1]}x{c[2]}")
-@pytest.mark.parametrize("precision", ["fp32"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_conv_dgrad_vs_autograd(cfg, precision):
-    """stride 1 (any dilation / padding) and the stride-2 parity decomposition on the forward kernels; thin convs on the gather kernel."""
+    """stride 1 (any dilation / padding) and the stride-2 parity decomposition on the forward kernels (fp32 FMA, and tcgen05 fp16x3 with the
+    gradient pre-scaled on the device); thin convs on the gather kernel."""
     from usot_b200 import train
     n, h, w, cin, cout, k, stride, pad, dil = cfg
     g = torch.Generator().manual_seed(h * 10 + cout)
     wt = torch.randn(cout, cin, k, k, generator=g) * 0.1
     x = torch.zeros(n, cin, h, w, requires_grad=True)
     y = F.conv2d(x, wt, None, stride, pad, dil)
-    gy = torch.randn(y.shape, generator=g)
+    gy = torch.randn(y.shape, generator=g) * 1e-7
     (ref,) = torch.autograd.grad(y, x, gy)
     out = train.conv_dgrad(gy.permute(0, 2, 3, 1).contiguous().cuda(), wt.cuda(), (h, w), stride, pad, dil, precision=precision)
     assert tuple(out.shape) == (n, h, w, cin)
-    assert rel_err(out.permute(0, 3, 1, 2), ref) <= 2e-5
+    assert rel_err(out.permute(0, 3, 1, 2), ref) <= PREC_TOL[precision]
+
+
+def test_pow2_scale():
+    from usot_b200 import train
+    for mag in (3e-9, 1.0, 700.0):
+        x = torch.randn(4096, generator=torch.Generator().manual_seed(1)) * mag
+        g, inv = train._prescale(x.cuda(), 8)
+        m = float(g.abs().max())
+        assert 1024.0 <= m < 2048.0
+        s = 1.0 / float(inv[0])
+        assert torch.equal(g.cpu(), x * s) and abs(torch.log2(torch.tensor(s)).item() - round(torch.log2(torch.tensor(s)).item())) == 0.0
+    g, inv = train._prescale(torch.zeros(64, device="cuda"), 4)
+    assert float(inv[0]) == 1.0 and float(g.abs().max()) == 0.0
 
 
 def test_stem_raw_and_device_weight_pack():

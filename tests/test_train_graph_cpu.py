@@ -106,3 +106,18 @@ def test_stride2_dgrad_decomposition_matches_autograd():
         with train_ref.install():
             out = train.conv_dgrad(gy.permute(0, 2, 3, 1).contiguous(), wt, (h, w), 2, pad, 1, precision="fp32")
         assert torch.allclose(out.permute(0, 3, 1, 2), ref, atol=1e-4, rtol=1e-4), (h, w, k, pad)
+
+
+def test_tensor_core_backward_route_prescales_and_unscales_exactly():
+    """In the tcgen05 modes conv_dgrad multiplies the gradient by a device-chosen power of two and divides it out in the conv epilogue:
+    the route (here on the CPU stand-ins) must give the same result as the unscaled fp32 route, to rounding."""
+    from usot_b200 import train
+    g = torch.Generator().manual_seed(6)
+    wt = torch.randn(64, 128, 3, 3, generator=g) * 0.1
+    gy = torch.randn(2, 9, 9, 64, generator=g) * 1e-7
+    with train_ref.install():
+        a = train.conv_dgrad(gy, wt, (9, 9), 1, 1, 1, precision="fp32")
+        b = train.conv_dgrad(gy, wt, (9, 9), 1, 1, 1, precision="fp16x3")
+        c = train.conv_dgrad(gy[:, :4, :4].contiguous(), wt, (9, 9), 2, 0, 1, precision="fp16x3")
+        d = train.conv_dgrad(gy[:, :4, :4].contiguous(), wt, (9, 9), 2, 0, 1, precision="fp32")
+    assert torch.allclose(a, b, rtol=1e-5, atol=1e-14) and torch.allclose(c, d, rtol=1e-5, atol=1e-14)

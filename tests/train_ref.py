@@ -85,7 +85,7 @@ def usot_stem_conv_raw(x, n, size, w_kn, out, stream):
 
 
 @torch.enable_grad()
-def usot_conv2d_wgrad_nhwc(x, gout, n, h, w, cin, cout, kh, kw, stride, ph, pw, dh, dw, gw_kn, stream):
+def usot_conv2d_wgrad_nhwc(x, gout, n, h, w, cin, cout, kh, kw, stride, ph, pw, dh, dw, gw_kn, precision, stream):
     xx = x.view(n, h, w, cin).permute(0, 3, 1, 2).detach().clone()
     wt = torch.zeros(cout, cin, kh, kw, requires_grad=True)
     y = F.conv2d(xx, wt, None, stride, (ph, pw), (dh, dw))
@@ -133,6 +133,15 @@ def usot_bn_backward(gy, y, x, bias, mean, invstd, gamma, train, relu, m, c, gx,
     gbeta.copy_(db.float())
     if gres is not None:
         gres.copy_(dz.float().view_as(gres))
+
+
+def usot_pow2_scale(x, numel, target_log2, y, scale2, stream):
+    import math
+    m = float(x.abs().max())
+    s = 1.0 if not (m > 0 and math.isfinite(m)) else 2.0 ** (target_log2 + 1 - math.frexp(m)[1])
+    scale2.copy_(torch.tensor([s, 1.0 / s]))
+    if y is not None:
+        y.copy_(x * s)
 
 
 def usot_channel_sum(x, m, c, out, stream):

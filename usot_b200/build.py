@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libusot_b200.so")
-SOURCES = ["kernels_simt.cu", "kernels_glue.cu", "conv_tc.cu", "stem_tc.cu", "xcorr_tma.cu", "pred_tma.cu", "crop.cu", "ops_abi.cu", "train_kernels.cu", "engine.cu"]
+SOURCES = ["kernels_simt.cu", "kernels_glue.cu", "conv_tc.cu", "stem_tc.cu", "xcorr_tma.cu", "pred_tma.cu", "crop.cu", "ops_abi.cu", "train_kernels.cu", "wgrad_tc.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-shared", "-cudart", "static",

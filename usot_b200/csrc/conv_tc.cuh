@@ -68,6 +68,10 @@ int launch_pack_tc_weights(const float* w_kn, int K, int cout, const float* scal
 void pack_tc_weights_host(const float* w_kn, int K, int cout, const float* scale_in, std::vector<__half>& hi, std::vector<__half>& lo,
                           std::vector<float>& scale_out);
 
+// wgrad_tc.cu: weight gradient on tcgen05 (MN-major operands straight from the NHWC maps) + the power-of-two gradient scaling it needs
+bool wgrad_tc_supported(const ConvGeom& g);
+int launch_conv_wgrad_tc(const float* x, const float* dy, const ConvGeom& g, float* dw_kn, bool split, cudaStream_t st);
+int launch_pow2_scale(const float* x, size_t n, int target_log2, float* y /*or null*/, float* out2 /*{s, 1/s}*/, cudaStream_t st);
 size_t stem_tc_image_bytes();  // size of the packed stem weight tile (validated when a packed-weight image is imported)
 void pack_stem_tc_host(const float* w_oihw, const float* scale_in, std::vector<uint8_t>& img, std::vector<float>& scale_out);
 

@@ -11,6 +11,7 @@
 //   _weighted_BCE / IoU   backward of the two losses                                 lib/models/models.py:42-100
 //   column sums           bias gradients
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "../../include/usot_b200.h"
 
 #include <cfloat>
@@ -475,12 +476,22 @@ static int make_geom(ConvGeom* g, int n, int h, int w, int cin, int cout, int kh
 }
 
 int usot_conv2d_wgrad_nhwc(const float* in, const float* grad_out, int n, int h, int w, int cin, int cout, int kh, int kw, int stride, int pad_h,
-                           int pad_w, int dil_h, int dil_w, float* grad_weight_kn, void* stream) {
+                           int pad_w, int dil_h, int dil_w, float* grad_weight_kn, int precision, void* stream) {
     USOT_REQUIRE(grad_weight_kn && (n == 0 || (in && grad_out)), "null pointer");
+    USOT_REQUIRE(precision >= USOT_PREC_FP32_SIMT && precision <= USOT_PREC_FP16_TC, "unknown precision mode");
     ConvGeom g;
     if (int rc = make_geom(&g, n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w)) return rc;
     count_op_launch(OPFAM_WGRAD, 1);
+    if (precision != USOT_PREC_FP32_SIMT && wgrad_tc_supported(g))
+        return launch_conv_wgrad_tc(in, grad_out, g, grad_weight_kn, precision == USOT_PREC_FP16X3_TC, (cudaStream_t)stream);
     return launch_conv_wgrad(in, grad_out, g, grad_weight_kn, (cudaStream_t)stream);
+}
+
+int usot_pow2_scale(const float* x, int64_t numel, int target_log2, float* y, float* scale2, void* stream) {
+    USOT_REQUIRE(x && scale2 && numel > 0 && numel % 4 == 0, "bad argument");
+    USOT_REQUIRE(target_log2 >= -20 && target_log2 <= 14, "target exponent out of range");
+    count_op_launch(OPFAM_TRAIN, y ? 3 : 2);
+    return launch_pow2_scale(x, (size_t)numel, target_log2, y, scale2, (cudaStream_t)stream);
 }
 
 int usot_conv2d_dgrad_nhwc(const float* grad_out, const float* weight_kn, int n, int h, int w, int cin, int cout, int kh, int kw, int stride,

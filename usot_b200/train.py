@@ -30,9 +30,12 @@ from .ops import _stream
 
 BN_EPS = 1e-5
 
-# Arithmetic of the dense convs on this path.  Forward: the engine's parity mode.  Backward (dgrad on the forward kernels): fp32 FMA --
-# gradient magnitudes sit far below fp16's normal range, so the split-fp16 tensor-core mode would need per-tensor scaling first.
-BWD_PRECISION = "fp32"
+# Arithmetic of the backward convs (dgrad on the forward kernels, wgrad): None = the same mode as the forward convs (tcgen05 fp16x3 by
+# default).  Gradient magnitudes sit far below fp16's normal range, so in the tensor-core modes every gradient map is first multiplied by a
+# power of two computed on the device from its absmax (usot_pow2_scale) and the factor is divided out in the conv epilogue -- exact.
+# "fp32" forces the fp32 FMA kernels.
+BWD_PRECISION = None
+GRAD_TARGET_LOG2 = 10
 
 
 class Mode:
@@ -114,9 +117,25 @@ def _wide(cin, cout, precision):
     return (cin % 64 == 0 and cout % 64 == 0) if precision != "fp32" else (cin % 16 == 0 and cout % 64 == 0)
 
 
-def conv_dgrad(grad_out, weight_oihw, in_hw, stride, pad, dil, precision=None):
+def _prescale(grad_out, n_scale_channels):
+    """(s * grad_out, per-channel vector 1/s) with s a power of two chosen on the device (no host sync)."""
+    g = torch.empty_like(grad_out)
+    sc2 = torch.empty(2, dtype=torch.float32, device=grad_out.device)
+    _lib_call("usot_pow2_scale", grad_out.device, _lib.ptr(grad_out), grad_out.numel(), GRAD_TARGET_LOG2, _lib.ptr(g), _lib.ptr(sc2), _stream(grad_out))
+    return g, sc2[1:2].expand(n_scale_channels).contiguous()
+
+
+def _dgrad_gemm(grad_out, weight_oihw, pad, dil, precision):
+    """Stride-1 input gradient on the forward conv kernel (transposed, flipped filter); tensor-core modes pre-scale the gradient."""
+    if precision == "fp32":
+        return ops.conv2d_nhwc_input_grad(grad_out, weight_oihw, pad, dil, precision=precision)
+    w_t, pad_t = ops.dgrad_weights(weight_oihw, pad, dil)
+    g, inv = _prescale(grad_out, w_t.shape[0])
+    return ops.conv2d_nhwc(g, w_t, inv, torch.zeros_like(inv), stride=1, padding=pad_t, dilation=dil, precision=precision)
+
+
+def conv_dgrad(grad_out, weight_oihw, in_hw, stride, pad, dil, precision="fp32"):
     """Gradient w.r.t. the input of a conv.  grad_out NHWC (n,ho,wo,cout) -> NHWC (n,h,w,cin)."""
-    precision = precision or BWD_PRECISION
     cout, cin, kh, kw = weight_oihw.shape
     n, ho, wo, _ = grad_out.shape
     h, w = in_hw
@@ -128,7 +147,7 @@ def conv_dgrad(grad_out, weight_oihw, in_hw, stride, pad, dil, precision=None):
                   ph, pw, dh, dw, _lib.ptr(gi), _stream(grad_out))
         return gi
     if stride == 1:
-        gi = ops.conv2d_nhwc_input_grad(grad_out, weight_oihw, (ph, pw), (dh, dw), precision=precision)
+        gi = _dgrad_gemm(grad_out, weight_oihw, (ph, pw), (dh, dw), precision)
         assert tuple(gi.shape[1:3]) == (h, w), (gi.shape, h, w)
         return gi
     # stride 2 (layer2.0.conv2, layer2.0.downsample; dilation 1): input rows of parity class r only see the taps kh = r (mod 2), and for
@@ -140,7 +159,7 @@ def conv_dgrad(grad_out, weight_oihw, in_hw, stride, pad, dil, precision=None):
             sub = weight_oihw[:, :, rh::2, rw::2]
             if sub.shape[2] == 0 or sub.shape[3] == 0:
                 continue
-            part = ops.conv2d_nhwc_input_grad(grad_out, sub.contiguous(), (0, 0), (1, 1), precision=precision)   # (n, ho+Jh-1, wo+Jw-1, cin)
+            part = _dgrad_gemm(grad_out, sub.contiguous(), (0, 0), (1, 1), precision)   # (n, ho+Jh-1, wo+Jw-1, cin)
             # part[u, v] is the gradient of input pixel (y, x) = (2u + rh - ph, 2v + rw - pw)
             ys = [(2 * u + rh - ph, u) for u in range(part.shape[1]) if 0 <= 2 * u + rh - ph < h]
             xs = [(2 * v + rw - pw, v) for v in range(part.shape[2]) if 0 <= 2 * v + rw - pw < w]
@@ -150,14 +169,14 @@ def conv_dgrad(grad_out, weight_oihw, in_hw, stride, pad, dil, precision=None):
     return gi
 
 
-def conv_wgrad(x, grad_out, weight_shape, stride, pad, dil):
+def conv_wgrad(x, grad_out, weight_shape, stride, pad, dil, precision="fp32"):
     """Gradient w.r.t. the OIHW weight.  x NHWC (n,h,w,cin), grad_out NHWC (n,ho,wo,cout)."""
     cout, cin, kh, kw = weight_shape
     n, h, w, _ = x.shape
     (ph, pw), (dh, dw) = _pair(pad), _pair(dil)
     gw = torch.empty((kh * kw * cin, cout), dtype=torch.float32, device=x.device)
     _lib_call("usot_conv2d_wgrad_nhwc", x.device, _lib.ptr(_c(x)), _lib.ptr(_c(grad_out)), n, h, w, cin, cout, kh, kw, stride, ph, pw, dh, dw,
-              _lib.ptr(gw), _stream(x))
+              _lib.ptr(gw), _lib.PRECISIONS[precision], _stream(x))
     return gw.view(kh, kw, cin, cout).permute(3, 2, 0, 1).contiguous()
 
 
@@ -168,16 +187,16 @@ class _Conv(Function):
     def forward(ctx, x, weight, stride, pad, dil, precision):
         x = _c(x)
         ctx.save_for_backward(x, weight)
-        ctx.cfg = (stride, _pair(pad), _pair(dil))
+        ctx.cfg = (stride, _pair(pad), _pair(dil), BWD_PRECISION or precision)
         return _conv_raw(x, weight, stride, _pair(pad), _pair(dil), precision)
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        stride, pad, dil = ctx.cfg
+        stride, pad, dil, prec = ctx.cfg
         g = _c(g)
-        gx = conv_dgrad(g, weight, x.shape[1:3], stride, pad, dil) if ctx.needs_input_grad[0] else None
-        gw = conv_wgrad(x, g, weight.shape, stride, pad, dil) if ctx.needs_input_grad[1] else None
+        gx = conv_dgrad(g, weight, x.shape[1:3], stride, pad, dil, prec) if ctx.needs_input_grad[0] else None
+        gw = conv_wgrad(x, g, weight.shape, stride, pad, dil, prec) if ctx.needs_input_grad[1] else None
         return gx, gw, None, None, None, None
 
 
