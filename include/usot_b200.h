@@ -177,6 +177,9 @@ USOT_API int usot_iou_loss(const float* bbox, const float* reg_target, const flo
  * gradients pre-scaled by a power of two on the device) when Cin % 64 == 0 and Cout % 64 == 0; otherwise / fp32: fp32 FMA kernel. */
 USOT_API int usot_conv2d_wgrad_nhwc(const float* in, const float* grad_out, int n, int h, int w, int cin, int cout, int kh, int kw, int stride,
                                     int pad_h, int pad_w, int dil_h, int dil_w, float* grad_weight_kn, int precision, void* stream);
+/* Weight gradient of the stem conv (usot_stem_conv_raw): x (n,3,size,size) nchw, grad_out (n,HO,HO,64) nhwc -> grad_weight_kn (147, 64) with
+ * k = (c*7 + kh)*7 + kw (the layout usot_stem_conv_raw takes), overwritten.  fp32 FMA, im2col on the fly. */
+USOT_API int usot_stem_conv_wgrad(const float* x, const float* grad_out, int n, int size, float* grad_weight_kn, void* stream);
 /* Power-of-two pre-scaling of a gradient map for the split-fp16 tensor-core kernels: s = 2^e with s * max|x| in [2^target_log2,
  * 2^(target_log2+1)) (s = 1 for an all-zero map); scale2[2] (device) = {s, 1/s}; y (optional, may alias nothing) = s * x.  No host sync. */
 USOT_API int usot_pow2_scale(const float* x, int64_t numel, int target_log2, float* y, float* scale2, void* stream);

@@ -57,3 +57,36 @@ def test_optimizer_step_changes_the_forward_only_engine_too():
         l2 = net(z, x, label, reg_target=reg_target, reg_weight=reg_weight, template_bbox=tb, search_memory=smem, search_bbox=sb)   # engine path (no_grad + eval)
     assert not torch.equal(before, after)
     assert float(l2[0] + l2[1] + l2[2]) < float(losses[0] + losses[1] + losses[2])   # a small step along -grad lowers the loss
+
+
+def test_cuda_graphed_training_step_matches_eager_steps():
+    """usot_b200.dist.GraphedTrainStep: the whole step (forward + backward + SGD) captured once and replayed must follow the eager steps
+    (same losses step by step; parameters agree to the rounding noise of the split-K atomics)."""
+    from usot_b200 import USOT
+    from usot_b200.dist import GradientReducer, GraphedTrainStep, train_step_sharded
+    z, x, tb, sb, smem, label, reg_target, reg_weight = [t.cuda() for t in _inputs(2, 2)]
+    batch = dict(template=z, search=x, search_memory=smem, label=label, reg_target=reg_target, reg_weight=reg_weight, template_bbox=tb, search_bbox=sb)
+
+    def make():
+        net = USOT({"mem_size": 2, "pr_pool": True}, precision="fp16x3")
+        net.load_state_dict(load_weights("damp025"), strict=True)
+        net = net.cuda().train()
+        red = GradientReducer(net.parameters())
+        opt = torch.optim.SGD(net.parameters(), lr=1e-4, momentum=0.9)
+        return net, red, opt
+
+    net_e, red_e, opt_e = make()
+    eager = [torch.stack(train_step_sharded(net_e, batch, red_e, opt_e)).cpu() for _ in range(5)]
+    net_g, red_g, opt_g = make()
+    gstep = GraphedTrainStep(net_g, red_g, opt_g, batch, warmup=3)      # 3 eager warm-up steps + 1 captured (not executed) step
+    graphed = [torch.stack(gstep(batch)).cpu().clone() for _ in range(2)]   # = steps 4 and 5
+    for a, b in zip(eager[3:], graphed):
+        assert torch.allclose(a, b, rtol=2e-4, atol=1e-6), (a, b)
+    assert float(eager[4].sum()) < float(eager[0].sum())                  # the loss goes down over the five SGD steps
+    pe, pg = dict(net_e.named_parameters()), dict(net_g.named_parameters())
+    for k in ("connect_model.cls_pred.weight", "features.features.layer3.5.conv3.weight", "features.features.conv1.weight", "neck.downsample.1.bias"):
+        assert rel_err_t(pg[k], pe[k]) <= 1e-4, k
+
+
+def rel_err_t(a, b):
+    return float((a.detach() - b.detach()).abs().max() / b.detach().abs().max().clamp_min(1e-30))

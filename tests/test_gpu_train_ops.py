@@ -93,8 +93,15 @@ def test_stem_raw_and_device_weight_pack():
     g = torch.Generator().manual_seed(1)
     x = torch.rand(2, 3, 127, 127, generator=g) * 255
     w = torch.randn(64, 3, 7, 7, generator=g) * 0.05
-    out = train._StemConv.apply(x.cuda(), w.cuda())
-    assert rel_err(out.permute(0, 3, 1, 2), F.conv2d(x, w, None, 2, 0)) <= 2e-6
+    wc = w.cuda().requires_grad_(True)
+    out = train._StemConv.apply(x.cuda(), wc)
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv2d(x, wr, None, 2, 0)
+    assert rel_err(out.permute(0, 3, 1, 2), ref) <= 2e-6
+    gy = torch.randn(ref.shape, generator=g) * 1e-3
+    ref.backward(gy)
+    out.backward(gy.permute(0, 2, 3, 1).contiguous().cuda())
+    assert rel_err(wc.grad, wr.grad) <= 2e-5      # usot_stem_conv_wgrad (im2col on the fly, (channel, tap) as the GEMM's M dimension)
     xa = torch.randn(2, 15, 15, 128, generator=g)
     wa = torch.randn(256, 128, 3, 3, generator=g) * 0.03
     one, zero = torch.ones(256), torch.zeros(256)

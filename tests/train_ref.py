@@ -85,6 +85,14 @@ def usot_stem_conv_raw(x, n, size, w_kn, out, stream):
 
 
 @torch.enable_grad()
+def usot_stem_conv_wgrad(x, gout, n, size, gw_kn, stream):
+    wt = torch.zeros(64, 3, 7, 7, requires_grad=True)
+    y = F.conv2d(x, wt, None, 2, 0)
+    (g,) = torch.autograd.grad(y, wt, gout.view(n, y.shape[2], y.shape[3], 64).permute(0, 3, 1, 2))
+    gw_kn.copy_(g.reshape(64, 147).t())
+
+
+@torch.enable_grad()
 def usot_conv2d_wgrad_nhwc(x, gout, n, h, w, cin, cout, kh, kw, stride, ph, pw, dh, dw, gw_kn, precision, stream):
     xx = x.view(n, h, w, cin).permute(0, 3, 1, 2).detach().clone()
     wt = torch.zeros(cout, cin, kh, kw, requires_grad=True)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "usot_weighted_bce": (_I, [_P, _P, _I, _P, _P]),
     "usot_iou_loss": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "usot_conv2d_wgrad_nhwc": (_I, [_P, _P] + [_I] * 12 + [_P, _I, _P]),
+    "usot_stem_conv_wgrad": (_I, [_P, _P, _I, _I, _P, _P]),
     "usot_pow2_scale": (_I, [_P, _I64, _I, _P, _P, _P]),
     "usot_conv2d_dgrad_nhwc": (_I, [_P, _P] + [_I] * 12 + [_P, _P]),
     "usot_bn_stats": (_I, [_P, _P, _I64, _I, _P, _P, _P]),

@@ -120,6 +120,76 @@ int launch_conv_wgrad(const float* x, const float* dy, const ConvGeom& g, float*
 }
 
 // =============================================================================================================================
+// stem wgrad: conv1 is 7x7 / stride 2 / pad 0 with Cin = 3 -- as a per-tap GEMM its M dimension would be 3 rows of a 64-row tile.  Here
+// (channel, tap) = 147 values form the M dimension instead (im2col on the fly from the NCHW image): dW[k][co] = sum_p patch[p][k] * dY[p][co],
+// k = (c*7 + kh)*7 + kw.  Block = a slab of output pixels; 256 threads = 16 (k groups of 10) x 16 (co groups of 4); chunks of 16 pixels
+// staged in shared memory; fp32 atomics into the (pre-zeroed) [147][64] result.
+// =============================================================================================================================
+constexpr int SW_K = 147, SW_KP = 160, SW_CHUNK = 16;
+
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x /*nchw (n,3,S,S)*/, const float* __restrict__ dy /*nhwc (n,HO,HO,64)*/,
+                                                         int S, int HO, int total_pix, int pix_per_block, float* __restrict__ dw /*[147][64]*/) {
+    __shared__ float As[SW_CHUNK][SW_KP];
+    __shared__ __align__(16) float Bs[SW_CHUNK][64];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int p_begin = blockIdx.x * pix_per_block, p_end = min(total_pix, p_begin + pix_per_block);
+    float acc[10][4];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int p0 = p_begin; p0 < p_end; p0 += SW_CHUNK) {
+        __syncthreads();
+        for (int i = tid; i < SW_CHUNK * SW_KP; i += 256) {
+            const int r = i / SW_KP, k = i - r * SW_KP, p = p0 + r;
+            float v = 0.f;
+            if (p < p_end && k < SW_K) {
+                const int n = p / (HO * HO), rem = p - n * HO * HO, oy = rem / HO, ox = rem - oy * HO;
+                const int c = k / 49, t = k - c * 49, kh = t / 7, kw = t - kh * 7;
+                v = __ldg(x + (((size_t)n * 3 + c) * S + oy * 2 + kh) * S + ox * 2 + kw);
+            }
+            As[r][k] = v;
+        }
+        for (int i = tid; i < SW_CHUNK * 16; i += 256) {
+            const int r = i >> 4, q = i & 15, p = p0 + r;
+            reinterpret_cast<float4*>(&Bs[r][0])[q] = p < p_end ? __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * 64) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < SW_CHUNK; ++r) {
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[r][tx * 4]);
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const float a = As[r][ty * 10 + i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a, bb[j], acc[i][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const int k = ty * 10 + i;
+        if (k >= SW_K) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(dw + (size_t)k * 64 + tx * 4 + j, acc[i][j]);
+    }
+}
+
+int launch_stem_wgrad(const float* x_nchw, const float* dy, int n, int S, float* dw_k64, cudaStream_t st) {
+    USOT_CUDA_OK(cudaMemsetAsync(dw_k64, 0, SW_K * 64 * sizeof(float), st));
+    const int HO = (S - 7) / 2 + 1, total = n * HO * HO;
+    if (total == 0) return 0;
+    int blocks = std::min(device_sm_count() * 4, (total + 255) / 256);
+    int ppb = (total + blocks - 1) / blocks;
+    ppb = (ppb + SW_CHUNK - 1) / SW_CHUNK * SW_CHUNK;
+    blocks = (total + ppb - 1) / ppb;
+    stem_wgrad_kernel<<<blocks, 256, 0, st>>>(x_nchw, dy, S, HO, total, ppb, dw_k64);
+    USOT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// =============================================================================================================================
 // generic conv dgrad (gather form): dX[n,y,x,ci] = sum_{taps hitting (y,x)} sum_co dY[n,oy,ox,co] * W[(t*cin+ci)][co]
 // Thread per (input pixel, ci).  Used for the thin prediction convs (cout 1 / 4); wide layers use the forward GEMM kernels.
 // =============================================================================================================================
@@ -204,6 +274,70 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(RedArgs a, double* __r
     }
 }
 
+// Vector variant (C % 4 == 0, C >= 16): a thread owns one float4 of channels, a warp reads 32 consecutive float4 = 512 contiguous bytes
+// of a row (or 2 / 4 shorter rows), rows are unrolled by two for memory-level parallelism.  Same partial-sum layout as above.
+__global__ void __launch_bounds__(256) chan_reduce_vec_kernel(RedArgs a, int qb /*float4 lanes along the channels: min(C/4, 32)*/,
+                                                              double* __restrict__ part) {
+    __shared__ double sm[256][9];   // (+1: bank spread)
+    const int tid = threadIdx.x, q = tid % qb, rl = tid / qb, rows = 256 / qb;
+    const int c4 = blockIdx.x * qb + q, C4 = a.C >> 2, c = c4 * 4;
+    const int m0 = blockIdx.y * a.slab, m1 = min(a.M, m0 + a.slab);
+    double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    if (c4 < C4) {
+        float b[4] = {0, 0, 0, 0}, mu[4] = {0, 0, 0, 0}, is[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 4; ++j) {
+            if (a.bias) b[j] = __ldg(a.bias + c + j);
+            if (a.mode == 1) { mu[j] = __ldg(a.mean + c + j); is[j] = __ldg(a.invstd + c + j); }
+        }
+        const float4* x4 = reinterpret_cast<const float4*>(a.x);
+        const float4* d4 = reinterpret_cast<const float4*>(a.dy);
+        const float4* y4 = reinterpret_cast<const float4*>(a.y);
+        auto accum = [&](const float4& xv, const float4& dv, const float4& yv) {
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (a.mode == 0) {
+                    const float v = xs[j] + b[j];
+                    s0[j] += (double)v; s1[j] += (double)v * (double)v;
+                } else if (a.mode == 1) {
+                    const float dz = (a.relu && !(ys[j] > 0.f)) ? 0.f : ds[j];
+                    const float xh = (xs[j] + b[j] - mu[j]) * is[j];
+                    s0[j] += (double)dz; s1[j] += (double)dz * (double)xh;
+                } else {
+                    s0[j] += (double)xs[j];
+                }
+            }
+        };
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int m = m0 + rl;
+        for (; m + rows < m1; m += 2 * rows) {
+            const size_t o0 = (size_t)m * C4 + c4, o1 = (size_t)(m + rows) * C4 + c4;
+            const float4 xa = __ldg(x4 + o0), xb = __ldg(x4 + o1);
+            const float4 da = a.mode == 1 ? __ldg(d4 + o0) : z4, db = a.mode == 1 ? __ldg(d4 + o1) : z4;
+            const float4 ya = (a.mode == 1 && a.relu) ? __ldg(y4 + o0) : z4, yb = (a.mode == 1 && a.relu) ? __ldg(y4 + o1) : z4;
+            accum(xa, da, ya);
+            accum(xb, db, yb);
+        }
+        if (m < m1) {
+            const size_t o0 = (size_t)m * C4 + c4;
+            accum(__ldg(x4 + o0), a.mode == 1 ? __ldg(d4 + o0) : z4, (a.mode == 1 && a.relu) ? __ldg(y4 + o0) : z4);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sm[tid][j] = s0[j]; sm[tid][4 + j] = s1[j]; }
+    __syncthreads();
+    if (rl == 0 && c4 < C4) {
+        for (int r = 1; r < rows; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s0[j] += sm[r * qb + q][j]; s1[j] += sm[r * qb + q][4 + j]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            part[((size_t)blockIdx.y * 2 + 0) * a.C + c + j] = s0[j];
+            part[((size_t)blockIdx.y * 2 + 1) * a.C + c + j] = s1[j];
+        }
+    }
+}
+
 // finalize: out0/out1 from the partial sums.  mode 0: mean, biased variance.  mode 1: dbeta (= sum dz), dgamma (= sum dz*xhat).  mode 2: sum.
 __global__ void chan_finalize_kernel(const double* __restrict__ part, int slabs, int C, int M, int mode, float* __restrict__ out0,
                                      float* __restrict__ out1) {
@@ -223,14 +357,17 @@ __global__ void chan_finalize_kernel(const double* __restrict__ part, int slabs,
 
 static int chan_reduce(RedArgs a, float* out0, float* out1, cudaStream_t st) {
     USOT_REQUIRE(a.M > 0 && a.C > 0, "empty reduction");
-    const int groups = (a.C + 31) / 32;
+    const bool vec = a.C % 4 == 0 && a.C >= 16 && (a.C / 4 <= 32 ? 256 % (a.C / 4) == 0 : true);
+    const int qb = vec ? std::min(a.C / 4, 32) : 0;
+    const int groups = vec ? (a.C / 4 + qb - 1) / qb : (a.C + 31) / 32;
     int slabs = std::max(1, std::min((device_sm_count() * 4 + groups - 1) / groups, (a.M + 63) / 64));
     a.slab = (a.M + slabs - 1) / slabs;
     slabs = (a.M + a.slab - 1) / a.slab;
     double* part = nullptr;
     ensure_async_pool();
     USOT_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)slabs * 2 * a.C * sizeof(double), st));
-    chan_reduce_kernel<<<dim3(groups, slabs), 256, 0, st>>>(a, part);
+    if (vec) chan_reduce_vec_kernel<<<dim3(groups, slabs), 256, 0, st>>>(a, qb, part);
+    else chan_reduce_kernel<<<dim3(groups, slabs), 256, 0, st>>>(a, part);
     chan_finalize_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(part, slabs, a.C, a.M, a.mode, out0, out1);
     USOT_CUDA_OK(cudaGetLastError());
     USOT_CUDA_OK(cudaFreeAsync(part, st));
@@ -485,6 +622,13 @@ int usot_conv2d_wgrad_nhwc(const float* in, const float* grad_out, int n, int h,
     if (precision != USOT_PREC_FP32_SIMT && wgrad_tc_supported(g))
         return launch_conv_wgrad_tc(in, grad_out, g, grad_weight_kn, precision == USOT_PREC_FP16X3_TC, (cudaStream_t)stream);
     return launch_conv_wgrad(in, grad_out, g, grad_weight_kn, (cudaStream_t)stream);
+}
+
+int usot_stem_conv_wgrad(const float* x, const float* grad_out, int n, int size, float* grad_weight_kn, void* stream) {
+    USOT_REQUIRE(grad_weight_kn && (n == 0 || (x && grad_out)), "null pointer");
+    USOT_REQUIRE(n >= 0 && size >= 7, "bad shape");
+    count_op_launch(OPFAM_WGRAD, 1);
+    return launch_stem_wgrad(x, grad_out, n, size, grad_weight_kn, (cudaStream_t)stream);
 }
 
 int usot_pow2_scale(const float* x, int64_t numel, int target_log2, float* y, float* scale2, void* stream) {

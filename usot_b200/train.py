@@ -217,8 +217,10 @@ class _StemConv(Function):
     @staticmethod
     def backward(ctx, g):
         (x_nchw,) = ctx.saved_tensors   # (the input image needs no gradient)
-        gw = conv_wgrad(to_nhwc(x_nchw), _c(g), (64, 3, 7, 7), 2, (0, 0), (1, 1))
-        return None, gw
+        n, _, s, _ = x_nchw.shape
+        gw = torch.empty((147, 64), dtype=torch.float32, device=x_nchw.device)
+        _lib_call("usot_stem_conv_wgrad", x_nchw.device, _lib.ptr(x_nchw), _lib.ptr(_c(g)), n, s, _lib.ptr(gw), _stream(x_nchw))
+        return None, gw.t().reshape(64, 3, 7, 7).contiguous()
 
 
 class _PredConv(Function):
