@@ -40,6 +40,25 @@ def _worker(rank, world, port, out):
         cls_l, bbox_l, _, _ = track_sharded(net, local["search"], gather=True)
         cls_f, bbox_f, _, _ = net.track(full["search"])
         assert torch.equal(cls_l, cls_f) and torch.equal(bbox_l, bbox_f)
+        # data-parallel TRAINING step (eval-mode BN so that shard and full batch see the same statistics): the all-reduced (mean) gradients
+        # of the two shards must equal the single-device gradients of the full batch
+        from usot_b200.dist import GradientReducer, train_step_sharded
+        red = GradientReducer(net.parameters(), bucket_mb=8.0)
+        l_local = train_step_sharded(net, local, red, None)
+        assert len(red.buckets) >= 4 and sorted(red.launch_order) == list(range(len(red.buckets)))
+        shard_grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+        red.close()
+        for p in net.parameters():
+            p.grad = None
+        lf = net(full["template"], full["search"], label=full["label"], reg_target=full["reg_target"], reg_weight=full["reg_weight"],
+                 template_bbox=full["template_bbox"], search_memory=full["search_memory"], search_bbox=full["search_bbox"], cls_ratio=0.4)
+        (lf[0] + lf[1] + lf[2]).backward()
+        worst = 0.0
+        for k, p in net.named_parameters():
+            den = float(p.grad.abs().max())
+            if den > 1e-8:
+                worst = max(worst, float((shard_grads[k] - p.grad).abs().max()) / den)
+        assert worst <= 2e-3, worst
         if rank == 0:
             out.put("ok")
     finally:

@@ -339,12 +339,19 @@ __global__ void __launch_bounds__(256) chan_reduce_vec_kernel(RedArgs a, int qb 
 }
 
 // finalize: out0/out1 from the partial sums.  mode 0: mean, biased variance.  mode 1: dbeta (= sum dz), dgamma (= sum dz*xhat).  mode 2: sum.
-__global__ void chan_finalize_kernel(const double* __restrict__ part, int slabs, int C, int M, int mode, float* __restrict__ out0,
-                                     float* __restrict__ out1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+__global__ void __launch_bounds__(256) chan_finalize_kernel(const double* __restrict__ part, int slabs, int C, int M, int mode, float* __restrict__ out0,
+                                                            float* __restrict__ out1) {
+    // block = 32 channels x 8 slab lanes: the (up to several hundred) per-slab partial sums of a channel are added by 8 threads in parallel
+    __shared__ double sm0[8][32], sm1[8][32];
+    const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     double s0 = 0.0, s1 = 0.0;
-    for (int s = 0; s < slabs; ++s) { s0 += part[((size_t)s * 2 + 0) * C + c]; s1 += part[((size_t)s * 2 + 1) * C + c]; }
+    if (c < C)
+        for (int s = sl; s < slabs; s += 8) { s0 += part[((size_t)s * 2 + 0) * C + c]; s1 += part[((size_t)s * 2 + 1) * C + c]; }
+    sm0[sl][cl] = s0; sm1[sl][cl] = s1;
+    __syncthreads();
+    if (sl != 0 || c >= C) return;
+    for (int i = 1; i < 8; ++i) { s0 += sm0[i][cl]; s1 += sm1[i][cl]; }
     if (mode == 0) {
         const double mean = s0 / M;
         out0[c] = (float)mean;
@@ -368,7 +375,7 @@ static int chan_reduce(RedArgs a, float* out0, float* out1, cudaStream_t st) {
     USOT_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)slabs * 2 * a.C * sizeof(double), st));
     if (vec) chan_reduce_vec_kernel<<<dim3(groups, slabs), 256, 0, st>>>(a, qb, part);
     else chan_reduce_kernel<<<dim3(groups, slabs), 256, 0, st>>>(a, part);
-    chan_finalize_kernel<<<(a.C + 127) / 128, 128, 0, st>>>(part, slabs, a.C, a.M, a.mode, out0, out1);
+    chan_finalize_kernel<<<(a.C + 31) / 32, 256, 0, st>>>(part, slabs, a.C, a.M, a.mode, out0, out1);
     USOT_CUDA_OK(cudaGetLastError());
     USOT_CUDA_OK(cudaFreeAsync(part, st));
     return 0;
