@@ -164,7 +164,7 @@ def workload_config(args):
         w = (f"USOT.track(x, template_mem, score_mem): batch={b} synthetic 255x255x3 search crops per GPU with a 7-entry memory queue per crop "
              "(full USOT* head: offline + memory branch, Conf_Fusion over N_q = 7) (BASELINE.json configs[2])")
     elif args.config == 4 and getattr(args, "train_step", False):
-        w = (f"cycle-memory TRAINING STEP (scripts/train_usot.py:196-236{', eager' if getattr(args, 'no_graph', False) else ', one CUDA-graph replay per step'}): USOT.forward in train() mode + loss.backward() + gradient all-reduce + SGD, "
+        w = (f"cycle-memory TRAINING STEP (scripts/train_usot.py:196-236{', eager' if getattr(args, 'no_graph', False) else ', one CUDA-graph replay per step' if (getattr(args, 'gpus', 1) == 1 or getattr(args, 'graph_nccl', False)) else ', eager'}): USOT.forward in train() mode + loss.backward() + gradient all-reduce + SGD, "
              f"{b} samples per GPU, 3 memory frames (= {b} templates + {4 * b} search-size crops per GPU per step) (BASELINE.json configs[3])")
     elif args.config == 4:
         w = (f"USOT.forward(...): cycle-memory training forward, {b} samples per GPU, 3 memory frames (= {b} templates + {4 * b} search-size crops per "
@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("USOT_B200_PRECISION", "fp16x3"), choices=["fp32", "fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-collective", action="store_true", help="N > 1: skip the cycle-forward all-gather record")
+    ap.add_argument("--graph-nccl", action="store_true", help="--train-step at N > 1: capture the step (NCCL all-reduces included) in a CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="--train-step: run the step eagerly instead of replaying a captured CUDA graph")
     ap.add_argument("--train-step", action="store_true", help="config 4: time the whole training step (forward + backward + gradient all-reduce + SGD), train()-mode BN")
     ap.add_argument("--tunable", action="append", default=[], help="name=value performance knob (usot_set_tunable), repeatable; A/B runs only")
@@ -298,6 +299,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    cleanup = []
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -320,6 +323,8 @@ def main():
     def finish(line):
         if rank == 0:
             print(json.dumps(line), flush=True)
+        for g in cleanup:   # captured graphs (they may hold NCCL work) go before the process group
+            g.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -426,9 +431,13 @@ def main():
             net.train()
             reducer = GradientReducer(net.parameters(), bucket_mb=25.0)
             optimizer = torch.optim.SGD(net.parameters(), lr=1e-6, momentum=0.9, weight_decay=1e-4)
-            if not args.no_graph:   # the eager step is host-bound (Python + ~5 000 launches): capture it once, replay per step
+            # The eager step is host-bound (Python + ~5 000 launches): capture it once, replay per step.  With N > 1 the captured graph contains
+            # the NCCL all-reduces; that works (2 GPUs: 85.8 vs 105.7 ms per step, profiles/r02_bench_2gpu_train_*.json) but the process hung in
+            # destroy_process_group with the graph alive, so multi-GPU runs stay eager unless --graph-nccl is given (graph reset before teardown).
+            if not args.no_graph and (world == 1 or args.graph_nccl):
                 from usot_b200.dist import GraphedTrainStep
                 graphed = GraphedTrainStep(net, reducer, optimizer, train_batch)
+                cleanup.append(graphed)
     else:
         net.template(z.to(dev), tb.to(dev))
 

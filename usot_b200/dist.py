@@ -234,6 +234,13 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.losses = train_step_sharded(net, self.static, reducer, optimizer, loss_weights, cls_ratio)
 
+    def close(self):
+        """Release the captured graph (do this before torch.distributed.destroy_process_group when the graph holds NCCL work)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
     def __call__(self, batch=None):
         if batch is not None:
             for k, v in batch.items():
