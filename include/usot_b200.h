@@ -119,6 +119,13 @@ USOT_API int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, con
                               int stride, int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift,
                               const float* residual, int relu, float* out, int precision, void* stream);
 
+/* The same conv with its INPUT multiplied by a device scalar first (tensor-core precisions only): the dgrad route of the training path,
+ * where `in` is a gradient map far below fp16's normal range, in_scale[0] = the power of two from usot_pow2_scale and `scale` carries its
+ * inverse.  The multiplication rides on the fp32 -> split-fp16 conversion (no extra pass, exact).  No residual, no ReLU. */
+USOT_API int usot_conv2d_nhwc_scaled(const float* in, const float* in_scale, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh,
+                                     int kw, int stride, int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift,
+                                     float* out, int precision, void* stream);
+
 /* Skinny prediction conv of the head: 3x3, pad 1, Cin = channels (256), Cout = 1 or 4, with bias, fused with the reference's
  * epilogue.  in (n,r,r,channels) nhwc; weight (9, cout, channels) with tap = kh*3+kw; out (n,cout,r,r) nchw.
  *   mode 0:  out = mul * (conv + bias)                          (`0.1 * cls_pred(x)`, connect.py:240-241,274-275)

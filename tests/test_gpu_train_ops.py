@@ -78,12 +78,12 @@ def test_pow2_scale():
     from usot_b200 import train
     for mag in (3e-9, 1.0, 700.0):
         x = torch.randn(4096, generator=torch.Generator().manual_seed(1)) * mag
-        g, inv = train._prescale(x.cuda(), 8)
+        g, inv, _ = train._prescale(x.cuda(), 8)
         m = float(g.abs().max())
         assert 1024.0 <= m < 2048.0
         s = 1.0 / float(inv[0])
         assert torch.equal(g.cpu(), x * s) and abs(torch.log2(torch.tensor(s)).item() - round(torch.log2(torch.tensor(s)).item())) == 0.0
-    g, inv = train._prescale(torch.zeros(64, device="cuda"), 4)
+    g, inv, _ = train._prescale(torch.zeros(64, device="cuda"), 4)
     assert float(inv[0]) == 1.0 and float(g.abs().max()) == 0.0
 
 

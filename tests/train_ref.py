@@ -17,7 +17,9 @@ import usot_oracle as O
 
 
 # ---- forward ops (tensor-level stand-ins for usot_b200.ops functions) -----------------------------------------------------------
-def conv2d_nhwc(x, weight_oihw, scale, shift, stride=1, padding=(0, 0), dilation=(1, 1), residual=None, relu=False, precision="fp32"):
+def conv2d_nhwc(x, weight_oihw, scale, shift, stride=1, padding=(0, 0), dilation=(1, 1), residual=None, relu=False, precision="fp32", in_scale=None):
+    if in_scale is not None:
+        x = x * in_scale
     y = F.conv2d(x.permute(0, 3, 1, 2), weight_oihw, None, stride, padding, dilation)
     y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     y = y.permute(0, 2, 3, 1)

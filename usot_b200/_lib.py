@@ -39,6 +39,7 @@ SIGNATURES = {
     "usot_xcorr_depthwise_backward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "usot_groupdw_xcorr": (_I, [_P] * 8 + [_I] * 5 + [_P]),
     "usot_conv2d_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _I, _P]),
+    "usot_conv2d_nhwc_scaled": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
     "usot_pred_conv": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, ctypes.c_float, _P, _P, _P, _P]),
     "usot_engine_track_frame": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_double, ctypes.c_double, _I, _P, _P, _P]),

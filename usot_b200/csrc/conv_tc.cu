@@ -726,10 +726,12 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
 // =============================================================================================
 // fp32 -> split-fp16 conversion (activations) and host-side weight packing
 // =============================================================================================
-__global__ void f32_to_split_kernel(const float4* __restrict__ in, size_t n4, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+__global__ void f32_to_split_kernel(const float4* __restrict__ in, size_t n4, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                                    const float* __restrict__ mul /*device scalar (a power of two) or null*/) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    const float4 v = __ldg(in + i);
+    float4 v = __ldg(in + i);
+    if (mul) { const float f = __ldg(mul); v.x *= f; v.y *= f; v.z *= f; v.w *= f; }
     const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
     const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
     const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
@@ -740,12 +742,12 @@ __global__ void f32_to_split_kernel(const float4* __restrict__ in, size_t n4, ui
     if (lo) lo[i] = b;
 }
 
-int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st) {
+int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st, const float* mul) {
     USOT_REQUIRE(n % 4 == 0, "f32_to_split: element count must be a multiple of 4");
     if (n == 0) return 0;
     const size_t n4 = n / 4;
     f32_to_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(in), n4, reinterpret_cast<uint2*>(hi),
-                                                                       reinterpret_cast<uint2*>(lo));
+                                                                       reinterpret_cast<uint2*>(lo), mul);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }

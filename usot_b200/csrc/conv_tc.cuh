@@ -61,7 +61,7 @@ int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuu
                 const cuuint32_t* box, int swizzle);
 extern Tunable g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
 int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st);
-int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st);
+int launch_f32_to_split(const float* in, size_t n, __half* hi, __half* lo, cudaStream_t st, const float* mul = nullptr);  // mul: device scalar
 int launch_split_to_f32(const __half* hi, const __half* lo /*or null*/, size_t n, float* out, cudaStream_t st);  // out = hi + lo
 int launch_pack_tc_weights(const float* w_kn, int K, int cout, const float* scale_in, __half* hi, __half* lo /*or null*/, float* scale_out,
                            cudaStream_t st);  // device-side twin of pack_tc_weights_host

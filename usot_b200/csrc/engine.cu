@@ -828,9 +828,29 @@ int usot_groupdw_xcorr(const float* x11, const float* x12, const float* x21, con
     return launch_groupdw(a, (cudaStream_t)stream);
 }
 
+static int conv2d_nhwc_impl(const float* in, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh, int kw, int stride,
+                            int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift, const float* residual,
+                            int relu, float* out, int precision, void* stream, const float* in_mul);
+
 int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh, int kw, int stride,
                      int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift, const float* residual,
                      int relu, float* out, int precision, void* stream) {
+    return conv2d_nhwc_impl(in, n, h, w, cin, weight_kn, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w, scale, shift, residual, relu, out, precision,
+                            stream, nullptr);
+}
+
+int usot_conv2d_nhwc_scaled(const float* in, const float* in_scale, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh, int kw,
+                            int stride, int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift, float* out,
+                            int precision, void* stream) {
+    USOT_REQUIRE(in_scale, "null in_scale");
+    USOT_REQUIRE(precision != USOT_PREC_FP32_SIMT, "usot_conv2d_nhwc_scaled is the tensor-core route (fp32 FMA needs no input scaling)");
+    return conv2d_nhwc_impl(in, n, h, w, cin, weight_kn, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w, scale, shift, nullptr, 0, out, precision, stream,
+                            in_scale);
+}
+
+static int conv2d_nhwc_impl(const float* in, int n, int h, int w, int cin, const float* weight_kn, int cout, int kh, int kw, int stride,
+                            int pad_h, int pad_w, int dil_h, int dil_w, const float* scale, const float* shift, const float* residual,
+                            int relu, float* out, int precision, void* stream, const float* in_mul) {
     USOT_REQUIRE(in && weight_kn && scale && shift && out, "null pointer");
     USOT_REQUIRE(precision >= USOT_PREC_FP32_SIMT && precision <= USOT_PREC_FP16_TC, "unknown precision mode");
     ConvGeom g{n, h, w, cin, cout, kh, kw, stride, pad_h, pad_w, dil_h, dil_w, conv_out(h, kh, stride, pad_h, dil_h),
@@ -867,7 +887,7 @@ int usot_conv2d_nhwc(const float* in, int n, int h, int w, int cin, const float*
     int rc = 0;
     do {
         if ((rc = launch_pack_tc_weights(weight_kn, K, cout, scale, d_whi, d_wlo, d_scale, st))) break;
-        if ((rc = launch_f32_to_split(in, n_in, d_ihi, d_ilo, st))) break;
+        if ((rc = launch_f32_to_split(in, n_in, d_ihi, d_ilo, st, in_mul))) break;
         if (residual) {
             d_rhi = reinterpret_cast<__half*>(take(n_out * 2));
             d_rlo = split ? reinterpret_cast<__half*>(take(n_out * 2)) : nullptr;

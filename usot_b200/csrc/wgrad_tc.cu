@@ -261,7 +261,7 @@ int launch_conv_wgrad_tc(const float* x, const float* dy, const ConvGeom& g, flo
     USOT_CUDA_OK(cudaMemsetAsync(dw_kn, 0, n_w * sizeof(float), st));
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
     const size_t planes = split ? 2 : 1;
-    const size_t bytes = planes * (al(n_x * 2) + al(n_y * 2)) + al(n_y * 4) + 256;
+    const size_t bytes = planes * (al(n_x * 2) + al(n_y * 2)) + 256;
     char* ws = nullptr;
     ensure_async_pool();
     USOT_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ws), bytes, st));
@@ -271,13 +271,12 @@ int launch_conv_wgrad_tc(const float* x, const float* dy, const ConvGeom& g, flo
     __half* x_lo = split ? reinterpret_cast<__half*>(take(n_x * 2)) : nullptr;
     __half* y_hi = reinterpret_cast<__half*>(take(n_y * 2));
     __half* y_lo = split ? reinterpret_cast<__half*>(take(n_y * 2)) : nullptr;
-    float* y_s = reinterpret_cast<float*>(take(n_y * 4));
     float* sc2 = reinterpret_cast<float*>(take(8));
     int rc = 0;
     do {
-        if ((rc = launch_pow2_scale(dy, n_y, 10, y_s, sc2, st))) break;          // |dY|_max -> [1024, 2048): far inside fp16's normal range
+        if ((rc = launch_pow2_scale(dy, n_y, 10, nullptr, sc2, st))) break;      // s with s*|dY|_max in [1024, 2048): far inside fp16's normal range
         if ((rc = launch_f32_to_split(x, n_x, x_hi, x_lo, st))) break;
-        if ((rc = launch_f32_to_split(y_s, n_y, y_hi, y_lo, st))) break;
+        if ((rc = launch_f32_to_split(dy, n_y, y_hi, y_lo, st, sc2))) break;     // the multiplication by s rides on the conversion (exact: power of two)
         WgParams p;
         memset(&p, 0, sizeof(p));
         choose_patch(g.ho, g.wo, &p.bw, &p.bh);

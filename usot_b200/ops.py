@@ -143,8 +143,9 @@ def groupdw_xcorr(x, z, weight, n_out=None):
     return out
 
 
-def conv2d_nhwc(x, weight_oihw, scale, shift, stride=1, padding=(0, 0), dilation=(1, 1), residual=None, relu=False, precision="fp32"):
-    """x NHWC (n,h,w,cin); weight in the reference's OIHW layout (repacked here); returns NHWC."""
+def conv2d_nhwc(x, weight_oihw, scale, shift, stride=1, padding=(0, 0), dilation=(1, 1), residual=None, relu=False, precision="fp32", in_scale=None):
+    """x NHWC (n,h,w,cin); weight in the reference's OIHW layout (repacked here); returns NHWC.  ``in_scale`` (1-element CUDA tensor,
+    tensor-core precisions only): x is multiplied by it inside the fp32 -> split-fp16 conversion (usot_conv2d_nhwc_scaled)."""
     _need_float(x, weight_oihw, scale, shift, residual)
     _need_cuda(x, weight_oihw, scale, shift, residual)
     n, h, w, cin = x.shape
@@ -156,6 +157,13 @@ def conv2d_nhwc(x, weight_oihw, scale, shift, stride=1, padding=(0, 0), dilation
     wo = (w + 2 * pw - dw * (kw - 1) - 1) // stride + 1
     w_kn = weight_oihw.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout).contiguous()
     out = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.device)
+    if in_scale is not None:
+        assert residual is None and not relu
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().usot_conv2d_nhwc_scaled(_lib.ptr(x.contiguous()), _lib.ptr(in_scale), n, h, w, cin, _lib.ptr(w_kn), cout, kh, kw, stride,
+                                                           ph, pw, dh, dw, _lib.ptr(scale.contiguous()), _lib.ptr(shift.contiguous()), _lib.ptr(out),
+                                                           _lib.PRECISIONS[precision], _stream(x)))
+        return out
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().usot_conv2d_nhwc(_lib.ptr(x.contiguous()), n, h, w, cin, _lib.ptr(w_kn), cout, kh, kw, stride, ph, pw, dh, dw,
                                                 _lib.ptr(scale.contiguous()), _lib.ptr(shift.contiguous()),

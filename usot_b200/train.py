@@ -117,21 +117,22 @@ def _wide(cin, cout, precision):
     return (cin % 64 == 0 and cout % 64 == 0) if precision != "fp32" else (cin % 16 == 0 and cout % 64 == 0)
 
 
-def _prescale(grad_out, n_scale_channels):
-    """(s * grad_out, per-channel vector 1/s) with s a power of two chosen on the device (no host sync)."""
-    g = torch.empty_like(grad_out)
+def _prescale(grad_out, n_scale_channels, materialise=True):
+    """Power of two s chosen on the device from max|grad_out| (no host sync).  Returns (s * grad_out or None, per-channel vector 1/s, s (1,))."""
+    g = torch.empty_like(grad_out) if materialise else None
     sc2 = torch.empty(2, dtype=torch.float32, device=grad_out.device)
     _lib_call("usot_pow2_scale", grad_out.device, _lib.ptr(grad_out), grad_out.numel(), GRAD_TARGET_LOG2, _lib.ptr(g), _lib.ptr(sc2), _stream(grad_out))
-    return g, sc2[1:2].expand(n_scale_channels).contiguous()
+    return g, sc2[1:2].expand(n_scale_channels).contiguous(), sc2[0:1]
 
 
 def _dgrad_gemm(grad_out, weight_oihw, pad, dil, precision):
-    """Stride-1 input gradient on the forward conv kernel (transposed, flipped filter); tensor-core modes pre-scale the gradient."""
+    """Stride-1 input gradient on the forward conv kernel (transposed, flipped filter).  Tensor-core modes: the gradient is multiplied by a
+    device-chosen power of two inside the fp32 -> split-fp16 conversion and the factor is divided out by the conv's per-channel scale."""
     if precision == "fp32":
         return ops.conv2d_nhwc_input_grad(grad_out, weight_oihw, pad, dil, precision=precision)
     w_t, pad_t = ops.dgrad_weights(weight_oihw, pad, dil)
-    g, inv = _prescale(grad_out, w_t.shape[0])
-    return ops.conv2d_nhwc(g, w_t, inv, torch.zeros_like(inv), stride=1, padding=pad_t, dilation=dil, precision=precision)
+    _, inv, s = _prescale(grad_out, w_t.shape[0], materialise=False)
+    return ops.conv2d_nhwc(grad_out, w_t, inv, torch.zeros_like(inv), stride=1, padding=pad_t, dilation=dil, precision=precision, in_scale=s)
 
 
 def conv_dgrad(grad_out, weight_oihw, in_hw, stride, pad, dil, precision="fp32"):
