@@ -74,6 +74,9 @@ USOT_API int usot_profile_reset(int on);
 USOT_API int usot_profile_family_count(void);
 USOT_API const char* usot_profile_family_name(int family);
 USOT_API int usot_profile_read(int family, double* out);
+/* Adds `launches` to a family's counter: for replays of a CUDA graph the CALLER captured around this library's calls (the launchers only
+ * see the capture, not the replays). */
+USOT_API int usot_profile_count(int family, int64_t launches);
 
 /* ------------------------------- stand-alone operators ------------------------------------------------ */
 

@@ -79,6 +79,7 @@ def test_cuda_graphed_training_step_matches_eager_steps():
     eager = [torch.stack(train_step_sharded(net_e, batch, red_e, opt_e)).cpu() for _ in range(5)]
     net_g, red_g, opt_g = make()
     gstep = GraphedTrainStep(net_g, red_g, opt_g, batch, warmup=3)      # 3 eager warm-up steps + 1 captured (not executed) step
+    assert sum(gstep.launches.values()) > 1000 and gstep.launches["conv_wgrad"] > 100    # launches of this library recorded into the graph
     graphed = [torch.stack(gstep(batch)).cpu().clone() for _ in range(2)]   # = steps 4 and 5
     for a, b in zip(eager[3:], graphed):
         assert torch.allclose(a, b, rtol=2e-4, atol=1e-6), (a, b)

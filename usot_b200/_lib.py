@@ -32,6 +32,7 @@ SIGNATURES = {
     "usot_profile_family_count": (_I, []),
     "usot_profile_family_name": (ctypes.c_char_p, [_I]),
     "usot_profile_read": (_I, [_I, ctypes.POINTER(ctypes.c_double)]),
+    "usot_profile_count": (_I, [_I, _I64]),
     "usot_prroi_pool_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "usot_prroi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "usot_prroi_pool_coor_backward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P]),
@@ -127,6 +128,15 @@ def ptr(t):
 
 def profile_reset(on=False):
     check(load().usot_profile_reset(1 if on else 0))
+
+
+def profile_count(counts):
+    """Add {family name: launches} to the library's counters (replays of a caller-captured CUDA graph)."""
+    lib = load()
+    names = {lib.usot_profile_family_name(i).decode(): i for i in range(lib.usot_profile_family_count())}
+    for k, n in counts.items():
+        if n:
+            check(lib.usot_profile_count(names[k], int(n)))
 
 
 def profile_read():

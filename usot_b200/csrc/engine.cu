@@ -748,6 +748,13 @@ int usot_profile_reset(int on) {
     return 0;
 }
 int usot_profile_family_count(void) { return FAM_COUNT; }
+/* Account for launches that did not pass through the library's launchers: a replay of a CUDA graph captured by the CALLER (the graphed
+ * training step) launches the kernels recorded at capture time; the caller adds those per-family counts after each replay. */
+int usot_profile_count(int fam, int64_t launches) {
+    USOT_REQUIRE(fam >= 0 && fam < FAM_COUNT, "bad family");
+    count_launches(fam, (long long)launches);
+    return 0;
+}
 const char* usot_profile_family_name(int fam) { return (fam >= 0 && fam < FAM_COUNT) ? kFamNames[fam] : ""; }
 /* Synchronises the device.  out[4] = {launches, milliseconds (0 unless profiling was on), algorithmic FLOPs, algorithmic bytes}. */
 int usot_profile_read(int fam, double* out) {

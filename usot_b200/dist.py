@@ -230,9 +230,14 @@ class GraphedTrainStep:
                 train_step_sharded(net, self.static, reducer, optimizer, loss_weights, cls_ratio)
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        from . import _lib
+        before = {k: v["launches"] for k, v in _lib.profile_read().items()}
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.losses = train_step_sharded(net, self.static, reducer, optimizer, loss_weights, cls_ratio)
+        # launches of this library recorded into the graph, per kernel family: the capture itself executed nothing, every replay runs them all
+        self.launches = {k: v["launches"] - before[k] for k, v in _lib.profile_read().items()}
+        _lib.profile_count({k: -n for k, n in self.launches.items()})
 
     def close(self):
         """Release the captured graph (do this before torch.distributed.destroy_process_group when the graph holds NCCL work)."""
@@ -247,4 +252,6 @@ class GraphedTrainStep:
                 if torch.is_tensor(v) and v.data_ptr() != self.static[k].data_ptr():
                     self.static[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        from . import _lib
+        _lib.profile_count(self.launches)
         return self.losses
