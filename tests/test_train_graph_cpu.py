@@ -121,3 +121,63 @@ def test_tensor_core_backward_route_prescales_and_unscales_exactly():
         c = train.conv_dgrad(gy[:, :4, :4].contiguous(), wt, (9, 9), 2, 0, 1, precision="fp16x3")
         d = train.conv_dgrad(gy[:, :4, :4].contiguous(), wt, (9, 9), 2, 0, 1, precision="fp32")
     assert torch.allclose(a, b, rtol=1e-5, atol=1e-14) and torch.allclose(c, d, rtol=1e-5, atol=1e-14)
+
+
+def test_naive_siamese_branch_and_partly_frozen_backbone_follow_torch_semantics():
+    """search_memory=None (models.py:288-295) with the reference's freezing recipe (scripts/train_usot.py:74-102): layer1 / layer2 / stem frozen
+    (requires_grad False, their BatchNorms in eval()), everything else in train().  Gradients must match the oracle run the same way, frozen
+    parameters must get none, and only the train()-mode BatchNorms may update their running statistics."""
+    from usot_b200 import USOT
+    sd = load_weights("damp025")
+    net = USOT({"mem_size": 2, "pr_pool": True}, precision="fp32")
+    net.load_state_dict(sd, strict=True)
+    net.train()
+    frozen = ("features.features.conv1", "features.features.bn1", "features.features.layer1", "features.features.layer2")
+    for k, p in net.named_parameters():
+        if k.startswith(frozen):
+            p.requires_grad_(False)
+    for k, m in net.named_modules():
+        if isinstance(m, torch.nn.BatchNorm2d) and k.startswith(frozen):
+            m.eval()
+    z, x, tb, sb, smem, label, reg_target, reg_weight = _inputs(2, 2)
+    before = {k: v.clone() for k, v in net.state_dict().items() if k.endswith("running_mean")}
+    with train_ref.install():
+        from usot_b200 import train
+        cls_loss, none, reg_loss = train.forward_train(net, z, x, label, reg_target, reg_weight, tb)   # (USOT.forward itself refuses CPU tensors)
+        assert none is None
+        (cls_loss + reg_loss).backward()
+    # oracle with the same mixed BatchNorm modes: batch statistics only where the module is in train()
+    params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var")) and not k.startswith(frozen))
+              for k, v in sd.items()}
+    orig_bn = O._bn
+
+    def mixed_bn(sd_, t, p):
+        O._CAL.on = not p.startswith(frozen)
+        try:
+            return orig_bn(sd_, t, p)
+        finally:
+            O._CAL.on = False
+
+    O._bn = mixed_bn
+    try:
+        lo = O.forward_train(params, z, x, label, reg_target, reg_weight, tb)
+    finally:
+        O._bn = orig_bn
+    (lo[0] + lo[2]).backward()
+    assert abs(float(cls_loss) - float(lo[0])) <= 1e-5 * abs(float(lo[0])) and abs(float(reg_loss) - float(lo[2])) <= 1e-5 * abs(float(lo[2]))
+    checked = 0
+    for k, p in net.named_parameters():
+        if k.startswith(frozen):
+            assert p.grad is None
+            continue
+        ref = params[k].grad
+        if ref is None or float(ref.abs().max()) < 1e-7:
+            continue
+        # (the three GroupDW weights sit behind a softmax: their gradient is a difference of large, nearly equal sums -- rounding-noise dominated)
+        tol = 0.15 if k.endswith("_dw.weight") else 1e-2
+        assert abs(float(p.grad.norm()) - float(ref.norm())) <= tol * float(ref.norm()), k
+        checked += 1
+    assert checked > 100
+    moved = {k for k, v in before.items() if not torch.equal(v, net.state_dict()[k])}
+    assert moved and all(not k.startswith(frozen) for k in moved)
+    assert all((k in moved) for k in before if k.startswith("features.features.layer3"))

@@ -239,7 +239,7 @@ class USOT_(nn.Module):
                 raise RuntimeError("usot_b200.USOT runs on CUDA only (call .cuda() first); there is no CPU fallback")
             from . import train
             return train.forward_train(self, template, search, label, reg_target, reg_weight, template_bbox, search_memory, search_bbox,
-                                       cls_ratio, train=self.training)
+                                       cls_ratio)   # every BatchNorm follows its own .training flag, like torch
         eng = self._engine(search.device)
         zf, _ = eng.template(template, template_bbox if self.pr_pool else None)
         pending = zf_exchange(zf) if zf_exchange is not None else None

@@ -39,10 +39,16 @@ GRAD_TARGET_LOG2 = 10
 
 
 class Mode:
-    """How one forward_train call runs: BatchNorm flavour and the arithmetic of the forward convs (the façade's precision mode)."""
+    """How one forward_train call runs: the arithmetic of the forward convs (the façade's precision mode) and the BatchNorm flavour.
+    ``train=None`` (default): every BatchNorm follows ITS OWN ``module.training`` flag, exactly like torch -- the reference freezes backbone
+    layers by putting their BatchNorms in eval() (scripts/train_usot.py:74-102) and then calls ``model.train()`` (:153); both states behave
+    here as they do there.  ``train=True / False`` forces one flavour for the whole call."""
 
     def __init__(self, train, precision):
-        self.train, self.precision = bool(train), precision
+        self.train, self.precision = (None if train is None else bool(train)), precision
+
+    def bn_train(self, bn):
+        return bn.training if self.train is None else self.train
 
 
 def _c(t):
@@ -416,19 +422,19 @@ def _bottleneck(blk, x, stride, dilation, has_down, down_k, down_stride, down_pa
     if dil2 > 1:
         pad2 = dil2
     P = md.precision
-    out = batchnorm(_Conv.apply(x, blk.conv1.weight, 1, 0, 1, P), blk.bn1, relu=True, train=md.train)
-    out = batchnorm(_Conv.apply(out, blk.conv2.weight, stride, pad2, dil2, P), blk.bn2, relu=True, train=md.train)
+    out = batchnorm(_Conv.apply(x, blk.conv1.weight, 1, 0, 1, P), blk.bn1, relu=True, train=md.bn_train(blk.bn1))
+    out = batchnorm(_Conv.apply(out, blk.conv2.weight, stride, pad2, dil2, P), blk.bn2, relu=True, train=md.bn_train(blk.bn2))
     out = _Conv.apply(out, blk.conv3.weight, 1, 0, 1, P)
     residual = x
     if has_down:
-        residual = batchnorm(_Conv.apply(x, blk.downsample[0].weight, down_stride, down_pad, 1, P), blk.downsample[1], train=md.train)
-    return batchnorm(out, blk.bn3, residual=residual, relu=True, train=md.train)
+        residual = batchnorm(_Conv.apply(x, blk.downsample[0].weight, down_stride, down_pad, 1, P), blk.downsample[1], train=md.bn_train(blk.downsample[1]))
+    return batchnorm(out, blk.bn3, residual=residual, relu=True, train=md.bn_train(blk.bn3))
 
 
 def backbone_neck(net, x_nchw, md):
     """feature_extractor + neck (lib/models/modules.py:137-151, connect.py:294-296): (n,3,S,S) image -> NHWC (n,F,F,256)."""
     f = net.features.features
-    x = batchnorm(_StemConv.apply(x_nchw, f.conv1.weight), f.bn1, relu=True, train=md.train)
+    x = batchnorm(_StemConv.apply(x_nchw, f.conv1.weight), f.bn1, relu=True, train=md.bn_train(f.bn1))
     x = _MaxPool.apply(x)
     for lname, blocks, stride, dilation in _LAYERS:
         layer = getattr(f, lname)
@@ -441,7 +447,7 @@ def backbone_neck(net, x_nchw, md):
                 x = _bottleneck(layer[i], x, stride, dilation, True, dk, stride, dpad, md)
             else:
                 x = _bottleneck(layer[i], x, 1, dilation, False, 0, 1, 0, md)
-    return batchnorm(_Conv.apply(x, net.neck.downsample[0].weight, 1, 0, 1, md.precision), net.neck.downsample[1], train=md.train)
+    return batchnorm(_Conv.apply(x, net.neck.downsample[0].weight, 1, 0, 1, md.precision), net.neck.downsample[1], train=md.bn_train(net.neck.downsample[1]))
 
 
 def prpool_feature(feat_nhwc, boxes):
@@ -454,7 +460,7 @@ def prpool_feature(feat_nhwc, boxes):
 
 def _cbr(seq, x, dil, pad, md):
     conv, bn = seq[0], seq[1]
-    return batchnorm(_Conv.apply(x, conv.weight, 1, pad, dil, md.precision), bn, conv_bias=conv.bias, relu=True, train=md.train)
+    return batchnorm(_Conv.apply(x, conv.weight, 1, pad, dil, md.precision), bn, conv_bias=conv.bias, relu=True, train=md.bn_train(bn))
 
 
 def _matrix_encode(enc, z, x, md):
@@ -477,7 +483,7 @@ def _groupdw(dw, zs, xs):
 def _tower(seq, x, md):
     for i in range(4):
         conv, bn = seq[3 * i], seq[3 * i + 1]
-        x = batchnorm(_Conv.apply(x, conv.weight, 1, 1, 1, md.precision), bn, conv_bias=conv.bias, relu=True, train=md.train)
+        x = batchnorm(_Conv.apply(x, conv.weight, 1, 1, 1, md.precision), bn, conv_bias=conv.bias, relu=True, train=md.bn_train(bn))
     return x
 
 
@@ -514,9 +520,9 @@ def connect(head, md, search, kernel=None, memory_kernel=None, memory_confidence
 
 def forward_train(net, template, search, label, reg_target, reg_weight, template_bbox, search_memory=None, search_bbox=None, cls_ratio=0.40,
                   train=None):
-    """USOT_.forward (lib/models/models.py:208-295) with an autograd graph.  ``train`` (default ``net.training``) selects batch-statistics
-    BatchNorm.  Returns (cls_loss, cls_memory_loss or None, reg_loss), 0-d tensors that support ``.backward()``."""
-    md = Mode(net.training if train is None else train, getattr(net, "precision", "fp16x3"))
+    """USOT_.forward (lib/models/models.py:208-295) with an autograd graph.  ``train=None`` (default): each BatchNorm follows its own
+    ``.training`` flag like torch; ``True`` / ``False`` force batch / running statistics everywhere.  Returns (cls_loss, cls_memory_loss or None, reg_loss), 0-d tensors that support ``.backward()``."""
+    md = Mode(train, getattr(net, "precision", "fp16x3"))
     head = net.connect_model
     dev = search.device
     f32 = lambda t: None if t is None else t.to(dev, torch.float32)
