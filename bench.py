@@ -528,12 +528,20 @@ def main():
         sampler.stop()
 
     # ---- N > 1: the one collective of this path (z_f all-gather of the cycle-memory forward), on the same ranks ----
-    collective = None
+    collective = collective_train = None
     if world > 1 and not args.no_collective:
         if args.config == 4 and args.train_step:
             collective = grad_allreduce_record(dist, net, reducer, dict(train_batch), timed, world)
         else:
             collective = collective_record(args, dist, dev, rank, world, sd, timed)
+            if args.config == 2:
+                # ... and the collective of the TRAINING step (gradient all-reduce), measured on the same ranks with a short eager run of
+                # BASELINE config 4 as a training step, so that the scaling record carries both collectives of this path.  A failure here must
+                # not cost the headline line: it is reported as a string instead.
+                try:
+                    collective_train = train_collective_record(args, dist, dev, rank, world, sd, timed)
+                except Exception as e:  # noqa: BLE001
+                    collective_train = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     line = None
     if rank == 0:
@@ -590,6 +598,8 @@ def main():
         }
         if collective is not None:
             line["collective"] = collective
+        if collective_train is not None:
+            line["collective_train"] = collective_train
         if not args.no_cpu_baseline and args.config in (2, 3):
             sample = 64
             cpu = CpuReference(nq=7 if args.config == 3 else 0)
@@ -631,6 +641,33 @@ def grad_allreduce_record(dist, net, reducer, batch, timed, world):
             "ms_per_step_overlapped": t_with / steps, "ms_per_step_no_collective": t_without / steps,
             "exposed_ms": (t_with - t_without) / steps, "allreduce_alone_ms": t_ar,
             "allreduce_bus_gbs": 2.0 * (world - 1) / world * nbytes / (t_ar / 1e3) / 1e9}
+
+
+def train_collective_record(args, dist, dev, rank, world, sd, timed):
+    """BASELINE config 4 as a TRAINING step on these ranks (16 samples + 3 memory frames per GPU, train()-mode BatchNorm, eager): step time
+    with the bucketed gradient all-reduce overlapped with backward vs without it, and the all-reduce of all buckets alone."""
+    from usot_b200 import USOT
+    from usot_b200.dist import GradientReducer
+    from usot_b200.synth import synthetic_inputs
+    B, M = 16, 3
+    net = USOT({"mem_size": M, "pr_pool": True}, precision=args.precision)
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    z, x, tb, sb = synthetic_inputs(300 + rank, B, n_templates=B)
+    g = torch.Generator().manual_seed(400 + rank)
+    label = torch.zeros(B, 25, 25)
+    label[:, 10:15, 10:15] = 1.0
+    rw = torch.zeros(B, 25, 25)
+    rw[:, 11:14, 11:14] = 1.0
+    batch = dict(template=z, search=x, search_memory=torch.rand(B, M, 3, 255, 255, generator=g) * 255.0, label=label,
+                 reg_target=torch.rand(B, 25, 25, 4, generator=g) * 40 + 5, reg_weight=rw, template_bbox=tb, search_bbox=sb)
+    batch = {k: v.to(dev) for k, v in batch.items()}
+    reducer = GradientReducer(net.parameters(), bucket_mb=25.0)
+    rec = grad_allreduce_record(dist, net, reducer, batch, timed, world)
+    rec["workload"] = f"cycle-memory training step, {B} samples + {M} memory frames per GPU, global batch {B * world}, eager (no CUDA graph)"
+    rec["samples_per_s"] = B * world / rec["ms_per_step_overlapped"] * 1e3
+    reducer.close()
+    return rec
 
 
 def collective_record(args, dist, dev, rank, world, sd, timed):
