@@ -21,6 +21,7 @@
  *   usot_groupdw_xcorr               <- GroupDW.forward                  lib/models/connect.py:86-102
  *   usot_conv2d_nhwc                 <- nn.Conv2d + BatchNorm2d (+ReLU)  lib/models/modules.py:37-58, connect.py:20-53
  *   usot_stem_conv / usot_maxpool3x3s2p1_nhwc <- conv1+bn1+relu / maxpool of ResNet_plus2   lib/models/modules.py:70-75,138-141
+ *   usot_stem_maxpool                         <- the same four modules as one fused kernel   lib/models/modules.py:70-75,138-141
  *   usot_conf_fusion                 <- Conf_Fusion.forward (reduction)  lib/models/connect.py:123-144
  *   usot_cycle_glue                  <- forward-track argmax + box maps  lib/models/models.py:131-162,262-274
  *   usot_weighted_bce / usot_iou_loss <- _weighted_BCE / add_iouloss    lib/models/models.py:42-100
@@ -157,6 +158,13 @@ USOT_API int usot_maxpool3x3s2p1_nhwc(const float* in, int n, int h, int w, int 
  * test/debug entry, which synchronises `stream`); out (n,HO,HO,64) nhwc fp32, HO = (size-7)/2+1.  precision = USOT_PREC_*. */
 USOT_API int usot_stem_conv(const float* x, int n, int size, const float* host_weight_oihw, const float* host_scale, const float* host_shift,
                             float* out, int precision, void* stream);
+
+/* conv1 + folded BN + ReLU + MaxPool 3x3/2 p1 as the engine runs them in the tensor-core modes (lib/models/modules.py:70-75,138-141): ONE
+ * TMA-fed tcgen05 implicit GEMM over the space-to-depth image with the pooling in its epilogue.  Arguments as usot_stem_conv; size <= 261;
+ * precision = USOT_PREC_FP16X3_TC or USOT_PREC_FP16_TC; out (n,PO,PO,64) nhwc fp32 = hi + lo of the split-fp16 planes the kernel writes,
+ * PO = (HO-1)/2+1.  Test/debug entry: packs and uploads the weights itself and synchronises `stream`. */
+USOT_API int usot_stem_maxpool(const float* x, int n, int size, const float* host_weight_oihw, const float* host_scale, const float* host_shift,
+                               float* out, int precision, void* stream);
 
 /* The bare stem convolution (7x7 / stride 2 / pad 0, 3 -> 64, no bias, no BN, no ReLU) in fp32 FMA arithmetic: the training path's conv1,
  * which is followed by train-mode BatchNorm (usot_bn_*).  x (n,3,size,size) nchw; weight_kn (147, 64) DEVICE pointer with

@@ -31,6 +31,27 @@ def test_stem_conv_vs_oracle(precision, tol, size, n):
     assert err <= tol
 
 
+@pytest.mark.parametrize("precision,tol", [("fp16x3", 2e-5), ("fp16", 4e-3)])
+@pytest.mark.parametrize("size,n", [(127, 1), (127, 9), (255, 1), (255, 3), (255, 40), (261, 2), (191, 5), (63, 2)])
+def test_fused_stem_maxpool_vs_oracle(precision, tol, size, n):
+    """conv1 + bn1 + relu + maxpool (lib/models/modules.py:138-141) as ONE tcgen05 kernel over the space-to-depth image (overlapping-row
+    TMA view = im2col, pooling in the epilogue), for every band plan these batch sizes select, against the fp32 oracle."""
+    from usot_b200 import ops
+    sd = load_weights("damp025")
+    p = "features.features."
+    g = torch.Generator().manual_seed(700 + size + n)
+    x = torch.rand(n, 3, size, size, generator=g) * 255.0
+    with torch.no_grad():
+        ref = F.max_pool2d(F.relu(O._bn(sd, O._conv(sd, x, p + "conv1", 2, 0), p + "bn1")), 3, 2, 1)
+    scale = sd[p + "bn1.weight"].double() / torch.sqrt(sd[p + "bn1.running_var"].double() + 1e-5)
+    shift = sd[p + "bn1.bias"].double() - sd[p + "bn1.running_mean"].double() * scale
+    out = ops.stem_maxpool(x.cuda(), sd[p + "conv1.weight"], scale.float(), shift.float(), precision)
+    assert tuple(out.shape) == tuple(ref.permute(0, 2, 3, 1).shape)
+    err = rel_err(out.permute(0, 3, 1, 2), ref)
+    print("stem+pool", precision, size, n, f"{err:.2e}")
+    assert err <= tol
+
+
 @pytest.mark.parametrize("shape", [(2, 125, 125, 64), (1, 61, 61, 64), (3, 8, 7, 16), (1, 1, 1, 4), (2, 2, 5, 8)])
 def test_maxpool_fp32_is_exact_and_split_rounds_like_fp16x2(shape):
     from usot_b200 import ops

@@ -46,6 +46,7 @@ SIGNATURES = {
                                      ctypes.c_double, ctypes.c_double, _I, _P, _P, _P]),
     "usot_maxpool3x3s2p1_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "usot_stem_conv": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "usot_stem_maxpool": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P]),
     "usot_stem_conv_raw": (_I, [_P, _I, _I, _P, _P, _P]),
     "usot_conf_fusion": (_I, [_P, _P, _I, _I, _I64, _P, _P]),
     "usot_cycle_glue": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),

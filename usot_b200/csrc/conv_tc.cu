@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <mutex>
 #include <unordered_map>
@@ -67,7 +68,40 @@ struct TcCfg {
     static constexpr int STAGES_RES = (227 * 1024 - MISC_BYTES - TC_EPI_GROUPS * 3 * BUF_BYTES) / STAGE_BYTES;
 };
 
-template <int BN, bool SPLIT>
+// One index of the persistent tile loop is a SEQUENCE of `count` accumulator tiles that the same CTA walks back to back:
+//   ordinary conv            count = 1
+//   fused Conf_Fusion        the p.group (= N_q) memory maps of one sample for a fixed (patch, N block): image advances
+//   fused stem + max-pool    the conv rows first..last that one band of pooled rows of one image needs: the tile row advances
+struct TileSeq { int nb, tw, th, img, count, dth, dimg; };
+static __device__ __forceinline__ TileSeq decode_seq(const TcParams& p, int tile) {
+    TileSeq s;
+    if (p.pool_bands > 0) {
+        const int band = tile % p.pool_bands;
+        const int p0 = band * p.pool_band_rows, p1 = min(p.pool_po, p0 + p.pool_band_rows);
+        const int first = p0 > 0 ? 2 * p0 - 1 : 0, last = min(2 * p1 - 1, p.ho - 1);   // pooled row py reads conv rows 2py-1 .. 2py+1
+        s.nb = 0; s.tw = 0; s.th = first; s.img = tile / p.pool_bands; s.count = last - first + 1; s.dth = 1; s.dimg = 0;
+        return s;
+    }
+    s.nb = tile % p.n_tiles_n;
+    int mt = tile / p.n_tiles_n;
+    s.tw = mt % p.tiles_w; mt /= p.tiles_w;
+    s.th = mt % p.tiles_h;
+    s.img = (mt / p.tiles_h) * p.group;
+    s.count = p.group; s.dth = 0; s.dimg = 1;
+    return s;
+}
+
+// EPI = 0: the ordinary epilogue (scale/shift, residual, ReLU -> split-fp16 / fp32 maps).
+// EPI = 2: fused stem + max-pool 3x3/2 p1 (modules.py:70-74,138-141).  The stem runs as a TMA-fed implicit GEMM over the space-to-depth
+//          image (see launch_stem_s2d_pool); a tile is ONE conv row (bh = 1), a CTA walks the rows of a band top to bottom, every epilogue
+//          thread (pixel, 32 channels) keeps the running vertical maximum in registers, and every second row the row of vertical maxima
+//          goes through a swizzled shared-memory buffer for the horizontal 3-tap / stride-2 maximum and leaves as the split-fp16 operand
+//          planes layer1 reads.  The (n, 125, 125, 64) conv map never exists in HBM.
+// EPI = 1: fused Conf_Fusion (connect.py:123-144).  The weight tile of N-block nb holds BN/2 channels of conf_gen followed by the SAME
+//          BN/2 channels of value_gen, a CTA walks the p.group (= N_q) memory maps of one sample back to back for a fixed (patch, nb),
+//          and the epilogue warps keep  sum_q e_q * v_q  and  sum_q e_q  (e = exp(clamp(conf)), v = value) in registers: neither the
+//          confidence nor the value maps ever reach HBM.  Same arithmetic, in the same order, as the two convs + conf_fusion_kernel.
+template <int BN, bool SPLIT, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, SPLIT>;
     const int STAGES = p.stages;
@@ -123,12 +157,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int nb = tile % p.n_tiles_n;
-                int mt = tile / p.n_tiles_n;
-                const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-                const int th = mt % p.tiles_h;
-                const int img = mt / p.tiles_h;
-                const int h0 = th * p.bh, w0 = tw * p.bw;
+                const TileSeq sq = decode_seq(p, tile);
+                const int nb = sq.nb, w0 = sq.tw * p.bw;
+                for (int q = 0; q < sq.count; ++q) {   // (count == 1 except in the fused Conf_Fusion / stem + max-pool launches)
+                const int img = sq.img + q * sq.dimg;
+                const int h0 = (sq.th + q * sq.dth) * p.bh;
                 for (int ks = 0; ks < nK; ++ks) {
                     const int tap = ks / p.cin_chunks, cc = ks - tap * p.cin_chunks;
                     const int kh = tap / p.kw, kwi = tap - kh * p.kw;
@@ -144,18 +177,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     mbar_expect_tx(full, tx);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::PLANES * TC_A_BYTES;
-                    tma_load_4d(sa, &p.a[0][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
-                    tma_load_2d(sb, &p.b[0], full, ks * TC_BK, nb * BN);
-                    if (SPLIT) {
-                        tma_load_4d(sa + TC_A_BYTES, &p.a[1][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
-                        tma_load_2d(sb + Cfg::B_BYTES, &p.b[1], full, ks * TC_BK, nb * BN);
+                    if (EPI == 2 && p.a_rank5) {
+                        tma_load_5d(sa, &p.a[0][0], full, 0, 0, w0 + offw, h0 + offh, img);
+                        if (SPLIT) tma_load_5d(sa + TC_A_BYTES, &p.a[1][0], full, 0, 0, w0 + offw, h0 + offh, img);
+                    } else {
+                        tma_load_4d(sa, &p.a[0][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
+                        if (SPLIT) tma_load_4d(sa + TC_A_BYTES, &p.a[1][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
                     }
+                    tma_load_2d(sb, &p.b[0], full, ks * TC_BK, nb * BN);
+                    if (SPLIT) tma_load_2d(sb + Cfg::B_BYTES, &p.b[1], full, ks * TC_BK, nb * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
                 }
                 // DRAM-bound 1x1 layers (K <= 1024, ring only 2-4 stages deep): once every load of THIS tile is queued, pull the NEXT
                 // tile's activation boxes into L2 (hints queue behind the demand loads), so its ring loads are L2 hits; every byte
                 // is still fetched from HBM once.  (3x3 layers re-read A from L2 per tap anyway.)
-                if (p.l2_prefetch && p.taps == 1 && p.stride == 1 && nb == p.n_tiles_n - 1) {
+                if (p.l2_prefetch && p.group == 1 && p.pool_bands == 0 && p.taps == 1 && p.stride == 1 && nb == p.n_tiles_n - 1) {
                     const int nt = tile + gridDim.x;  // same M tile is shared by the n_tiles_n consecutive tiles: prefetch once
                     if (nt < p.num_tiles) {
                         int mt2 = nt / p.n_tiles_n;
@@ -182,7 +219,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            for (int q = 0, count = decode_seq(p, tile).count; q < count; ++q, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
@@ -217,6 +255,185 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         }
     } else if (warp >= 4) {
+      if constexpr (EPI == 1) {
+        // ================================ epilogue: fused Conf_Fusion ================================
+        // Columns [0, BN/2) of the tile are conf_gen channels nb*BN/2 + j, columns [BN/2, BN) the same channels of value_gen.  Group g
+        // of 4 warps owns conf / value columns [32g, 32g + 32); thread = (tile row = pixel, group).  Per memory map q:
+        //   e = exp(min(max(relu(conf), -6), 4)),  den += e,  num = fma(e, relu(value), num)      (connect.py:128-142)
+        // and after the last map of the sample  out = num / den  goes to the fused map (split-fp16 planes and / or fp32).
+        static_assert(EPI == 0 || BN == 128, "fused Conf_Fusion epilogue is written for the 64 + 64 column tile");
+        constexpr int HALF = BN / 2;
+        const int ew = warp & 3, eg = (warp - 4) >> 2, row = ew * 32 + lane, eall = threadIdx.x - 128;
+        float num[32], den[32];
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int nb = tile % p.n_tiles_n;
+            int mt = tile / p.n_tiles_n;
+            const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+            const int th = mt % p.tiles_h;
+            const int img0 = mt / p.tiles_h;
+            const int hl = row / p.bw, wl = row - hl * p.bw;
+            const int oh = th * p.bh + hl, ow = tw * p.bw + wl;
+            const bool valid = hl < p.bh && oh < p.ho && ow < p.wo;
+            for (int i = eall; i < BN; i += 128 * TC_EPI_GROUPS) { s_scale[i] = __ldg(p.scale + nb * BN + i); s_shift[i] = __ldg(p.shift + nb * BN + i); }
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { num[j] = 0.f; den[j] = 0.f; }
+#pragma unroll 1
+            for (int q = 0; q < p.group; ++q, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(bar_tfull + 8 * as, aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = eg * 32 + h * 16;   // conf column; the matching value column is HALF + c
+                    uint32_t u[16], w[16];
+                    tmem_ld16(taddr + c, u);
+                    tmem_ld16(taddr + HALF + c, w);
+                    if (Cfg::XACC) {
+                        uint32_t xu[16], xw[16];
+                        tmem_ld16(taddr + BN + c, xu);
+                        tmem_ld16(taddr + BN + HALF + c, xw);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            u[j] = __float_as_uint(__uint_as_float(u[j]) + __uint_as_float(xu[j]));
+                            w[j] = __float_as_uint(__uint_as_float(w[j]) + __uint_as_float(xw[j]));
+                        }
+                    } else {
+                        tmem_ld_wait();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float cf = fmaf(__uint_as_float(u[j]), s_scale[c + j], s_shift[c + j]);
+                        float v = fmaf(__uint_as_float(w[j]), s_scale[HALF + c + j], s_shift[HALF + c + j]);
+                        if (p.relu) { cf = fmaxf(cf, 0.f); v = fmaxf(v, 0.f); }
+                        const float e = expf(fminf(fmaxf(cf, -6.f), 4.f));
+                        den[h * 16 + j] += e;
+                        num[h * 16 + j] = fmaf(e, v, num[h * 16 + j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            }
+            if (valid) {
+                const size_t off = (((size_t)img0 * p.ho + oh) * p.wo + ow) * p.fuse_cout + nb * HALF + eg * 32;
+                float y[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] = num[j] / den[j];
+                if (p.out_hi) {
+                    uint4* oh4 = reinterpret_cast<uint4*>(p.out_hi + off);
+                    uint4* ol4 = reinterpret_cast<uint4*>(p.out_lo + off);
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        uint4 a, b;
+                        __half2* ah = reinterpret_cast<__half2*>(&a);
+                        __half2* bl = reinterpret_cast<__half2*>(&b);
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const float f0 = y[g4 * 8 + 2 * e2], f1 = y[g4 * 8 + 2 * e2 + 1];
+                            const __half2 hh = __floats2half2_rn(f0, f1);
+                            const float2 hf = __half22float2(hh);
+                            ah[e2] = hh;
+                            bl[e2] = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+                        }
+                        oh4[g4] = a;
+                        if (SPLIT) ol4[g4] = b;
+                    }
+                }
+                if (p.out_f32) {
+                    float4* o = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) o[g4] = make_float4(y[4 * g4], y[4 * g4 + 1], y[4 * g4 + 2], y[4 * g4 + 3]);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");  // scale/shift staging may be overwritten next iteration
+        }
+      } else if constexpr (EPI == 2) {
+        // ================================ epilogue: fused stem + max-pool ================================
+        static_assert(EPI != 2 || BN == 64, "the stem has 64 output channels");
+        const int ew = warp & 3, eg = (warp - 4) >> 2, row = ew * 32 + lane, eall = threadIdx.x - 128;
+        for (int i = eall; i < BN; i += 128 * TC_EPI_GROUPS) { s_scale[i] = __ldg(p.scale + i); s_shift[i] = __ldg(p.shift + i); }
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");
+        uint8_t* rowbuf = s_out;   // 128 pixels x 64 channels fp32, 16-byte chunks XOR-swizzled with the pixel index (32 KiB = the two staging buffers)
+        float vmax[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vmax[j] = -FLT_MAX;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileSeq sq = decode_seq(p, tile);
+            for (int q = 0; q < sq.count; ++q, ++it) {
+                const int oy = sq.th + q;
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                mbar_wait(bar_tfull + 8 * as, aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS + eg * 32;
+                uint32_t v[32];
+                tmem_ld32(taddr, v);
+                if (Cfg::XACC) {
+                    uint32_t x[32];
+                    tmem_ld32(taddr + BN, x);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(x[j]));
+                } else {
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * as);   // the accumulator is in registers: the next row's MMAs may start
+                const bool first = q == 0, odd = (oy & 1) != 0;
+                const bool emit = (odd && !first) || (!odd && oy == p.ho - 1);   // conv row 2py+1 (or the last row of the map) completes pooled row py
+                float y[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    y[j] = fmaf(__uint_as_float(v[j]), s_scale[eg * 32 + j], s_shift[eg * 32 + j]);
+                    if (p.relu) y[j] = fmaxf(y[j], 0.f);
+                    vmax[j] = first ? fmaxf(-FLT_MAX, y[j]) : fmaxf(vmax[j], y[j]);
+                }
+                if (emit) {   // (CTA-uniform)
+                    if (row < p.wo) {
+                        uint8_t* rp = rowbuf + row * 256;
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            *reinterpret_cast<float4*>(rp + (((eg * 8 + g4) ^ (row & 7)) << 4)) =
+                                make_float4(vmax[4 * g4], vmax[4 * g4 + 1], vmax[4 * g4 + 2], vmax[4 * g4 + 3]);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");
+                    const int py = oy >> 1;   // odd row 2py+1 -> py ; even last row 2py -> py
+                    for (int idx = eall; idx < p.pool_po * 16; idx += 128 * TC_EPI_GROUPS) {
+                        const int px = idx >> 4, cg = idx & 15;   // pooled pixel, group of 4 channels
+                        float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int xx = 2 * px - 1 + dx;
+                            if (xx < 0 || xx >= p.wo) continue;
+                            const float4 a = *reinterpret_cast<const float4*>(rowbuf + xx * 256 + ((cg ^ (xx & 7)) << 4));
+                            m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
+                        }
+                        const __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
+                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                        const __half2 l0 = __floats2half2_rn(m.x - f0.x, m.y - f0.y), l1 = __floats2half2_rn(m.z - f1.x, m.w - f1.y);
+                        uint2 a, c;
+                        a.x = *reinterpret_cast<const uint32_t*>(&h0); a.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        c.x = *reinterpret_cast<const uint32_t*>(&l0); c.y = *reinterpret_cast<const uint32_t*>(&l1);
+                        const size_t o = (((size_t)sq.img * p.pool_po + py) * p.pool_po + px) * 16 + cg;   // in units of 4 channels
+                        reinterpret_cast<uint2*>(p.out_hi)[o] = a;
+                        if (SPLIT) reinterpret_cast<uint2*>(p.out_lo)[o] = c;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");   // the row buffer may be overwritten by the next emit
+                    if (odd) {   // conv row 2py+1 is also the first row of pooled row py+1
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) vmax[j] = fmaxf(-FLT_MAX, y[j]);
+                    }
+                }
+            }
+        }
+      } else {
         // ================================ epilogue ================================
         // Two groups of 4 warps; warp w reads TMEM lane quarter w % 4; group g owns the 32-column chunks with (chunk % 2 == g)
         // and one store-staging buffer, so the groups never synchronise with each other inside a tile.
@@ -451,6 +668,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
             asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");  // scale/shift staging may be overwritten next iteration
         }
+      }
     }
     if (threadIdx.x >= 128 && ((threadIdx.x - 128) & 127) == 0 && p.tma_store) bulk_wait_read<0>();  // staging must outlive the stores' reads
     __syncthreads();
@@ -512,15 +730,16 @@ static void choose_tiling(int ho, int wo, int* tiles_w, int* bw, int* bh) {
     }
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, int EPI = 0>
 static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     using Cfg = TcCfg<BN, SPLIT>;
     static_assert(Cfg::STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
     static SmemAttrCache attr;
-    if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT>, 227 * 1024)) return rc;
-    if (!Cfg::TMA_OUT) { p.tma_store = 0; p.tma_res = 0; }
+    if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT, EPI>, 227 * 1024)) return rc;
+    if (!Cfg::TMA_OUT || EPI != 0) { p.tma_store = 0; p.tma_res = 0; }
     if (p.tma_res && Cfg::STAGES_RES < 2) p.tma_res = 0;
-    p.nbuf = p.tma_res ? 3 : 1;
+    p.nbuf = EPI == 1 ? 0 : (p.tma_res ? 3 : 1);   // (the fused Conf_Fusion epilogue stores from registers: no staging buffers; the
+                                                   //  stem + max-pool epilogue uses the two 16 KiB buffers of nbuf = 1 as its row buffer)
     p.stages = p.tma_res ? (Cfg::STAGES_RES < Cfg::STAGES ? Cfg::STAGES_RES : Cfg::STAGES) : Cfg::STAGES;
     const int smem = Cfg::smem_bytes(p.stages, p.nbuf);
     USOT_REQUIRE(smem <= 227 * 1024, "conv_tc: shared memory plan exceeds 227 KiB");
@@ -537,10 +756,10 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
         attr.val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        USOT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT>, p));
+        USOT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, EPI>, p));
         return 0;
     }
-    conv_tc_kernel<BN, SPLIT><<<grid, TC_THREADS, smem, st>>>(p);
+    conv_tc_kernel<BN, SPLIT, EPI><<<grid, TC_THREADS, smem, st>>>(p);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -558,7 +777,7 @@ Tunable g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cro
 struct PlanKey {  // plain words only (no padding: the key is hashed and compared as raw bytes)
     const void* ptr[11];
     int geom[14];
-    int K, relu, split, device, knobs[9], pad_;
+    int K, relu, split, device, knobs[9], group;
 };
 struct Plan { TcParams p; int bn, grid; };
 struct PlanKeyHash {
@@ -589,6 +808,8 @@ static void plan_store(const PlanKey& k, const Plan& pl) {
 }
 
 static int launch_plan(Plan& pl, bool split, cudaStream_t st) {
+    if (pl.p.pool_bands > 0) return split ? launch_cfg<64, true, 2>(pl.p, pl.grid, st) : launch_cfg<64, false, 2>(pl.p, pl.grid, st);
+    if (pl.p.group > 1 || pl.p.fuse_cout) return split ? launch_cfg<128, true, 1>(pl.p, pl.grid, st) : launch_cfg<128, false, 1>(pl.p, pl.grid, st);
     if (split) {
         if (pl.bn == 256) return launch_cfg<256, true>(pl.p, pl.grid, st);
         if (pl.bn == 128) return launch_cfg<128, true>(pl.p, pl.grid, st);
@@ -599,7 +820,7 @@ static int launch_plan(Plan& pl, bool split, cudaStream_t st) {
     return launch_cfg<64, false>(pl.p, pl.grid, st);
 }
 
-int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st) {
+int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, const TcEpilogue& ep, bool split, cudaStream_t st, int fuse_group) {
     USOT_REQUIRE(g.cin % TC_BK == 0, "conv_tc needs Cin % 64 == 0");
     USOT_REQUIRE(g.cout % 64 == 0, "conv_tc needs Cout % 64 == 0");
     USOT_REQUIRE(g.stride == 1 || g.stride == 2, "conv_tc supports stride 1 and 2");
@@ -607,6 +828,10 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     USOT_REQUIRE(w.hi && (!split || w.lo), "conv_tc: missing weight plane");
     USOT_REQUIRE(ep.out_hi || ep.out_f32, "conv_tc: no output requested");
     if ((size_t)g.n * g.ho * g.wo == 0) return 0;
+    if (fuse_group > 0) {
+        USOT_REQUIRE(g.cout % 128 == 0 && g.n % fuse_group == 0, "fused Conf_Fusion: cout must be a multiple of 128 and n a multiple of the group");
+        USOT_REQUIRE(!ep.res_hi && g.stride == 1, "fused Conf_Fusion: no residual, stride 1");
+    }
 
     // Launch-plan cache: the tensor maps (up to 14 cuTensorMapEncodeTiled calls), tiling and kernel variant of a launch depend only on
     // the pointers, the geometry and the knobs.  The engine's arena hands out the same addresses for the same call shape, so in steady
@@ -617,7 +842,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     const int kg[14] = {g.n, g.h, g.w, g.cin, g.cout, g.kh, g.kw, g.stride, g.ph, g.pw, g.dh, g.dw, g.ho, g.wo};
     memcpy(key.ptr, kp, sizeof(kp));
     memcpy(key.geom, kg, sizeof(kg));
-    key.K = w.K; key.relu = ep.relu; key.split = split ? 1 : 0;
+    key.K = w.K; key.relu = ep.relu; key.split = split ? 1 : 0; key.group = fuse_group;
     key.knobs[0] = g_tc_bn_max; key.knobs[1] = g_tc_split_bn_max; key.knobs[2] = g_tc_tma_store; key.knobs[3] = g_tc_tma_res;
     key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch; key.knobs[7] = g_tc_latency_split;
     key.knobs[8] = g_tc_pdl;
@@ -640,13 +865,16 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     // and every MMA of a tile's K loop is half as wide (half as long).  The accumulation order of each output element does not
     // change, so results stay bit-identical to the wide-tile launch of a large batch (tests: batch independence, graph replay).
     // (Not across the 256 -> 128 step of split mode, which would switch to the two-accumulator arithmetic.)
-    if (g_tc_latency_split) {
+    if (fuse_group > 0) bn = 128;   // 64 conf + 64 value columns per tile
+    else if (g_tc_latency_split) {
         const int m_tiles = g.n * p.tiles_h * p.tiles_w;
         while (bn > 64 && !(split && bn == 256) && m_tiles * (g.cout / bn) * 2 <= num_sms) bn /= 2;
     }
     p.n_img = g.n; p.ho = g.ho; p.wo = g.wo; p.cout = g.cout;
     p.n_tiles_n = g.cout / bn;
-    p.num_tiles = g.n * p.tiles_h * p.tiles_w * p.n_tiles_n;
+    p.group = fuse_group > 0 ? fuse_group : 1;
+    p.fuse_cout = fuse_group > 0 ? g.cout / 2 : 0;
+    p.num_tiles = (g.n / p.group) * p.tiles_h * p.tiles_w * p.n_tiles_n;   // fused launch: one tile index = the `group` maps of a sample
     p.taps = g.kh * g.kw; p.kw = g.kw; p.cin_chunks = g.cin / TC_BK;
     p.stride = g.stride; p.ph = g.ph; p.pw = g.pw; p.dh = g.dh; p.dw = g.dw;
     p.scale = w.scale; p.shift = ep.shift;
@@ -686,9 +914,9 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     p.fuse_cross = g_tc_fuse_cross;
     p.l2_prefetch = g_tc_l2_prefetch;
     p.pdl = 0;  // decided below, once the tile count is known
-    p.tma_store = (g_tc_tma_store && p.out_hi && !(split && bn == 256)) ? 1 : 0;
+    p.tma_store = (g_tc_tma_store && p.out_hi && !(split && bn == 256) && fuse_group == 0) ? 1 : 0;
     p.tma_f32 = 0;
-    if (g_tc_tma_store && g_tc_tma_f32 && !p.out_hi && p.out_f32 && !p.res_hi && !(split && bn == 256)) {
+    if (fuse_group == 0 && g_tc_tma_store && g_tc_tma_f32 && !p.out_hi && p.out_f32 && !p.res_hi && !(split && bn == 256)) {
         // fp32-only output: one fp32 map, box {32 floats = 128 B, bw, bh, 1}, 128B swizzle; uses the split path's staging buffers
         cuuint64_t od[4] = {(cuuint64_t)g.cout, (cuuint64_t)g.wo, (cuuint64_t)g.ho, (cuuint64_t)g.n};
         cuuint64_t os[3] = {(cuuint64_t)g.cout * 4, (cuuint64_t)g.wo * g.cout * 4, (cuuint64_t)g.ho * g.wo * g.cout * 4};
@@ -718,7 +946,152 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     plan.grid = std::min(p.num_tiles, num_sms);
     // Programmatic dependent launch pays in the latency regime (every tile has its own SM, idle SMs host the successor's prologue):
     // batch 1: -7 % per track() call.  At batch 256 it measured -1.6 % (within clock noise, no possible gain): not used there.
-    plan.p.pdl = (g_tc_pdl && p.num_tiles <= num_sms) ? 1 : 0;
+    plan.p.pdl = (g_tc_pdl && p.num_tiles * p.group <= num_sms) ? 1 : 0;
+    plan_store(key, plan);
+    return launch_plan(plan, split, st);
+}
+
+// =============================================================================================
+// Stem (conv1 7x7 / stride 2 / pad 0, Cin = 3) + max-pool as a TMA-fed implicit GEMM            lib/models/modules.py:70-74,138-141
+// =============================================================================================
+// Space-to-depth turns the stride-2 7x7 conv over 3 channels into a stride-1 4x4 conv over 12 channels (filter zero-padded to 8x8):
+//     s2d[n][Y][X][c*4 + a*2 + b] = x[n][c][2Y + a][2X + b]          (16 channels per pixel, 12 used)
+//     out[oy][ox][co] = sum_{ky,kx<4} sum_{ch<16} s2d[oy + ky][ox + kx][ch] * w2[co][ky][kx][ch],   w2 = w[co][c][2ky + a][2kx + b]
+// For a fixed ky the 64 values (kx, ch) of output pixel ox are the 128 contiguous bytes that START at s2d pixel (oy + ky, ox): the A
+// operand of K-chunk ky is a view of the s2d plane whose "pixel" stride is 32 bytes and whose row length is 128 bytes -- rows overlap.
+// A tensor map with dims {64, HO, HP, n} and strides {32 B, WP*32 B, HP*WP*32 B} describes exactly that, so ONE TMA box {64, HO, 1, 1}
+// per (ky, plane) lands the im2col rows of a whole output row in shared memory, already 128B-swizzled: no software im2col, no
+// per-tap conversion (the image is split into fp16 hi / lo planes once, by stem_s2d_kernel).  K = 4 x 64 = 256 (147 useful).
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ x, int n, int S, int HP, uint4* __restrict__ hi, uint4* __restrict__ lo) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n * HP * HP;
+    if (idx >= total) return;
+    const int X = (int)(idx % HP);
+    const int Y = (int)((idx / HP) % HP);
+    const size_t b = idx / ((size_t)HP * HP);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+                const int yy = 2 * Y + a, xx = 2 * X + bb;
+                v[c * 4 + a * 2 + bb] = (yy < S && xx < S) ? __ldg(x + ((b * 3 + c) * S + yy) * S + xx) : 0.f;
+            }
+#pragma unroll
+    for (int j = 12; j < 16; ++j) v[j] = 0.f;
+    uint4 h[2], l[2];
+    __half2* hh = reinterpret_cast<__half2*>(h);
+    __half2* ll = reinterpret_cast<__half2*>(l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const __half2 t = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        const float2 tf = __half22float2(t);
+        hh[e] = t;
+        ll[e] = __floats2half2_rn(v[2 * e] - tf.x, v[2 * e + 1] - tf.y);
+    }
+    hi[2 * idx] = h[0]; hi[2 * idx + 1] = h[1];
+    if (lo) { lo[2 * idx] = l[0]; lo[2 * idx + 1] = l[1]; }
+}
+
+// stem_w: [147][64] fp32 with k = (c*7 + kh)*7 + kw  ->  w_kn2: [256][64] fp32 with k2 = ky*64 + kx*16 + c*4 + a*2 + b (kh = 2ky+a, kw = 2kx+b)
+__global__ void stem_s2d_weight_kernel(const float* __restrict__ stem_w, float* __restrict__ w_kn2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 256 * 64) return;
+    const int co = i & 63, k2 = i >> 6;
+    const int ky = k2 >> 6, kx = (k2 >> 4) & 3, ch = k2 & 15;
+    const int c = ch >> 2, a = (ch >> 1) & 1, b = ch & 1;
+    const int kh = 2 * ky + a, kw = 2 * kx + b;
+    w_kn2[i] = (ch < 12 && kh < 7 && kw < 7) ? __ldg(stem_w + ((c * 7 + kh) * 7 + kw) * 64 + co) : 0.f;
+}
+
+int launch_stem_s2d_weights(const float* stem_w, const float* stem_scale, float* w_kn2_scratch, __half* w_hi, __half* w_lo, float* scale_out,
+                            cudaStream_t st) {
+    stem_s2d_weight_kernel<<<64, 256, 0, st>>>(stem_w, w_kn2_scratch);
+    USOT_CUDA_OK(cudaGetLastError());
+    return launch_pack_tc_weights(w_kn2_scratch, 256, 64, stem_scale, w_hi, w_lo, scale_out, st);
+}
+
+// Bands per image for the fused stem + max-pool launch (0: not applicable, the map is wider than one 128-pixel tile, S > 261).
+// A band walks its 2*band_rows + 1 conv rows one after the other on ONE SM: pick the count that minimises waves x rows per band.
+int stem_pool_bands(int n, int s) {
+    const int HO = (s - 7) / 2 + 1, PO = (HO + 2 - 3) / 2 + 1;
+    if (HO > 128 || HO < 3 || n <= 0) return 0;
+    const int G = device_sm_count();
+    long best = -1;
+    int best_nb = 0;
+    for (int nb = 1; nb <= PO && nb <= 64; ++nb) {
+        const int band_rows = (PO + nb - 1) / nb;
+        if ((nb - 1) * band_rows >= PO) continue;   // the last band would be empty
+        const long cost = (((long)n * nb + G - 1) / G) * (2L * band_rows + 1);
+        if (best < 0 || cost < best) { best = cost; best_nb = nb; }
+    }
+    return best_nb;
+}
+
+size_t stem_s2d_plane_elems(int n, int s) { const int HP = (s - 7) / 2 + 1 + 3; return (size_t)n * HP * HP * 16; }
+
+int launch_stem_s2d_pool(const float* x, int n, int s, const __half* w_hi, const __half* w_lo, const float* scale_tc, const float* shift,
+                         __half* s2d_hi, __half* s2d_lo, __half* pool_hi, __half* pool_lo, bool split, cudaStream_t st) {
+    const int nb = stem_pool_bands(n, s);
+    USOT_REQUIRE(nb > 0, "fused stem + max-pool is not applicable to this shape (ask stem_pool_bands first)");
+    USOT_REQUIRE(s2d_hi && pool_hi && (!split || (s2d_lo && pool_lo && w_lo)), "fused stem + max-pool: missing plane");
+    const int HO = (s - 7) / 2 + 1, HP = HO + 3, PO = (HO + 2 - 3) / 2 + 1;
+    {   // image -> space-to-depth fp16 planes
+        const size_t total = (size_t)n * HP * HP;
+        stem_s2d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, n, s, HP, reinterpret_cast<uint4*>(s2d_hi),
+                                                                          split ? reinterpret_cast<uint4*>(s2d_lo) : nullptr);
+        USOT_CUDA_OK(cudaGetLastError());
+    }
+    PlanKey key;
+    memset(&key, 0, sizeof(key));
+    const void* kp[11] = {s2d_hi, s2d_lo, w_hi, w_lo, scale_tc, shift, nullptr, nullptr, pool_hi, pool_lo, nullptr};
+    const int kg[14] = {n, HP, HP, 16, 64, 4, 1, 1, 0, 0, 1, 1, HO, HO};
+    memcpy(key.ptr, kp, sizeof(kp));
+    memcpy(key.geom, kg, sizeof(kg));
+    key.K = 256; key.relu = 1; key.split = split ? 1 : 0; key.group = 1000 + nb;
+    key.knobs[4] = g_tc_fuse_cross;
+    USOT_CUDA_OK(cudaGetDevice(&key.device));
+    Plan plan;
+    if (plan_lookup(key, &plan)) return launch_plan(plan, split, st);
+
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_img = n; p.ho = HO; p.wo = HO; p.cout = 64;
+    p.bw = HO; p.bh = 1; p.tiles_w = 1; p.tiles_h = HO;
+    p.n_tiles_n = 1; p.group = 1;
+    p.pool_bands = nb; p.pool_band_rows = (PO + nb - 1) / nb; p.pool_po = PO;
+    p.num_tiles = n * nb;
+    p.taps = 4; p.kw = 1; p.cin_chunks = 1;
+    p.stride = 1; p.ph = 0; p.pw = 0; p.dh = 1; p.dw = 1;
+    p.scale = scale_tc; p.shift = shift;
+    p.out_hi = pool_hi; p.out_lo = pool_lo;
+    p.relu = 1;
+    p.fuse_cross = g_tc_fuse_cross;
+    for (int pl = 0; pl < (split ? 2 : 1); ++pl) {
+        // overlapping-row view of the s2d plane: "pixel" ox = the 64 halves that start at s2d pixel ox (stride 16 halves = 32 B)
+        const __half* base = pl == 0 ? s2d_hi : s2d_lo;
+        cuuint64_t dims[4] = {64, (cuuint64_t)HO, (cuuint64_t)HP, (cuuint64_t)n};
+        cuuint64_t strides[3] = {32, (cuuint64_t)HP * 32, (cuuint64_t)HP * HP * 32};
+        cuuint32_t box[4] = {64, (cuuint32_t)HO, 1, 1};
+        if (!p.a_rank5 && encode_map(&p.a[pl][0], base, 4, dims, strides, box) != 0) {
+            USOT_REQUIRE(pl == 0, "stem: tensor-map encode failed for the lo plane only");
+            p.a_rank5 = 1;   // the driver refuses rows that overlap: describe the same bytes as {16 ch, 4 kx, ox, row, image}
+        }
+        if (p.a_rank5) {
+            cuuint64_t d5[5] = {16, 4, (cuuint64_t)HO, (cuuint64_t)HP, (cuuint64_t)n};
+            cuuint64_t s5[4] = {32, 32, (cuuint64_t)HP * 32, (cuuint64_t)HP * HP * 32};
+            cuuint32_t b5[5] = {16, 4, (cuuint32_t)HO, 1, 1};
+            if (int rc = encode_map(&p.a[pl][0], base, 5, d5, s5, b5)) return rc;
+        }
+        cuuint64_t wd[2] = {256, 64}, ws[1] = {256 * 2};
+        cuuint32_t wb[2] = {64, 64};
+        if (int rc = encode_map(&p.b[pl], pl == 0 ? w_hi : w_lo, 2, wd, ws, wb)) return rc;
+    }
+    plan.p = p;
+    plan.bn = 64;
+    plan.grid = std::min(p.num_tiles, device_sm_count());
     plan_store(key, plan);
     return launch_plan(plan, split, st);
 }

@@ -47,6 +47,8 @@ static void count_launches(int fam, long long n) {
 }
 // launch accounting for the operators that live in other translation units (ops_abi.cu, train_kernels.cu)
 void count_op_launch(int family, int n) { if (family >= 0 && family < FAM_COUNT) count_launches(family, n); }
+static Tunable g_conf_fusion_fused{1};  // tunable "conf_fusion_fused": 1 = conf_gen || value_gen as ONE conv with the Conf_Fusion reduction in its epilogue (tcgen05 modes)
+static Tunable g_stem_pool_fused{1};  // tunable "stem_pool_fused": 1 = stem + max-pool as ONE TMA-fed implicit GEMM over the space-to-depth image (conv_tc.cu, EPI = 2)
 static Tunable g_stem_tc{1};  // tunable "stem_tc": 1 = tensor-core stem in the tcgen05 precision modes, 0 = CUDA-core stem
 struct Scope {
     int fam; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
@@ -187,6 +189,8 @@ struct usot_engine {
     float *stem_w = nullptr, *stem_scale = nullptr, *stem_shift = nullptr;
     void* stem_tc_img = nullptr;      // tensor-core stem: packed weight tile + scale*2^-e
     float* stem_tc_scale = nullptr;
+    __half *stem2_hi = nullptr, *stem2_lo = nullptr;  // fused stem + max-pool: [64][256] K-major planes of the space-to-depth filter
+    float* stem2_scale = nullptr;                     // (derived on the device from stem_w; not part of the packed image)
     PredW bbox_pred, cls_pred, cls_memory_pred;
     float dw_cls[3] = {0, 0, 0}, dw_reg[3] = {0, 0, 0};  // softmax(GroupDW.weight)
     float *adjust = nullptr, *bias4 = nullptr;
@@ -425,6 +429,45 @@ static int finalize_impl(usot_engine* e) {
     }
     if (upload(e, adj, &e->adjust, 1) || upload(e, b4, &e->bias4, 4)) return 1;
     if (rp) USOT_REQUIRE(e->replay == e->replay_end, "packed weight image has trailing data (built for another architecture?)");
+    if (tc) {
+        // Fused stem + max-pool: the 7x7/2 filter re-indexed for the space-to-depth image (4x4 taps x 16 channels, K = 256)
+        void *h2 = nullptr, *l2 = nullptr, *s2 = nullptr, *scratch = nullptr;
+        USOT_CUDA_OK(cudaMalloc(&h2, 64 * 256 * sizeof(__half))); e->owned.push_back(h2);
+        USOT_CUDA_OK(cudaMalloc(&l2, 64 * 256 * sizeof(__half))); e->owned.push_back(l2);
+        USOT_CUDA_OK(cudaMalloc(&s2, 64 * sizeof(float))); e->owned.push_back(s2);
+        USOT_CUDA_OK(cudaMalloc(&scratch, 256 * 64 * sizeof(float))); e->owned.push_back(scratch);
+        e->stem2_hi = static_cast<__half*>(h2); e->stem2_lo = static_cast<__half*>(l2); e->stem2_scale = static_cast<float*>(s2);
+        if (int rc = launch_stem_s2d_weights(e->stem_w, e->stem_scale, static_cast<float*>(scratch), e->stem2_hi, e->stem2_lo, e->stem2_scale, 0)) return rc;
+    }
+    if (tc) {
+        // Fused Conf_Fusion (connect.py:104-144): conf_gen and value_gen read the same input, so they run as ONE conv whose 128-column
+        // weight tiles hold 64 conf channels followed by the same 64 value channels (conv_tc.cu, EPI = 1).  The interleaved planes are
+        // DERIVED on the device from the two packed layers (not part of the packed-weight image).
+        const ConvW& cg = e->convs["connect_model.conf_fusion.conf_gen.0"];
+        const ConvW& vg = e->convs["connect_model.conf_fusion.value_gen.0"];
+        ConvW f;
+        f.s = cg.s;
+        f.s.name = "connect_model.conf_fusion.fused";
+        f.s.cout = 512;
+        const size_t K = (size_t)9 * 256;
+        void *whi = nullptr, *wlo = nullptr, *sc = nullptr, *sh = nullptr;
+        USOT_CUDA_OK(cudaMalloc(&whi, 512 * K * sizeof(__half))); e->owned.push_back(whi);
+        USOT_CUDA_OK(cudaMalloc(&wlo, 512 * K * sizeof(__half))); e->owned.push_back(wlo);
+        USOT_CUDA_OK(cudaMalloc(&sc, 512 * sizeof(float))); e->owned.push_back(sc);
+        USOT_CUDA_OK(cudaMalloc(&sh, 512 * sizeof(float))); e->owned.push_back(sh);
+        f.w_hi = static_cast<__half*>(whi); f.w_lo = static_cast<__half*>(wlo);
+        f.scale_tc = static_cast<float*>(sc); f.shift = static_cast<float*>(sh);
+        for (int b = 0; b < 4; ++b)
+            for (int half = 0; half < 2; ++half) {
+                const ConvW& src = half ? vg : cg;
+                const size_t drow = (size_t)128 * b + 64 * half, srow = (size_t)64 * b;
+                USOT_CUDA_OK(cudaMemcpy(f.w_hi + drow * K, src.w_hi + srow * K, 64 * K * sizeof(__half), cudaMemcpyDeviceToDevice));
+                USOT_CUDA_OK(cudaMemcpy(f.w_lo + drow * K, src.w_lo + srow * K, 64 * K * sizeof(__half), cudaMemcpyDeviceToDevice));
+                USOT_CUDA_OK(cudaMemcpy(f.scale_tc + drow, src.scale_tc + srow, 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+                USOT_CUDA_OK(cudaMemcpy(f.shift + drow, src.shift + srow, 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+            }
+        e->convs[f.s.name] = f;
+    }
     USOT_CUDA_OK(cudaDeviceSynchronize());
     e->finalized = true;
     return 0;
@@ -511,8 +554,16 @@ static int backbone_neck(Ctx& c, const float* x, int n, int S, float* xf_dst, T*
     usot_engine* e = c.e;
     const int h1 = (S - 7) / 2 + 1;
     const int h2 = (h1 + 2 - 3) / 2 + 1;
-    float* a0 = ar.f((size_t)n * h1 * h1 * 64);
-    if (!ar.plan) {
+    // stem + max-pool as ONE tensor-core kernel over the space-to-depth image (no (n, h1, h1, 64) fp32 map in HBM, no software im2col);
+    // maps wider than one 128-pixel tile (271-pixel crops) keep the two kernels
+    const bool fused_pool = c.tc() && g_stem_tc && g_stem_pool_fused && stem_pool_bands(n, S) > 0;
+    __half *s2d_hi = nullptr, *s2d_lo = nullptr;
+    if (fused_pool) {
+        s2d_hi = ar.h(stem_s2d_plane_elems(n, S));
+        s2d_lo = c.split() ? ar.h(stem_s2d_plane_elems(n, S)) : nullptr;
+    }
+    float* a0 = fused_pool ? nullptr : ar.f((size_t)n * h1 * h1 * 64);
+    if (!ar.plan && !fused_pool) {
         Scope sc(FAM_STEM, c.st, 2.0 * n * h1 * h1 * 64.0 * 147);
         if (c.tc() && g_stem_tc) RUN(launch_stem_tc(x, n, S, e->stem_tc_img, e->stem_tc_scale, e->stem_shift, a0, c.split(), c.st));
         else RUN(launch_stem(x, n, S, e->stem_w, e->stem_scale, e->stem_shift, a0, c.st));
@@ -525,7 +576,12 @@ static int backbone_neck(Ctx& c, const float* x, int n, int S, float* xf_dst, T*
     } else {
         cur.f = ar.f(cur.numel());
     }
-    if (!ar.plan) {
+    if (!ar.plan && fused_pool) {
+        Scope sc(FAM_STEM, c.st, 2.0 * n * h1 * h1 * 64.0 * 147);
+        count_launches(FAM_STEM, 1); tl_launches[FAM_STEM]++;   // (two kernels: image -> space-to-depth planes, then the GEMM + pooling epilogue)
+        RUN(launch_stem_s2d_pool(x, n, S, e->stem2_hi, e->stem2_lo, e->stem2_scale, e->stem_shift, s2d_hi, s2d_lo, cur.hi, cur.lo, c.split(), c.st));
+    }
+    if (!ar.plan && !fused_pool) {
         Scope sc(FAM_POOL, c.st, 0, 4.0 * n * 64 * ((double)h1 * h1 + (double)h2 * h2));
         RUN(launch_maxpool3x3s2p1(a0, n, h1, h1, 64, cur.f, cur.hi, cur.lo, c.st));
     }
@@ -654,15 +710,34 @@ static int head_memory(Ctx& c, const Enc3& cls_x, int n, int F, const float* mem
     if (int rc = encode(c, "cls_encode", 'k', m, &mz)) return rc;
     T dw, conf, val, t;
     if (int rc = groupdw(c, cls_x, mz, n * nq, F, e->dw_cls, &dw)) return rc;
-    if (int rc = run_conv(c, "connect_model.conf_fusion.conf_gen.0", dw, nullptr, OUT_F32, &conf)) return rc;
-    if (int rc = run_conv(c, "connect_model.conf_fusion.value_gen.0", dw, nullptr, OUT_F32, &val)) return rc;
     const size_t per_map = (size_t)R * R * 256;
     T fused;
     fused.n = n; fused.h = fused.w = R; fused.c = 256;
-    fused.f = ar.f(fused.numel());
-    if (!ar.plan) {
-        Scope sc(FAM_FUSION, c.st, 0, 4.0 * per_map * (2.0 * n * nq + n));
-        RUN(launch_conf_fusion(conf.f, val.f, n, nq, per_map, fused.f, c.st));
+    if (c.split() && g_conf_fusion_fused) {   // (single-fp16 mode: its two N = 256 tiles share more operand traffic than the 64 + 64 tile saves)
+        // ONE conv for conf_gen || value_gen (every activation box is loaded once for both) with the clamp / exp / sum over the N_q maps /
+        // divide in its epilogue: the two (n*nq, R, R, 256) fp32 maps are never written, and the result leaves as the split-fp16
+        // planes the memory tower reads (no conversion pass).
+        const ConvW& cw = e->convs.find("connect_model.conf_fusion.fused")->second;
+        if (int rc = ensure_split(c, dw)) return rc;
+        fused.hi = ar.h(fused.numel());
+        fused.lo = c.split() ? ar.h(fused.numel()) : nullptr;
+        ConvGeom g;
+        g.n = n * nq; g.h = g.w = R; g.cin = 256; g.cout = 512; g.kh = g.kw = 3; g.stride = 1; g.ph = g.pw = 1; g.dh = g.dw = 1; g.ho = g.wo = R;
+        TcTensor ti{dw.hi, dw.lo};
+        TcWeights tw{cw.w_hi, cw.w_lo, cw.scale_tc, 9 * 256};
+        TcEpilogue ep{cw.shift, nullptr, nullptr, fused.hi, fused.lo, nullptr, 1};
+        if (!ar.plan) {
+            Scope sc(FAM_CONV, c.st, 2.0 * g.n * R * R * 512.0 * 9 * 256);
+            RUN(launch_conv_tc(ti, g, tw, ep, c.split(), c.st, nq));
+        }
+    } else {
+        if (int rc = run_conv(c, "connect_model.conf_fusion.conf_gen.0", dw, nullptr, OUT_F32, &conf)) return rc;
+        if (int rc = run_conv(c, "connect_model.conf_fusion.value_gen.0", dw, nullptr, OUT_F32, &val)) return rc;
+        fused.f = ar.f(fused.numel());
+        if (!ar.plan) {
+            Scope sc(FAM_FUSION, c.st, 0, 4.0 * per_map * (2.0 * n * nq + n));
+            RUN(launch_conf_fusion(conf.f, val.f, n, nq, per_map, fused.f, c.st));
+        }
     }
     if (int rc = tower(c, "cls_memory_tower", fused, &t)) return rc;
     if (int rc = pred(c, e->cls_memory_pred, t, 0, cls_mem)) return rc;
@@ -773,6 +848,8 @@ int usot_set_tunable(const char* name, int value) {
     if (!strcmp(name, "tc_bn_max")) { USOT_REQUIRE(value == 64 || value == 128 || value == 256, "tc_bn_max must be 64, 128 or 256"); g_tc_bn_max = value; return 0; }
     if (!strcmp(name, "graph_max_batch")) { USOT_REQUIRE(value >= 0 && value <= 64, "graph_max_batch must be in [0, 64]"); g_graph_max_batch = value; return 0; }
     if (!strcmp(name, "groupdw_tma")) { USOT_REQUIRE(value >= 0 && value <= 2, "groupdw_tma must be 0 (register-staged), 1 (TMA ring, scalar FMA) or 2 (TMA ring, packed FFMA2)"); g_groupdw_tma = value; return 0; }
+    if (!strcmp(name, "conf_fusion_fused")) { USOT_REQUIRE(value == 0 || value == 1, "conf_fusion_fused must be 0 or 1"); g_conf_fusion_fused = value; return 0; }
+    if (!strcmp(name, "stem_pool_fused")) { USOT_REQUIRE(value == 0 || value == 1, "stem_pool_fused must be 0 or 1"); g_stem_pool_fused = value; return 0; }
     if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
     if (!strcmp(name, "tc_pdl")) { USOT_REQUIRE(value == 0 || value == 1, "tc_pdl must be 0 or 1"); g_tc_pdl = value; return 0; }

@@ -70,6 +70,43 @@ int usot_stem_conv(const float* x, int n, int size, const float* host_weight_oih
     return rc;
 }
 
+int usot_stem_maxpool(const float* x, int n, int size, const float* host_weight_oihw, const float* host_scale, const float* host_shift,
+                      float* out, int precision, void* stream) {
+    USOT_REQUIRE(x && host_weight_oihw && host_scale && host_shift && out, "null pointer");
+    USOT_REQUIRE(n > 0 && size >= 13, "bad shape");
+    USOT_REQUIRE(precision == USOT_PREC_FP16X3_TC || precision == USOT_PREC_FP16_TC, "usot_stem_maxpool runs the tensor-core path (fp16x3 / fp16)");
+    USOT_REQUIRE(stem_pool_bands(n, size) > 0, "usot_stem_maxpool: the conv map must fit one 128-pixel tile (size <= 261)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool split = precision == USOT_PREC_FP16X3_TC;
+    const int HO = (size - 7) / 2 + 1, PO = (HO - 1) / 2 + 1;
+    const size_t n_pool = (size_t)n * PO * PO * 64, n_s2d = stem_s2d_plane_elems(n, size);
+    std::vector<float> packed(147 * 64);
+    for (int co = 0; co < 64; ++co)
+        for (int k = 0; k < 147; ++k) packed[(size_t)k * 64 + co] = host_weight_oihw[(size_t)co * 147 + k];
+    float *d_w = nullptr, *d_scale = nullptr, *d_shift = nullptr, *d_scratch = nullptr, *d_scale2 = nullptr;
+    __half *w_hi = nullptr, *w_lo = nullptr, *s_hi = nullptr, *s_lo = nullptr, *p_hi = nullptr, *p_lo = nullptr;
+    int rc = 0;
+    do {
+        if (cudaMalloc(&d_w, packed.size() * 4) || cudaMalloc(&d_scale, 256) || cudaMalloc(&d_shift, 256) || cudaMalloc(&d_scale2, 256) ||
+            cudaMalloc(&d_scratch, 256 * 64 * 4) || cudaMalloc(&w_hi, 64 * 256 * 2) || cudaMalloc(&w_lo, 64 * 256 * 2) ||
+            cudaMalloc(&s_hi, n_s2d * 2) || cudaMalloc(&s_lo, n_s2d * 2) || cudaMalloc(&p_hi, n_pool * 2) || cudaMalloc(&p_lo, n_pool * 2)) {
+            set_error("usot_stem_maxpool: cudaMalloc failed"); rc = 1; break;
+        }
+        cudaMemcpyAsync(d_w, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_scale, host_scale, 256, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_shift, host_shift, 256, cudaMemcpyHostToDevice, st);
+        if ((rc = launch_stem_s2d_weights(d_w, d_scale, d_scratch, w_hi, w_lo, d_scale2, st))) break;
+        count_op_launch(OPFAM_STEM, 2);
+        if ((rc = launch_stem_s2d_pool(x, n, size, w_hi, w_lo, d_scale2, d_shift, s_hi, split ? s_lo : nullptr, p_hi, split ? p_lo : nullptr, split, st))) break;
+        if ((rc = launch_split_to_f32(p_hi, split ? p_lo : nullptr, n_pool, out, st))) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("usot_stem_maxpool: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; }
+    } while (0);
+    cudaStreamSynchronize(st);
+    cudaFree(d_w); cudaFree(d_scale); cudaFree(d_shift); cudaFree(d_scale2); cudaFree(d_scratch); cudaFree(w_hi); cudaFree(w_lo);
+    cudaFree(s_hi); cudaFree(s_lo); cudaFree(p_hi); cudaFree(p_lo);
+    return rc;
+}
+
 int usot_stem_conv_raw(const float* x, int n, int size, const float* weight_kn, float* out, void* stream) {
     USOT_REQUIRE(n == 0 || (x && weight_kn && out), "null pointer");
     USOT_REQUIRE(n >= 0 && size >= 7, "bad shape");

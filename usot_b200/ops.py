@@ -6,6 +6,7 @@
     conv2d_nhwc       nn.Conv2d + folded BatchNorm2d (+residual)(+ReLU)
     pred_conv         bbox_pred / cls_pred / cls_memory_pred + epilogue, lib/models/connect.py:235-241,274-275
     stem_conv, maxpool3x3s2p1_nhwc   conv1+bn1+relu / maxpool, lib/models/modules.py:70-75,138-141
+    stem_maxpool                     the same four modules as one fused tensor-core kernel
     conf_fusion       reduction of Conf_Fusion.forward, lib/models/connect.py:123-144
     cycle_glue        forward-tracking argmax / box maps, lib/models/models.py:262-274
     weighted_bce, iou_loss           lib/models/models.py:42-100
@@ -239,6 +240,24 @@ def stem_conv(x, weight_oihw, scale, shift, precision="fp32"):
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().usot_stem_conv(_lib.ptr(x.contiguous()), n, s, _lib.ptr(host[0]), _lib.ptr(host[1]), _lib.ptr(host[2]),
                                               _lib.ptr(out), _lib.PRECISIONS[precision], _stream(x)))
+    return out
+
+
+def stem_maxpool(x, weight_oihw, scale, shift, precision="fp16x3"):
+    """conv1 7x7/2 p0 + folded BN + ReLU + maxpool 3x3/2 p1 (lib/models/modules.py:70-75,138-141) as ONE tensor-core kernel over the
+    space-to-depth image (the engine's path in the tcgen05 modes; crops up to 261 pixels).  Returns NHWC (n,PO,PO,64) fp32 = hi + lo of
+    the split-fp16 planes the kernel writes."""
+    _need_float(x)
+    _need_cuda(x)
+    n, c, s, s2 = x.shape
+    assert c == 3 and s == s2 and tuple(weight_oihw.shape) == (64, 3, 7, 7)
+    ho = (s - 7) // 2 + 1
+    po = (ho - 1) // 2 + 1
+    host = [t.detach().to("cpu", torch.float32).contiguous() for t in (weight_oihw, scale, shift)]
+    out = torch.empty((n, po, po, 64), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().usot_stem_maxpool(_lib.ptr(x.contiguous()), n, s, _lib.ptr(host[0]), _lib.ptr(host[1]), _lib.ptr(host[2]),
+                                                 _lib.ptr(out), _lib.PRECISIONS[precision], _stream(x)))
     return out
 
 
