@@ -110,8 +110,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // 1024-byte aligned operand ring (required by the 128B swizzle atoms)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    uint8_t* s_out = smem_gen + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
-    float* s_scale = reinterpret_cast<float*>(s_out + (Cfg::TMA_OUT ? TC_EPI_GROUPS * p.nbuf * Cfg::BUF_BYTES : 0));
+    // (EPI = 2, fused stem: the operand region is ROLL_R rolling activation rows + the resident filter, followed by the 768-byte
+    //  cross-warp edge buffer of the pooling epilogue instead of store-staging buffers)
+    constexpr int ROLL_R = SPLIT ? 5 : 6;
+    constexpr uint32_t ROLL_SLOT = Cfg::PLANES * TC_A_BYTES, ROLL_B = Cfg::PLANES * Cfg::B_BYTES, ROLL_EDGE = 768;
+    uint8_t* s_out = smem_gen + (EPI == 2 ? ROLL_R * ROLL_SLOT + 4 * ROLL_B : STAGES * Cfg::STAGE_BYTES);  // 1024-aligned
+    float* s_scale = reinterpret_cast<float*>(s_out + (EPI == 2 ? ROLL_EDGE : (Cfg::TMA_OUT ? TC_EPI_GROUPS * p.nbuf * Cfg::BUF_BYTES : 0)));
     float* s_shift = s_scale + BN;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * MAXST, bar_tfull = bar_empty + 8 * MAXST,
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (SPLIT) { tma_prefetch_desc(&p.b[1]); tma_prefetch_desc(&p.a[1][0]); }
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < (EPI == 2 ? ROLL_R : STAGES); ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * TC_EPI_GROUPS); }
         for (int s = 0; s < 3 * TC_EPI_GROUPS; ++s) mbar_init(bar_res + 8 * s, 1);
         fence_barrier_init();
@@ -149,9 +153,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
 
-    if (warp == 0) {
+    // Fused stem (EPI = 2): the operand region is NOT a ring of (A, B) stages.  The whole filter (4 K-chunks) stays resident, and the A
+    // side is a rolling window of space-to-depth rows: conv row oy reads s2d rows oy..oy+3 (K-chunk ky = row oy+ky), and the CTA walks
+    // the rows of a band top to bottom, so every row is loaded once per band instead of four times -- six times less L2 -> SM traffic than
+    // re-fetching (A, B) per K-step, which is what bounded the first version of this kernel (ncu: 11.7 TB/s of TMA reads, tensor pipe 39 %).
+    // (a window of exactly four rows would leave ONE load in flight per CTA, issued only after chunk 0 of a conv row has retired: measured,
+    //  the per-row load latency (~1.7 us for the two 16 KiB boxes) then paced the whole kernel; ROLL_R - 4 extra slots keep loads ahead.)
+    //   slot(L) = L % ROLL_R for the L-th row load of this CTA; a slot is free again once the MMAs of its LAST reader are done: chunk ky = 0 of
+    //   the conv row that starts at it (or, for the three bottom rows of a band, chunks ky = 1..3 of the band's last conv row).
+    const uint32_t roll_b_base = smem_base + ROLL_R * ROLL_SLOT;
+    if (EPI == 2 && warp == 0) {
+        {   // (all 32 lanes walk the loop; the single-thread instructions are predicated on elect_one())
+            const uint32_t a_box_bytes = (uint32_t)p.bw * TC_BK * 2;
+            if (elect_one()) {
+                mbar_expect_tx(bar_res, 4 * ROLL_B);
+                for (int ky = 0; ky < 4; ++ky) {
+                    tma_load_2d(roll_b_base + ky * ROLL_B, &p.b[0], bar_res, ky * TC_BK, 0);
+                    if (SPLIT) tma_load_2d(roll_b_base + ky * ROLL_B + Cfg::B_BYTES, &p.b[1], bar_res, ky * TC_BK, 0);
+                }
+            }
+            uint32_t L = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileSeq sq = decode_seq(p, tile);
+                for (int r = 0; r < sq.count + 3; ++r, ++L) {
+                    const uint32_t slot = L % ROLL_R, full = bar_full + 8 * slot;
+                    mbar_wait(bar_empty + 8 * slot, ((L / ROLL_R) & 1) ^ 1);
+                    const uint32_t sa = smem_base + slot * ROLL_SLOT;
+                    if (elect_one()) {
+                        mbar_expect_tx(full, Cfg::PLANES * a_box_bytes);
+                        if (p.a_rank5) {
+                            tma_load_5d(sa, &p.a[0][0], full, 0, 0, 0, sq.th + r, sq.img);
+                            if (SPLIT) tma_load_5d(sa + TC_A_BYTES, &p.a[1][0], full, 0, 0, 0, sq.th + r, sq.img);
+                        } else {
+                            tma_load_4d(sa, &p.a[0][0], full, 0, 0, sq.th + r, sq.img);
+                            if (SPLIT) tma_load_4d(sa + TC_A_BYTES, &p.a[1][0], full, 0, 0, sq.th + r, sq.img);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (EPI == 2 && warp == 1) {
+        {
+            const uint32_t idesc = make_idesc(TC_BM, BN), idesc2 = make_idesc(TC_BM, 2 * BN);
+            const bool fuse = Cfg::XACC && p.fuse_cross;
+            mbar_wait(bar_res, 0);   // the filter is resident
+            tc_fence_after();
+            uint32_t base = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int count = decode_seq(p, tile).count;
+                for (int q = 0; q < count; ++q, ++it) {
+                    const int as = it & 1;
+                    mbar_wait(bar_tempty + 8 * as, ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * Cfg::ACC_COLS;
+                    const uint32_t tmem_x = Cfg::XACC ? tmem_d + BN : tmem_d;
+                    for (int ky = 0; ky < 4; ++ky) {
+                        const uint32_t L = base + q + ky, slot = L % ROLL_R;
+                        mbar_wait(bar_full + 8 * slot, (L / ROLL_R) & 1);   // (returns at once for the rows earlier conv rows already waited for)
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + slot * ROLL_SLOT, sb = roll_b_base + ky * ROLL_B;
+                        if (elect_one()) {
+                            // (descriptors of the four k16 slices / the lo planes are the base descriptor plus a constant: the start-address
+                            //  field counts 16-byte units and shared-memory addresses stay far below its 14 bits)
+                            const uint64_t a0 = make_smem_desc(sa), b0 = make_smem_desc(sb);
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; ++k) {
+                                const uint64_t a_hi = a0 + 2 * k, b_hi = b0 + 2 * k;
+                                if (SPLIT && fuse) {
+                                    umma_f16(tmem_d, a_hi, b_hi, idesc2, (ky | k) ? 1u : 0u);
+                                    umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
+                                    continue;
+                                }
+                                umma_f16(tmem_d, a_hi, b_hi, idesc, (ky | k) ? 1u : 0u);
+                                if (SPLIT) {
+                                    umma_f16(tmem_x, a_hi, b_hi + (Cfg::B_BYTES >> 4), idesc, Cfg::XACC ? ((ky | k) ? 1u : 0u) : 1u);
+                                    umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
+                                }
+                            }
+                            if (ky == 0 || q == count - 1) umma_commit(bar_empty + 8 * slot);   // last reader of this row is done
+                            if (ky == 3) umma_commit(bar_tfull + 8 * as);
+                        }
+                        __syncwarp();
+                    }
+                }
+                base += count + 3;
+            }
+        }
+    } else if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        {   // (all 32 lanes walk the loop; the single-thread instructions are predicated on elect_one(), see tc_ptx.cuh)
             const uint32_t a_box_bytes = (uint32_t)p.bw * p.bh * TC_BK * 2;
             const uint32_t tx = Cfg::PLANES * (a_box_bytes + Cfg::B_BYTES);
             int stage = 0;
@@ -174,18 +266,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
-                    mbar_expect_tx(full, tx);
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::PLANES * TC_A_BYTES;
-                    if (EPI == 2 && p.a_rank5) {
-                        tma_load_5d(sa, &p.a[0][0], full, 0, 0, w0 + offw, h0 + offh, img);
-                        if (SPLIT) tma_load_5d(sa + TC_A_BYTES, &p.a[1][0], full, 0, 0, w0 + offw, h0 + offh, img);
-                    } else {
+                    if (elect_one()) {
+                        mbar_expect_tx(full, tx);
                         tma_load_4d(sa, &p.a[0][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
-                        if (SPLIT) tma_load_4d(sa + TC_A_BYTES, &p.a[1][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
+                        tma_load_2d(sb, &p.b[0], full, ks * TC_BK, nb * BN);
+                        if (SPLIT) {
+                            tma_load_4d(sa + TC_A_BYTES, &p.a[1][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
+                            tma_load_2d(sb + Cfg::B_BYTES, &p.b[1], full, ks * TC_BK, nb * BN);
+                        }
                     }
-                    tma_load_2d(sb, &p.b[0], full, ks * TC_BK, nb * BN);
-                    if (SPLIT) tma_load_2d(sb + Cfg::B_BYTES, &p.b[1], full, ks * TC_BK, nb * BN);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 }
@@ -199,17 +291,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const int tw2 = mt2 % p.tiles_w; mt2 /= p.tiles_w;
                         const int th2 = mt2 % p.tiles_h;
                         const int img2 = mt2 / p.tiles_h;
-                        for (int cc2 = 0; cc2 < p.cin_chunks; ++cc2) {
-                            tma_prefetch_l2_4d(&p.a[0][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
-                            if (SPLIT) tma_prefetch_l2_4d(&p.a[1][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
-                        }
+                        if (elect_one())
+                            for (int cc2 = 0; cc2 < p.cin_chunks; ++cc2) {
+                                tma_prefetch_l2_4d(&p.a[0][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
+                                if (SPLIT) tma_prefetch_l2_4d(&p.a[1][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
+                            }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        {   // (all 32 lanes walk the loop and wait on the barriers; one elected lane issues the MMAs and commits of a K-step)
             const uint32_t idesc = make_idesc(TC_BM, BN);
             // Fused cross term: the lo weight tile sits right behind the hi tile in the stage and `cross` right behind `main` in
             // TMEM, so ONE MMA with N = 2*BN computes a_hi*w_hi -> main and a_hi*w_lo -> cross while reading a_hi from shared
@@ -232,26 +326,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::PLANES * TC_A_BYTES;
+                    if (elect_one()) {
+                        // (descriptors of the four k16 slices / the lo planes are the base descriptor plus a constant: the start-address field
+                        //  counts 16-byte units and shared-memory addresses stay far below its 14 bits -- one shift + mask per K-step, not per MMA)
+                        const uint64_t a0 = make_smem_desc(sa), b0 = make_smem_desc(sb);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
-                        const uint64_t a_hi = make_smem_desc(sa + k * 32), b_hi = make_smem_desc(sb + k * 32);
-                        if (SPLIT && fuse) {
-                            const uint64_t a_lo = make_smem_desc(sa + TC_A_BYTES + k * 32);
-                            umma_f16(tmem_d, a_hi, b_hi, idesc2, (ks | k) ? 1u : 0u);
-                            umma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
-                            continue;
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            const uint64_t a_hi = a0 + 2 * k, b_hi = b0 + 2 * k;
+                            if (SPLIT && fuse) {
+                                umma_f16(tmem_d, a_hi, b_hi, idesc2, (ks | k) ? 1u : 0u);
+                                umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
+                                continue;
+                            }
+                            umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) ? 1u : 0u);
+                            if (SPLIT) {
+                                umma_f16(tmem_x, a_hi, b_hi + (Cfg::B_BYTES >> 4), idesc, Cfg::XACC ? ((ks | k) ? 1u : 0u) : 1u);
+                                umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
+                            }
                         }
-                        umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) ? 1u : 0u);
-                        if (SPLIT) {
-                            const uint64_t a_lo = make_smem_desc(sa + TC_A_BYTES + k * 32), b_lo = make_smem_desc(sb + Cfg::B_BYTES + k * 32);
-                            umma_f16(tmem_x, a_hi, b_lo, idesc, Cfg::XACC ? ((ks | k) ? 1u : 0u) : 1u);
-                            umma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
-                        }
+                        umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
+                        if (ks == nK - 1) umma_commit(bar_tfull + 8 * as);  // accumulator complete
                     }
-                    umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * as);  // accumulator complete
             }
         }
     } else if (warp >= 4) {
@@ -354,19 +452,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       } else if constexpr (EPI == 2) {
         // ================================ epilogue: fused stem + max-pool ================================
+        // thread = (pixel = TMEM lane, group g = channels [32g, 32g + 32)).  Vertical 3-tap maximum: a running maximum in registers.
+        // Horizontal 3-tap / stride-2 maximum: warp shuffles (the even pixel 2px collects 2px - 1 and 2px + 1); the one neighbour that
+        // lives in another warp (pixel 32w - 1, lane 31 of warp w - 1) crosses through a 128-byte shared-memory slot per (group, warp).
         static_assert(EPI != 2 || BN == 64, "the stem has 64 output channels");
         const int ew = warp & 3, eg = (warp - 4) >> 2, row = ew * 32 + lane, eall = threadIdx.x - 128;
         for (int i = eall; i < BN; i += 128 * TC_EPI_GROUPS) { s_scale[i] = __ldg(p.scale + i); s_shift[i] = __ldg(p.shift + i); }
         asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");
-        uint8_t* rowbuf = s_out;   // 128 pixels x 64 channels fp32, 16-byte chunks XOR-swizzled with the pixel index (32 KiB = the two staging buffers)
+        float* edge = reinterpret_cast<float*>(s_out);   // [group][warp 0..2][32 channels]
         float vmax[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) vmax[j] = -FLT_MAX;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileSeq sq = decode_seq(p, tile);
-            for (int q = 0; q < sq.count; ++q, ++it) {
-                const int oy = sq.th + q;
+            const int count = sq.count, th0 = sq.th, img = sq.img;
+            for (int q = 0; q < count; ++q, ++it) {
+                const int oy = th0 + q;
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(bar_tfull + 8 * as, aphase);
@@ -395,37 +497,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (p.relu) y[j] = fmaxf(y[j], 0.f);
                     vmax[j] = first ? fmaxf(-FLT_MAX, y[j]) : fmaxf(vmax[j], y[j]);
                 }
-                if (emit) {   // (CTA-uniform)
-                    if (row < p.wo) {
-                        uint8_t* rp = rowbuf + row * 256;
-#pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4)
-                            *reinterpret_cast<float4*>(rp + (((eg * 8 + g4) ^ (row & 7)) << 4)) =
-                                make_float4(vmax[4 * g4], vmax[4 * g4 + 1], vmax[4 * g4 + 2], vmax[4 * g4 + 3]);
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");
+                if (emit) {   // (uniform over the CTA)
                     const int py = oy >> 1;   // odd row 2py+1 -> py ; even last row 2py -> py
-                    for (int idx = eall; idx < p.pool_po * 16; idx += 128 * TC_EPI_GROUPS) {
-                        const int px = idx >> 4, cg = idx & 15;   // pooled pixel, group of 4 channels
-                        float4 m = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");   // the previous emit's edge values have been read
+                    if (lane == 31 && ew < 3) {
+                        float4* e4 = reinterpret_cast<float4*>(edge + (eg * 3 + ew) * 32);
 #pragma unroll
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const int xx = 2 * px - 1 + dx;
-                            if (xx < 0 || xx >= p.wo) continue;
-                            const float4 a = *reinterpret_cast<const float4*>(rowbuf + xx * 256 + ((cg ^ (xx & 7)) << 4));
-                            m.x = fmaxf(m.x, a.x); m.y = fmaxf(m.y, a.y); m.z = fmaxf(m.z, a.z); m.w = fmaxf(m.w, a.w);
-                        }
-                        const __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
-                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-                        const __half2 l0 = __floats2half2_rn(m.x - f0.x, m.y - f0.y), l1 = __floats2half2_rn(m.z - f1.x, m.w - f1.y);
-                        uint2 a, c;
-                        a.x = *reinterpret_cast<const uint32_t*>(&h0); a.y = *reinterpret_cast<const uint32_t*>(&h1);
-                        c.x = *reinterpret_cast<const uint32_t*>(&l0); c.y = *reinterpret_cast<const uint32_t*>(&l1);
-                        const size_t o = (((size_t)sq.img * p.pool_po + py) * p.pool_po + px) * 16 + cg;   // in units of 4 channels
-                        reinterpret_cast<uint2*>(p.out_hi)[o] = a;
-                        if (SPLIT) reinterpret_cast<uint2*>(p.out_lo)[o] = c;
+                        for (int g4 = 0; g4 < 8; ++g4) e4[g4] = make_float4(vmax[4 * g4], vmax[4 * g4 + 1], vmax[4 * g4 + 2], vmax[4 * g4 + 3]);
                     }
-                    asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");   // the row buffer may be overwritten by the next emit
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
+                    const bool writer = (row & 1) == 0 && row < p.wo;   // even pixel 2px writes pooled pixel px
+                    const bool has_right = row + 1 < p.wo;
+                    const float* left_edge = edge + (eg * 3 + (ew > 0 ? ew - 1 : 0)) * 32;
+                    const size_t o8 = ((((size_t)img * p.pool_po + py) * p.pool_po + (row >> 1)) * 64 + eg * 32) / 8;   // in uint4 (8 halves)
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        float m[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int j = g4 * 8 + e;
+                            float left = __shfl_up_sync(0xffffffffu, vmax[j], 1);
+                            float right = __shfl_down_sync(0xffffffffu, vmax[j], 1);
+                            if (lane == 0) left = ew > 0 ? left_edge[j] : -FLT_MAX;
+                            if (!has_right) right = -FLT_MAX;
+                            m[e] = fmaxf(fmaxf(fmaxf(-FLT_MAX, left), vmax[j]), right);
+                        }
+                        if (writer) {
+                            uint4 a, c;
+                            __half2* ah = reinterpret_cast<__half2*>(&a);
+                            __half2* cl = reinterpret_cast<__half2*>(&c);
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2) {
+                                const __half2 hh = __floats2half2_rn(m[2 * e2], m[2 * e2 + 1]);
+                                const float2 hf = __half22float2(hh);
+                                ah[e2] = hh;
+                                cl[e2] = __floats2half2_rn(m[2 * e2] - hf.x, m[2 * e2 + 1] - hf.y);
+                            }
+                            reinterpret_cast<uint4*>(p.out_hi)[o8 + g4] = a;
+                            if (SPLIT) reinterpret_cast<uint4*>(p.out_lo)[o8 + g4] = c;
+                        }
+                    }
                     if (odd) {   // conv row 2py+1 is also the first row of pooled row py+1
 #pragma unroll
                         for (int j = 0; j < 32; ++j) vmax[j] = fmaxf(-FLT_MAX, y[j]);
@@ -460,7 +571,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tma_load_4d(dst, &p.r[0], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
             if (SPLIT) tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
         };
-        if (p.tma_res && et == 0 && (int)blockIdx.x < p.num_tiles && eg * 32 < BN) issue_res(blockIdx.x, eg * 32, 0);
+        // (single-thread TMA work of a group: one ELECTED lane of its first warp -- elect.sync picks the same lane every time, so the bulk
+        //  async-groups it commits are the ones it later waits for; see elect_one() in tc_ptx.cuh for why not `if (et == 0)`)
+        if (p.tma_res && et < 32 && (int)blockIdx.x < p.num_tiles && eg * 32 < BN) { if (elect_one()) issue_res(blockIdx.x, eg * 32, 0); __syncwarp(); }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int nb = tile % p.n_tiles_n;
@@ -496,11 +609,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS;
 #pragma unroll 1
             for (int c0 = cfirst; c0 < BN; c0 += cstep) {
-                if (p.tma_res && et == 0) {
+                if (p.tma_res && et < 32) {
                     int nc0 = c0 + cstep, ntile = tile;
                     const bool wrap = nc0 >= BN;
                     if (wrap) { nc0 = cfirst; ntile = tile + gridDim.x; }
-                    if (ntile < p.num_tiles) {
+                    if (ntile < p.num_tiles && elect_one()) {
                         bulk_wait_read<1>();
                         issue_res(ntile, nc0, (gc + 1) % 3);
                         if (wrap && p.l2_prefetch) {
@@ -517,6 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             }
                         }
                     }
+                    __syncwarp();
                 }
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
@@ -572,7 +686,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         if (p.tma_f32) {
                             // fp32-only outputs (encoders -> xcorr, last tower conv -> pred): same staging buffer, rows of 128 B
                             // (32 floats) in the 128B-swizzled layout of the fp32 output map, ONE bulk tensor store per chunk
-                            if (et == 0) bulk_wait_read<0>();
+                            if (et < 32) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }
                             asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
                             uint8_t* rp32 = s_out + buf * Cfg::BUF_BYTES + row * 128;
                             const int sw7 = row & 7;
@@ -581,9 +695,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                 *reinterpret_cast<float4*>(rp32 + ((q ^ sw7) << 4)) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
                             fence_proxy_async_smem();
                             asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
-                            if (et == 0) {
-                                tma_store_4d(&p.o[0], s_out_u32 + buf * Cfg::BUF_BYTES, n0 + c0, tw * p.bw, th * p.bh, img);
-                                bulk_commit();
+                            if (et < 32) {
+                                if (elect_one()) {
+                                    tma_store_4d(&p.o[0], s_out_u32 + buf * Cfg::BUF_BYTES, n0 + c0, tw * p.bw, th * p.bh, img);
+                                    bulk_commit();
+                                }
+                                __syncwarp();
                             }
                             ++gc;
                             continue;
@@ -608,7 +725,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                 for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
                             }
                         } else {
-                            if (et == 0) bulk_wait_read<0>();
+                            if (et < 32) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }
                             asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
                         }
 #pragma unroll
@@ -629,11 +746,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         }
                         fence_proxy_async_smem();
                         asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");
-                        if (et == 0) {
+                        if (et < 32) {
                             const uint32_t src = s_out_u32 + buf * Cfg::BUF_BYTES;
-                            tma_store_4d(&p.o[0], src, n0 + c0, tw * p.bw, th * p.bh, img);
-                            if (SPLIT) tma_store_4d(&p.o[1], src + TC_BM * 64, n0 + c0, tw * p.bw, th * p.bh, img);
-                            bulk_commit();
+                            if (elect_one()) {
+                                tma_store_4d(&p.o[0], src, n0 + c0, tw * p.bw, th * p.bh, img);
+                                if (SPLIT) tma_store_4d(&p.o[1], src + TC_BM * 64, n0 + c0, tw * p.bw, th * p.bh, img);
+                                bulk_commit();
+                            }
+                            __syncwarp();
                         }
                         ++gc;
                     } else if (p.out_hi) {
@@ -670,7 +790,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     }
-    if (threadIdx.x >= 128 && ((threadIdx.x - 128) & 127) == 0 && p.tma_store) bulk_wait_read<0>();  // staging must outlive the stores' reads
+    if (threadIdx.x >= 128 && ((threadIdx.x - 128) & 127) < 32 && p.tma_store) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }  // staging must outlive the stores' reads
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -741,7 +861,13 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     p.nbuf = EPI == 1 ? 0 : (p.tma_res ? 3 : 1);   // (the fused Conf_Fusion epilogue stores from registers: no staging buffers; the
                                                    //  stem + max-pool epilogue uses the two 16 KiB buffers of nbuf = 1 as its row buffer)
     p.stages = p.tma_res ? (Cfg::STAGES_RES < Cfg::STAGES ? Cfg::STAGES_RES : Cfg::STAGES) : Cfg::STAGES;
-    const int smem = Cfg::smem_bytes(p.stages, p.nbuf);
+    int smem = Cfg::smem_bytes(p.stages, p.nbuf);
+    if (EPI == 2) {   // rolling activation rows + resident filter + edge buffer (must match the kernel's carve-up)
+        constexpr int ROLL_R = SPLIT ? 5 : 6;
+        p.stages = ROLL_R;
+        p.nbuf = 0;
+        smem = ROLL_R * Cfg::PLANES * TC_A_BYTES + 4 * Cfg::PLANES * Cfg::B_BYTES + 768 + Cfg::MISC_BYTES;
+    }
     USOT_REQUIRE(smem <= 227 * 1024, "conv_tc: shared memory plan exceeds 227 KiB");
     if (p.pdl) {
         cudaLaunchConfig_t cfg;

@@ -42,6 +42,19 @@ static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) 
         }
     }
 }
+// One lane of a fully converged warp (elect.sync).  The producer / MMA-issuer warps keep all 32 lanes in the same control flow and
+// predicate only the single-thread instructions (TMA, tcgen05.mma / commit, expect_tx) on this: the operands then live in uniform
+// registers.  Issuing them from an `if (lane == 0)` region instead makes the compiler wrap every UTCHMMA / UTMALDG in an
+// ELECT / BRA.U.ANY "waterfall" loop (~130 issue cycles per MMA measured on the stem kernel, which made the issuing thread the bottleneck).
+static __device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 static __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 static __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 static __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0 && p_begin < p_end) {
+        if (p_begin < p_end) {   // (all 32 lanes walk the loop; the single-thread instructions are predicated on elect_one(), see tc_ptx.cuh)
             const int kh = tap / p.kw, kwi = tap - kh * p.kw;
             int offh = kh * p.dh - p.ph, offw = kwi * p.dw_dil - p.pw, par = 0;
             if (p.stride == 2) {
@@ -118,20 +118,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 const int h0 = th * p.bh, w0 = tw * p.bw;
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 const uint32_t full = bar_full + 8 * stage;
-                mbar_expect_tx(full, tx);
                 const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                for (int pl = 0; pl < planes; ++pl) {
-                    for (int blk = 0; blk < a_blocks; ++blk)
-                        tma_load_4d(sa + (pl * 2 + blk) * WG_BOX_BYTES, &p.a[pl][par], full, ci0 + blk * 64, w0 + offw, h0 + offh, img);
-                    for (int blk = 0; blk < BN / 64; ++blk)
-                        tma_load_4d(sb + (pl * (BN / 64) + blk) * WG_BOX_BYTES, &p.b[pl], full, co0 + blk * 64, w0, h0, img);
+                if (elect_one()) {
+                    mbar_expect_tx(full, tx);
+                    for (int pl = 0; pl < planes; ++pl) {
+                        for (int blk = 0; blk < a_blocks; ++blk)
+                            tma_load_4d(sa + (pl * 2 + blk) * WG_BOX_BYTES, &p.a[pl][par], full, ci0 + blk * 64, w0 + offw, h0 + offh, img);
+                        for (int blk = 0; blk < BN / 64; ++blk)
+                            tma_load_4d(sb + (pl * (BN / 64) + blk) * WG_BOX_BYTES, &p.b[pl], full, co0 + blk * 64, w0, h0, img);
+                    }
                 }
+                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0 && p_begin < p_end) {
+        if (p_begin < p_end) {   // (all lanes wait on the barriers; one elected lane issues the MMAs and commits of a stage)
             const uint32_t idesc = make_idesc_mn(WG_BM, BN), idesc2 = make_idesc_mn(WG_BM, 2 * BN);
             const uint32_t tmem_d = tmem_base, tmem_x = tmem_base + BN;
             int stage = 0;
@@ -141,23 +144,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < WG_KP / 16; ++k) {   // 16 pixels per MMA = two 8-pixel groups = 2048 B
-                    const uint64_t a_hi = make_smem_desc_mn(sa + k * 2048, WG_BOX_BYTES), b_hi = make_smem_desc_mn(sb + k * 2048, WG_BOX_BYTES);
-                    if (p.split) {
-                        // [b_hi blocks | b_lo blocks] are contiguous with a uniform block stride: ONE N = 2*BN MMA gives x_hi*dy_hi -> main, x_hi*dy_lo -> cross
-                        const uint64_t a_lo = make_smem_desc_mn(sa + 2 * WG_BOX_BYTES + k * 2048, WG_BOX_BYTES);
-                        umma_f16(tmem_d, a_hi, b_hi, idesc2, first ? 0u : 1u);
-                        umma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
-                    } else {
-                        umma_f16(tmem_d, a_hi, b_hi, idesc, first ? 0u : 1u);
+                    for (int k = 0; k < WG_KP / 16; ++k) {   // 16 pixels per MMA = two 8-pixel groups = 2048 B
+                        const uint64_t a_hi = make_smem_desc_mn(sa + k * 2048, WG_BOX_BYTES), b_hi = make_smem_desc_mn(sb + k * 2048, WG_BOX_BYTES);
+                        const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                        if (p.split) {
+                            // [b_hi blocks | b_lo blocks] are contiguous with a uniform block stride: ONE N = 2*BN MMA gives x_hi*dy_hi -> main, x_hi*dy_lo -> cross
+                            const uint64_t a_lo = make_smem_desc_mn(sa + 2 * WG_BOX_BYTES + k * 2048, WG_BOX_BYTES);
+                            umma_f16(tmem_d, a_hi, b_hi, idesc2, acc);
+                            umma_f16(tmem_x, a_lo, b_hi, idesc, 1u);
+                        } else {
+                            umma_f16(tmem_d, a_hi, b_hi, idesc, acc);
+                        }
                     }
-                    first = false;
+                    umma_commit(bar_empty + 8 * stage);
+                    if (pt == p_end - 1) umma_commit(bar_done);
                 }
-                umma_commit(bar_empty + 8 * stage);
+                __syncwarp();
+                first = false;
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(bar_done);
         }
     } else if (warp >= 4) {
         // ================================ epilogue: TMEM -> scale -> atomic add into dW ================================

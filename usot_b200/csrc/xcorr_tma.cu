@@ -295,18 +295,21 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 3) groupdw_ffma2_kernel(const _
 
     if (warp == NCW) {
         // ------------------------------- producer -------------------------------
-        if (lane == 0) {
-            tma_prefetch_desc(&p.m11); tma_prefetch_desc(&p.m12); tma_prefetch_desc(&p.m21);
-            for (int t = r0; t < t_end; ++t) {
-                const int lt = t - r0, s = lt % G2_STAGES;
-                if (lt >= G2_STAGES) mbar_wait(bar_empty + 8 * s, ((lt / G2_STAGES) + 1) & 1);
-                const bool has12 = t >= 2 && t - 2 < H12;
-                const uint32_t full = bar_full + 8 * s, dst = base + s * stage_bytes;
+        // (all 32 lanes walk the loop; expect_tx + the three row loads are issued by one ELECTED lane, see elect_one() in tc_ptx.cuh)
+        if (lane == 0) { tma_prefetch_desc(&p.m11); tma_prefetch_desc(&p.m12); tma_prefetch_desc(&p.m21); }
+        __syncwarp();
+        for (int t = r0; t < t_end; ++t) {
+            const int lt = t - r0, s = lt % G2_STAGES;
+            if (lt >= G2_STAGES) mbar_wait(bar_empty + 8 * s, ((lt / G2_STAGES) + 1) & 1);
+            const bool has12 = t >= 2 && t - 2 < H12;
+            const uint32_t full = bar_full + 8 * s, dst = base + s * stage_bytes;
+            if (elect_one()) {
                 mbar_expect_tx(full, (uint32_t)(row11 + row21 + (has12 ? row12 : 0)));
                 tma_load_4d(dst, &p.m11, full, cblk * 64, 0, t, xb);
                 tma_load_4d(dst + row11, &p.m21, full, cblk * 64, 0, t, xb);
                 if (has12) tma_load_4d(dst + row11 + row21, &p.m12, full, cblk * 64, 0, t - 2, xb);
             }
+            __syncwarp();
         }
         return;
     }
