@@ -567,7 +567,7 @@ def main():
         pr_gbs = pr["bytes"] / (pr["ms"] / 1e3) / 1e9 if pr["ms"] > 0 else 0.0
         step_ms_prof = sum(f["ms"] for f in prof.values()) / nprof
         traffic = {}
-        for name in ("r02_roofline_traffic.json", "r01b_roofline_traffic.json"):
+        for name in ("r02b_roofline_traffic.json", "r02_roofline_traffic.json", "r01b_roofline_traffic.json"):
             tp = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tp):
                 with open(tp) as f:
