@@ -14,7 +14,7 @@ def _set(name, v):
     _lib.check(_lib.load().usot_set_tunable(name.encode(), v))
 
 
-DEFAULTS = {"tc_pdl": 1, "groupdw_row_split": 1, "tc_latency_split": 1, "tc_l2_prefetch": 0, "tc_tma_f32": 1, "tc_fuse_cross": 1, "tc_tma_store": 1, "tc_tma_res": 1, "stem_tc": 1, "groupdw_tma": 2, "pred_tma_min_batch": 48, "tc_bn_max": 256, "tc_split_bn_max": 128, "groupdw_warps4": 1, "conf_fusion_fused": 1, "stem_pool_fused": 1, "graph_max_batch": 8}
+DEFAULTS = {"tc_pdl": 1, "groupdw_row_split": 1, "tc_latency_split": 1, "tc_l2_prefetch": 0, "tc_tma_f32": 1, "tc_fuse_cross": 1, "tc_tma_store": 1, "tc_tma_res": 1, "stem_tc": 1, "groupdw_tma": 2, "pred_tma_min_batch": 48, "tc_bn_max": 256, "tc_split_bn_max": 128, "groupdw_warps4": 1, "conf_fusion_fused": 1, "tc_multi_image_tiles": 1, "stem_pool_fused": 1, "graph_max_batch": 8}
 
 
 @pytest.fixture()
@@ -27,7 +27,7 @@ def net():
         _set(k, v)
 
 
-@pytest.mark.parametrize("knob,value,exact", [("tc_fuse_cross", 0, False), ("tc_tma_f32", 0, True), ("tc_l2_prefetch", 1, True), ("tc_latency_split", 0, True), ("groupdw_row_split", 0, True), ("tc_pdl", 0, True), ("tc_tma_store", 0, True), ("tc_tma_res", 0, True), ("groupdw_tma", 0, True), ("groupdw_tma", 1, True), ("groupdw_warps4", 0, True), ("stem_pool_fused", 0, False), ("conf_fusion_fused", 0, True),
+@pytest.mark.parametrize("knob,value,exact", [("tc_fuse_cross", 0, False), ("tc_tma_f32", 0, True), ("tc_l2_prefetch", 1, True), ("tc_latency_split", 0, True), ("groupdw_row_split", 0, True), ("tc_pdl", 0, True), ("tc_tma_store", 0, True), ("tc_tma_res", 0, True), ("groupdw_tma", 0, True), ("groupdw_tma", 1, True), ("groupdw_warps4", 0, True), ("stem_pool_fused", 0, False), ("tc_multi_image_tiles", 0, True), ("conf_fusion_fused", 0, True),
                                               ("stem_tc", 0, False), ("pred_tma_min_batch", 1, True), ("tc_bn_max", 64, False)])
 def test_knob_keeps_results(net, knob, value, exact):
     z, x, tb, sb = O.synth_inputs(91, batch=3)
@@ -122,3 +122,35 @@ def test_fused_stem_maxpool_feature_map_agrees_with_two_kernels(precision, tol, 
         for k, v in DEFAULTS.items():
             _set(k, v)
         eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+@pytest.mark.parametrize("batch", [4, 5, 13])
+def test_multi_image_tiles_keep_results_bit_identical(precision, batch):
+    """M tiles that span several images (one TMA box {64 ch, bw, bh, bimg}: a 31-wide map fills 124 of 128 MMA rows with ONE row of FOUR
+    images instead of four rows of one) change only which pixels share a tile: every output element keeps its accumulation order, so
+    track() with a memory queue must agree bit for bit with the one-image-per-tile plan, also when the batch is not a multiple of bimg."""
+    from usot_b200 import USOT
+    n = USOT(precision=precision)
+    n.load_state_dict(load_weights("damp025"))
+    n = n.eval().cuda()
+    try:
+        _set("graph_max_batch", 0)
+        z, x, tb, sb = O.synth_inputs(95, batch=batch)
+        n.template(z.cuda(), tb.cuda())
+        nq = 2
+        feats = n.extract_memory_feature(ori_x=x[:4].cuda(), search_bbox=sb[:4].cuda())
+        pick = torch.tensor([(b * nq + q) % 4 for b in range(batch) for q in range(nq)]).cuda()
+        mem = feats[pick].contiguous(memory_format=torch.channels_last)
+        score = torch.full((batch, nq), 0.9).cuda()
+        _set("tc_multi_image_tiles", 0)
+        n.template(z.cuda(), tb.cuda())
+        ref = [t.clone() for t in n.track(x.cuda(), mem, score)]
+        _set("tc_multi_image_tiles", 1)
+        n.template(z.cuda(), tb.cuda())
+        out = n.track(x.cuda(), mem, score)
+        for a, b in zip(out, ref):
+            assert torch.isfinite(a).all() and torch.equal(a, b), float((a - b).abs().max())
+    finally:
+        for k, v in DEFAULTS.items():
+            _set(k, v)

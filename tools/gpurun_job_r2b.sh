@@ -1,12 +1,14 @@
-# Second-session job of round 2: parity tests of the conv / stem / fusion kernels, then bench lines + ncu of the stem.
+# Second-session job of round 2: parity tests of the conv / stem / fusion kernels, then A/B bench lines.
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_standalone_ops.py tests/test_gpu_tunables.py tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_gpu_configs.py -q -m gpu -x --durations=5 2>&1 | tail -12 > gpurun_out/r2b_pytest.log
+timeout 1200 python -m pytest tests/test_gpu_tunables.py tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_gpu_configs.py tests/test_gpu_train_ops.py -q -m gpu -x --durations=5 2>&1 | tail -12 > gpurun_out/r2b_pytest.log
 tail -12 gpurun_out/r2b_pytest.log
 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err
+timeout 300 python bench.py --no-cpu-baseline --tunable tc_multi_image_tiles=0 > gpurun_out/r2b_bench_ab.json 2> gpurun_out/r2b_bench_ab.err
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r2b_bench2.json 2> gpurun_out/r2b_bench2.err
+timeout 300 python bench.py --no-cpu-baseline --tunable tc_multi_image_tiles=0 > gpurun_out/r2b_bench_ab2.json 2> gpurun_out/r2b_bench_ab2.err
 timeout 300 python bench.py --no-cpu-baseline --precision fp16 > gpurun_out/r2b_bench_fp16.json 2> gpurun_out/r2b_bench_fp16.err
-timeout 300 python bench.py --config 3 --no-cpu-baseline > gpurun_out/r2b_c3.json 2> gpurun_out/r2b_c3.err
-timeout 300 python bench.py --config 3 --no-cpu-baseline --precision fp16 > gpurun_out/r2b_c3_fp16.json 2> gpurun_out/r2b_c3_fp16.err
-for f in r2b_bench r2b_bench_fp16 r2b_c3 r2b_c3_fp16; do echo "== $f"; python - "$f" <<'PY'
+timeout 300 python bench.py --no-cpu-baseline --precision fp16 --tunable tc_multi_image_tiles=0 > gpurun_out/r2b_bench_fp16_ab.json 2> gpurun_out/r2b_bench_fp16_ab.err
+for f in r2b_bench r2b_bench_ab r2b_bench2 r2b_bench_ab2 r2b_bench_fp16 r2b_bench_fp16_ab; do echo "== $f"; python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(f"gpurun_out/{sys.argv[1]}.json").read().strip().splitlines()[-1])
@@ -15,5 +17,3 @@ except Exception as e:
     print("ERR", e); print(open(f"gpurun_out/{sys.argv[1]}.err").read()[-1500:])
 PY
 done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel --launch-skip 2 -c 1 -o gpurun_out/r02b_stem_gemm_pool_roll -f python tools/stem_case.py > gpurun_out/ncu_s1.log 2>&1
-tail -n 2 gpurun_out/ncu_s1.log

@@ -86,7 +86,7 @@ static __device__ __forceinline__ TileSeq decode_seq(const TcParams& p, int tile
     int mt = tile / p.n_tiles_n;
     s.tw = mt % p.tiles_w; mt /= p.tiles_w;
     s.th = mt % p.tiles_h;
-    s.img = (mt / p.tiles_h) * p.group;
+    s.img = (mt / p.tiles_h) * p.group * p.bimg;   // first image of the tile (bimg == 1 whenever group > 1)
     s.count = p.group; s.dth = 0; s.dimg = 1;
     return s;
 }
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     } else if (warp == 0) {
         // ================================ TMA producer ================================
         {   // (all 32 lanes walk the loop; the single-thread instructions are predicated on elect_one(), see tc_ptx.cuh)
-            const uint32_t a_box_bytes = (uint32_t)p.bw * p.bh * TC_BK * 2;
+            const uint32_t a_box_bytes = (uint32_t)p.bw * p.bh * p.bimg * TC_BK * 2;
             const uint32_t tx = Cfg::PLANES * (a_box_bytes + Cfg::B_BYTES);
             int stage = 0;
             uint32_t phase = 0;
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         int mt2 = nt / p.n_tiles_n;
                         const int tw2 = mt2 % p.tiles_w; mt2 /= p.tiles_w;
                         const int th2 = mt2 % p.tiles_h;
-                        const int img2 = mt2 / p.tiles_h;
+                        const int img2 = (mt2 / p.tiles_h) * p.bimg;
                         if (elect_one())
                             for (int cc2 = 0; cc2 < p.cin_chunks; ++cc2) {
                                 tma_prefetch_l2_4d(&p.a[0][0], cc2 * TC_BK, tw2 * p.bw - p.pw, th2 * p.bh - p.ph, img2);
@@ -565,9 +565,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             int mt_ = t / p.n_tiles_n;
             const int tw_ = mt_ % p.tiles_w; mt_ /= p.tiles_w;
             const int th_ = mt_ % p.tiles_h;
-            const int img_ = mt_ / p.tiles_h;
+            const int img_ = (mt_ / p.tiles_h) * p.bimg;
             const uint32_t dst = s_out_u32 + (eg * p.nbuf + b) * Cfg::BUF_BYTES, rb = bar_res + 8 * (eg * 3 + b);
-            mbar_expect_tx(rb, (SPLIT ? 2u : 1u) * p.bw * p.bh * 64u);
+            mbar_expect_tx(rb, (SPLIT ? 2u : 1u) * p.bw * p.bh * p.bimg * 64u);
             tma_load_4d(dst, &p.r[0], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
             if (SPLIT) tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
         };
@@ -580,11 +580,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             int mt = tile / p.n_tiles_n;
             const int tw = mt % p.tiles_w; mt /= p.tiles_w;
             const int th = mt % p.tiles_h;
-            const int img = mt / p.tiles_h;
-            const int hl = row / p.bw, wl = row - hl * p.bw;
+            const int img = (mt / p.tiles_h) * p.bimg;   // first image of the tile: tile row = (image il, patch row hl, column wl)
+            const int il = row / (p.bw * p.bh), r2 = row - il * p.bw * p.bh;
+            const int hl = r2 / p.bw, wl = r2 - hl * p.bw;
             const int oh = th * p.bh + hl, ow = tw * p.bw + wl;
-            const bool valid = hl < p.bh && oh < p.ho && ow < p.wo;
-            const size_t pix = ((size_t)img * p.ho + oh) * p.wo + ow;
+            const bool valid = il < p.bimg && img + il < p.n_img && oh < p.ho && ow < p.wo;
+            const size_t pix = ((size_t)(img + il) * p.ho + oh) * p.wo + ow;
             const int n0 = nb * BN;
             // stage this tile's scale/shift (previous tile's readers are past the barrier at the end of the loop body)
             for (int i = eall; i < BN; i += 128 * TC_EPI_GROUPS) { s_scale[i] = __ldg(p.scale + n0 + i); s_shift[i] = __ldg(p.shift + n0 + i); }
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             int mt2 = ntile / p.n_tiles_n;
                             const int tw2 = mt2 % p.tiles_w; mt2 /= p.tiles_w;
                             const int th2 = mt2 % p.tiles_h;
-                            const int img2 = mt2 / p.tiles_h;
+                            const int img2 = (mt2 / p.tiles_h) * p.bimg;
                             for (int c2 = cfirst + cstep; c2 < BN; c2 += cstep) {
                                 tma_prefetch_l2_4d(&p.r[0], nb2 * BN + c2, tw2 * p.bw, th2 * p.bh, img2);
                                 if (SPLIT) tma_prefetch_l2_4d(&p.r[1], nb2 * BN + c2, tw2 * p.bw, th2 * p.bh, img2);
@@ -837,17 +838,24 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 }
 
 
-// choose (tiles_w, bw, bh) maximising the fraction of the 128 MMA rows that are real output pixels
-static void choose_tiling(int ho, int wo, int* tiles_w, int* bw, int* bh) {
+// choose (tiles_w, bw, bh, bimg) maximising the fraction of the 128 MMA rows that are real output pixels.  A tile is a (bh x bw) patch of
+// bimg consecutive images (one 4-D TMA box {64 ch, bw, bh, bimg}).  With one image per tile a 31-wide map fills 124 of 128 rows and its
+// last row tile is 3/4 full (93.8 % overall; the 29 x 29 encoder maps: 82 %); ONE row of FOUR images fills the same 124 rows with no ragged
+// last tile (96.9 %; 29 x 29: 90.6 %).  Every output element keeps its own accumulation order, so results do not depend on the choice.
+Tunable g_tc_multi_image_tiles = 1;   // tunable "tc_multi_image_tiles": 0 = one image per tile (A/B switch; same arithmetic)
+static void choose_tiling(int n, int ho, int wo, bool multi, int* tiles_w, int* bw, int* bh, int* bimg) {
     double best = -1;
-    for (int tw = 1; tw <= 8; ++tw) {
-        int w = (wo + tw - 1) / tw;
-        if (w > 128) continue;
-        int h = std::min(128 / w, ho);
-        int th = (ho + h - 1) / h;
-        double eff = (double)ho * wo / ((double)tw * th * 128.0);
-        if (eff > best + 1e-9) { best = eff; *tiles_w = tw; *bw = w; *bh = h; }
-    }
+    for (int tw = 1; tw <= 8; ++tw)   // full-width patches first: a narrower patch (shorter TMA rows) must buy at least 2 % more useful rows
+        for (int bi = 1; bi <= (multi ? 8 : 1) && bi <= n; ++bi) {
+            const int w = (wo + tw - 1) / tw;
+            if (w * bi > 128) continue;
+            const int h = std::min(128 / (w * bi), ho);
+            const int th = (ho + h - 1) / h;
+            const long tiles = (long)tw * th * ((n + bi - 1) / bi);
+            const double eff = (double)n * ho * wo / ((double)tiles * 128.0);
+            const double need = best < 0 ? 0 : (tw > *tiles_w ? 0.02 : 1e-3);   // (near-ties keep the earlier = simpler plan)
+            if (eff > best + need) { best = eff; *tiles_w = tw; *bw = w; *bh = h; *bimg = bi; }
+        }
 }
 
 template <int BN, bool SPLIT, int EPI = 0>
@@ -970,7 +978,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     memcpy(key.geom, kg, sizeof(kg));
     key.K = w.K; key.relu = ep.relu; key.split = split ? 1 : 0; key.group = fuse_group;
     key.knobs[0] = g_tc_bn_max; key.knobs[1] = g_tc_split_bn_max; key.knobs[2] = g_tc_tma_store; key.knobs[3] = g_tc_tma_res;
-    key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch; key.knobs[7] = g_tc_latency_split;
+    key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch | (g_tc_multi_image_tiles << 1); key.knobs[7] = g_tc_latency_split;
     key.knobs[8] = g_tc_pdl;
     USOT_CUDA_OK(cudaGetDevice(&key.device));
     {
@@ -984,8 +992,10 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     const int bn_cap = split ? std::min(g_tc_bn_max.load(), g_tc_split_bn_max.load()) : g_tc_bn_max.load();
     if (g.cout % 256 == 0 && bn_cap >= 256) bn = 256;
     else if (g.cout % 128 == 0 && bn_cap >= 128) bn = 128;
-    choose_tiling(g.ho, g.wo, &p.tiles_w, &p.bw, &p.bh);
+    p.bimg = 1;
+    choose_tiling(g.n, g.ho, g.wo, g_tc_multi_image_tiles && fuse_group == 0, &p.tiles_w, &p.bw, &p.bh, &p.bimg);
     p.tiles_h = (g.ho + p.bh - 1) / p.bh;
+    const int img_tiles = (g.n / (fuse_group > 0 ? fuse_group : 1) + p.bimg - 1) / p.bimg;   // tiles along the image axis
     const int num_sms = device_sm_count();
     // Latency mode (small batches): while the grid would leave at least half of the SMs idle, halve the N tile -- twice as many CTAs,
     // and every MMA of a tile's K loop is half as wide (half as long).  The accumulation order of each output element does not
@@ -993,14 +1003,14 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     // (Not across the 256 -> 128 step of split mode, which would switch to the two-accumulator arithmetic.)
     if (fuse_group > 0) bn = 128;   // 64 conf + 64 value columns per tile
     else if (g_tc_latency_split) {
-        const int m_tiles = g.n * p.tiles_h * p.tiles_w;
+        const int m_tiles = img_tiles * p.tiles_h * p.tiles_w;
         while (bn > 64 && !(split && bn == 256) && m_tiles * (g.cout / bn) * 2 <= num_sms) bn /= 2;
     }
     p.n_img = g.n; p.ho = g.ho; p.wo = g.wo; p.cout = g.cout;
     p.n_tiles_n = g.cout / bn;
     p.group = fuse_group > 0 ? fuse_group : 1;
     p.fuse_cout = fuse_group > 0 ? g.cout / 2 : 0;
-    p.num_tiles = (g.n / p.group) * p.tiles_h * p.tiles_w * p.n_tiles_n;   // fused launch: one tile index = the `group` maps of a sample
+    p.num_tiles = img_tiles * p.tiles_h * p.tiles_w * p.n_tiles_n;   // fused launch: one tile index = the `group` maps of a sample
     p.taps = g.kh * g.kw; p.kw = g.kw; p.cin_chunks = g.cin / TC_BK;
     p.stride = g.stride; p.ph = g.ph; p.pw = g.pw; p.dh = g.dh; p.dw = g.dw;
     p.scale = w.scale; p.shift = ep.shift;
@@ -1018,7 +1028,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         for (int par = 0; par < npar; ++par) {
             const int py = par >> 1, px = par & 1;
             cuuint64_t dims[4], strides[3];
-            cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+            cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bimg};
             const __half* b = base;
             if (g.stride == 1) {
                 dims[0] = g.cin; dims[1] = g.w; dims[2] = g.h; dims[3] = g.n;
@@ -1046,7 +1056,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         // fp32-only output: one fp32 map, box {32 floats = 128 B, bw, bh, 1}, 128B swizzle; uses the split path's staging buffers
         cuuint64_t od[4] = {(cuuint64_t)g.cout, (cuuint64_t)g.wo, (cuuint64_t)g.ho, (cuuint64_t)g.n};
         cuuint64_t os[3] = {(cuuint64_t)g.cout * 4, (cuuint64_t)g.wo * g.cout * 4, (cuuint64_t)g.ho * g.wo * g.cout * 4};
-        cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+        cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bimg};
         if (int rc = encode_tmap(&p.o[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.out_f32, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
         p.o[1] = p.o[0];
         p.tma_store = 1;
@@ -1054,7 +1064,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     } else if (p.tma_store) {
         cuuint64_t od[4] = {(cuuint64_t)g.cout, (cuuint64_t)g.wo, (cuuint64_t)g.ho, (cuuint64_t)g.n};
         cuuint64_t os[3] = {(cuuint64_t)g.cout * 2, (cuuint64_t)g.wo * g.cout * 2, (cuuint64_t)g.ho * g.wo * g.cout * 2};
-        cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+        cuuint32_t ob[4] = {32, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bimg};
         if (int rc = encode_map(&p.o[0], p.out_hi, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
         if (split) { if (int rc = encode_map(&p.o[1], p.out_lo, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_64B)) return rc; }
         else p.o[1] = p.o[0];
@@ -1185,7 +1195,7 @@ int launch_stem_s2d_pool(const float* x, int n, int s, const __half* w_hi, const
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.n_img = n; p.ho = HO; p.wo = HO; p.cout = 64;
-    p.bw = HO; p.bh = 1; p.tiles_w = 1; p.tiles_h = HO;
+    p.bw = HO; p.bh = 1; p.bimg = 1; p.tiles_w = 1; p.tiles_h = HO;
     p.n_tiles_n = 1; p.group = 1;
     p.pool_bands = nb; p.pool_band_rows = (PO + nb - 1) / nb; p.pool_po = PO;
     p.num_tiles = n * nb;
