@@ -258,6 +258,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const int tap = ks / p.cin_chunks, cc = ks - tap * p.cin_chunks;
                     const int kh = tap / p.kw, kwi = tap - kh * p.kw;
                     int offh = kh * p.dh - p.ph, offw = kwi * p.dw - p.pw, par = 0;
+                    // One-row tiles (bh == 1): a filter row that falls into the zero padding contributes exactly zero to every pixel of
+                    // the tile -- neither loaded nor multiplied (the MMA issuer skips the same K-steps; adding 0 is exact, so results
+                    // are unchanged).  2 of 31 rows x 1/3 of the taps for a pad-1 3x3 layer, 4 of 31 for the dilation-2 layers.
+                    if (p.skip_pad_rows && (unsigned)(h0 + offh) >= (unsigned)p.hin) continue;
                     if (p.stride == 2) {
                         const int py = offh & 1, px = offw & 1;
                         par = py * 2 + px;
@@ -313,15 +317,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
-            for (int q = 0, count = decode_seq(p, tile).count; q < count; ++q, ++it) {
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileSeq sq = decode_seq(p, tile);
+            for (int q = 0; q < sq.count; ++q, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * Cfg::ACC_COLS;
                 const uint32_t tmem_x = Cfg::XACC ? tmem_d + BN : tmem_d;
-                for (int ks = 0; ks < nK; ++ks) {
+                const int h0 = (sq.th + q * sq.dth) * p.bh;
+                uint32_t started = 0;   // 0 until the first K-step of this tile has been issued (it overwrites the accumulator)
+                const int per_row = p.kw * p.cin_chunks, n_rows = nK / per_row;   // K-steps per filter row (no divisions in the loop)
+                for (int kh = 0; kh < n_rows; ++kh) {
+                    // (same predicate as the producer: the K-steps of a filter row inside the zero padding were never loaded)
+                    if (p.skip_pad_rows && (unsigned)(h0 + kh * p.dh - p.ph) >= (unsigned)p.hin) continue;
+                for (int kj = 0; kj < per_row; ++kj) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -333,23 +344,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t a_hi = a0 + 2 * k, b_hi = b0 + 2 * k;
+                            const uint32_t acc = (started | k) ? 1u : 0u;
                             if (SPLIT && fuse) {
-                                umma_f16(tmem_d, a_hi, b_hi, idesc2, (ks | k) ? 1u : 0u);
+                                umma_f16(tmem_d, a_hi, b_hi, idesc2, acc);
                                 umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
                                 continue;
                             }
-                            umma_f16(tmem_d, a_hi, b_hi, idesc, (ks | k) ? 1u : 0u);
+                            umma_f16(tmem_d, a_hi, b_hi, idesc, acc);
                             if (SPLIT) {
-                                umma_f16(tmem_x, a_hi, b_hi + (Cfg::B_BYTES >> 4), idesc, Cfg::XACC ? ((ks | k) ? 1u : 0u) : 1u);
+                                umma_f16(tmem_x, a_hi, b_hi + (Cfg::B_BYTES >> 4), idesc, Cfg::XACC ? acc : 1u);
                                 umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
                             }
                         }
                         umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
-                        if (ks == nK - 1) umma_commit(bar_tfull + 8 * as);  // accumulator complete
                     }
                     __syncwarp();
+                    started = 1;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                }
+                if (elect_one()) umma_commit(bar_tfull + 8 * as);  // accumulator complete (tracks every MMA issued above)
+                __syncwarp();
+            }
             }
         }
     } else if (warp >= 4) {
@@ -842,8 +858,10 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 // bimg consecutive images (one 4-D TMA box {64 ch, bw, bh, bimg}).  With one image per tile a 31-wide map fills 124 of 128 rows and its
 // last row tile is 3/4 full (93.8 % overall; the 29 x 29 encoder maps: 82 %); ONE row of FOUR images fills the same 124 rows with no ragged
 // last tile (96.9 %; 29 x 29: 90.6 %).  Every output element keeps its own accumulation order, so results do not depend on the choice.
+Tunable g_tc_skip_pad_rows = 1;       // tunable "tc_skip_pad_rows": one-row tiles skip the K-steps of filter rows that lie in the zero padding (A/B switch; same results)
 Tunable g_tc_multi_image_tiles = 1;   // tunable "tc_multi_image_tiles": 0 = one image per tile (A/B switch; same arithmetic)
-static void choose_tiling(int n, int ho, int wo, bool multi, int* tiles_w, int* bw, int* bh, int* bimg) {
+static void choose_tiling(int n, int ho, int wo, bool multi, double skip_frac_one_row, int* tiles_w, int* bw, int* bh, int* bimg) {
+    // skip_frac_one_row: fraction of the (row, filter-row) pairs that fall into the zero padding, which ONE-ROW tiles skip entirely
     double best = -1;
     for (int tw = 1; tw <= 8; ++tw)   // full-width patches first: a narrower patch (shorter TMA rows) must buy at least 2 % more useful rows
         for (int bi = 1; bi <= (multi ? 8 : 1) && bi <= n; ++bi) {
@@ -852,7 +870,7 @@ static void choose_tiling(int n, int ho, int wo, bool multi, int* tiles_w, int* 
             const int h = std::min(128 / (w * bi), ho);
             const int th = (ho + h - 1) / h;
             const long tiles = (long)tw * th * ((n + bi - 1) / bi);
-            const double eff = (double)n * ho * wo / ((double)tiles * 128.0);
+            const double eff = (double)n * ho * wo / ((double)tiles * 128.0) / (h == 1 ? 1.0 - skip_frac_one_row : 1.0);   // useful rows per executed MMA row
             const double need = best < 0 ? 0 : (tw > *tiles_w ? 0.02 : 1e-3);   // (near-ties keep the earlier = simpler plan)
             if (eff > best + need) { best = eff; *tiles_w = tw; *bw = w; *bh = h; *bimg = bi; }
         }
@@ -978,7 +996,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     memcpy(key.geom, kg, sizeof(kg));
     key.K = w.K; key.relu = ep.relu; key.split = split ? 1 : 0; key.group = fuse_group;
     key.knobs[0] = g_tc_bn_max; key.knobs[1] = g_tc_split_bn_max; key.knobs[2] = g_tc_tma_store; key.knobs[3] = g_tc_tma_res;
-    key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch | (g_tc_multi_image_tiles << 1); key.knobs[7] = g_tc_latency_split;
+    key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch | (g_tc_multi_image_tiles << 1) | (g_tc_skip_pad_rows << 2); key.knobs[7] = g_tc_latency_split;
     key.knobs[8] = g_tc_pdl;
     USOT_CUDA_OK(cudaGetDevice(&key.device));
     {
@@ -993,7 +1011,17 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     if (g.cout % 256 == 0 && bn_cap >= 256) bn = 256;
     else if (g.cout % 128 == 0 && bn_cap >= 128) bn = 128;
     p.bimg = 1;
-    choose_tiling(g.n, g.ho, g.wo, g_tc_multi_image_tiles && fuse_group == 0, &p.tiles_w, &p.bw, &p.bh, &p.bimg);
+    double skip_frac = 0;   // stride-1 layers with vertical padding: share of (output row, filter row) pairs whose input row lies outside the map
+    const bool multi = g_tc_multi_image_tiles && fuse_group == 0;
+    if (multi && g_tc_skip_pad_rows && g.stride == 1 && g.ph > 0 && g.kh > 1) {
+        int out = 0;
+        for (int oy = 0; oy < g.ho; ++oy)
+            for (int k = 0; k < g.kh; ++k) out += (oy + k * g.dh - g.ph < 0 || oy + k * g.dh - g.ph >= g.h) ? 1 : 0;
+        skip_frac = (double)out / ((double)g.ho * g.kh);
+    }
+    choose_tiling(g.n, g.ho, g.wo, multi, skip_frac, &p.tiles_w, &p.bw, &p.bh, &p.bimg);
+    p.hin = g.h;
+    p.skip_pad_rows = (skip_frac > 0 && p.bh == 1) ? 1 : 0;
     p.tiles_h = (g.ho + p.bh - 1) / p.bh;
     const int img_tiles = (g.n / (fuse_group > 0 ? fuse_group : 1) + p.bimg - 1) / p.bimg;   // tiles along the image axis
     const int num_sms = device_sm_count();

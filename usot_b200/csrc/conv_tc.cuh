@@ -21,6 +21,7 @@ struct TcParams {
     int tma_store;        // 1: split-fp16 outputs leave through smem staging + cp.async.bulk.tensor stores
     int n_img, ho, wo, cout;
     int bw, bh, tiles_w, tiles_h;  // spatial patch of one M tile
+    int hin, skip_pad_rows;        // input height; 1: one-row tiles skip the K-steps whose filter row lies in the zero padding
     int bimg;                      // images per M tile (bw*bh*bimg <= 128 rows; one TMA box {64 ch, bw, bh, bimg})
     int n_tiles_n, num_tiles;
     int group;            // maps walked back to back per (patch, N block): 1, or N_q in the fused Conf_Fusion launch (image = sample * group + q)
@@ -64,7 +65,7 @@ struct TcEpilogue {
 // generic cuTensorMapEncodeTiled wrapper (dtype / swizzle are CUtensorMapDataType / CUtensorMapSwizzle values)
 int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                 const cuuint32_t* box, int swizzle);
-extern Tunable g_tc_multi_image_tiles, g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
+extern Tunable g_tc_skip_pad_rows, g_tc_multi_image_tiles, g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
 // fuse_group > 0: fused Conf_Fusion launch (connect.py:123-144).  `w` holds conf_gen / value_gen interleaved in blocks of 64 output channels
 // (rows [128 b, 128 b + 64) = conf channels [64 b, 64 b + 64), rows [128 b + 64, 128 b + 128) = the same value channels; scale / shift alike),
 // g.n = samples * fuse_group maps, and ep.out_* receive the (samples, ho, wo, cout / 2) fused map.
