@@ -14,7 +14,7 @@ def _set(name, v):
     _lib.check(_lib.load().usot_set_tunable(name.encode(), v))
 
 
-DEFAULTS = {"tc_pdl": 1, "groupdw_row_split": 1, "tc_latency_split": 1, "tc_l2_prefetch": 0, "tc_tma_f32": 1, "tc_fuse_cross": 1, "tc_tma_store": 1, "tc_tma_res": 1, "stem_tc": 1, "groupdw_tma": 2, "pred_tma_min_batch": 48, "tc_bn_max": 256, "tc_split_bn_max": 128, "groupdw_warps4": 1, "conf_fusion_fused": 1, "tc_multi_image_tiles": 1, "tc_skip_pad_rows": 1, "stem_pool_fused": 1, "graph_max_batch": 8}
+DEFAULTS = {"tc_pdl": 1, "groupdw_row_split": 1, "tc_latency_split": 1, "tc_l2_prefetch": 0, "tc_tma_f32": 1, "tc_fuse_cross": 1, "tc_tma_store": 1, "tc_tma_res": 1, "stem_tc": 1, "groupdw_tma": 2, "pred_tma_min_batch": 48, "tc_bn_max": 256, "tc_split_bn_max": 128, "groupdw_warps4": 1, "conf_fusion_fused": 1, "tc_multi_image_tiles": 1, "tc_skip_pad_rows": 1, "tc_res_ahead": 1, "stem_pool_fused": 1, "graph_max_batch": 8}
 
 
 @pytest.fixture()
@@ -27,7 +27,7 @@ def net():
         _set(k, v)
 
 
-@pytest.mark.parametrize("knob,value,exact", [("tc_fuse_cross", 0, False), ("tc_tma_f32", 0, True), ("tc_l2_prefetch", 1, True), ("tc_latency_split", 0, True), ("groupdw_row_split", 0, True), ("tc_pdl", 0, True), ("tc_tma_store", 0, True), ("tc_tma_res", 0, True), ("groupdw_tma", 0, True), ("groupdw_tma", 1, True), ("groupdw_warps4", 0, True), ("stem_pool_fused", 0, False), ("tc_multi_image_tiles", 0, True), ("tc_skip_pad_rows", 0, True), ("conf_fusion_fused", 0, True),
+@pytest.mark.parametrize("knob,value,exact", [("tc_fuse_cross", 0, False), ("tc_tma_f32", 0, True), ("tc_l2_prefetch", 1, True), ("tc_latency_split", 0, True), ("groupdw_row_split", 0, True), ("tc_pdl", 0, True), ("tc_tma_store", 0, True), ("tc_tma_res", 0, True), ("groupdw_tma", 0, True), ("groupdw_tma", 1, True), ("groupdw_warps4", 0, True), ("stem_pool_fused", 0, False), ("tc_multi_image_tiles", 0, True), ("tc_skip_pad_rows", 0, True), ("tc_res_ahead", 2, True), ("conf_fusion_fused", 0, True),
                                               ("stem_tc", 0, False), ("pred_tma_min_batch", 1, True), ("tc_bn_max", 64, False)])
 def test_knob_keeps_results(net, knob, value, exact):
     z, x, tb, sb = O.synth_inputs(91, batch=3)

@@ -40,6 +40,7 @@ namespace usot {
 // Kernel
 // =============================================================================================
 constexpr int TC_BM = 128, TC_BK = 64;
+constexpr int TC_RES_BUFS = 6;                           // residual-landed barriers per epilogue group (upper bound of TcParams::nbuf)
 constexpr int TC_EPI_GROUPS = 2;                          // epilogue warp groups (4 warps each, one per TMEM lane quarter)
 constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;     // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4..: epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB per plane per stage
@@ -63,6 +64,7 @@ struct TcCfg {
     static constexpr int TMEM_COLS = 2 * ACC_COLS;  // double buffered; power of two for BN in {64,128,256}
     static constexpr int BUF_BYTES = 2 * TC_BM * 64;  // one staging buffer: 2 planes x 128 rows x 64 B
     static constexpr int MISC_BYTES = 2 * BN * 4 + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int stages_with_bufs(int nbuf) { return (227 * 1024 - MISC_BYTES - TC_EPI_GROUPS * nbuf * BUF_BYTES) / STAGE_BYTES; }
     static constexpr int smem_bytes(int stages, int nbuf) { return stages * STAGE_BYTES + TC_EPI_GROUPS * nbuf * BUF_BYTES * (TMA_OUT ? 1 : 0) + MISC_BYTES; }
     // ring depth when every epilogue group rotates 3 staging buffers (TMA-prefetched residual)
     static constexpr int STAGES_RES = (227 * 1024 - MISC_BYTES - TC_EPI_GROUPS * 3 * BUF_BYTES) / STAGE_BYTES;
@@ -120,8 +122,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + BN);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * MAXST, bar_tfull = bar_empty + 8 * MAXST,
                    bar_tempty = bar_tfull + 16;
-    const uint32_t bar_res = bar_tempty + 16;  // [TC_EPI_GROUPS][3] residual chunk landed in staging buffer b of group g
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 4 + 3 * TC_EPI_GROUPS);
+    const uint32_t bar_res = bar_tempty + 16;  // [TC_EPI_GROUPS][TC_RES_BUFS] residual chunk landed in staging buffer b of group g
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 4 + TC_RES_BUFS * TC_EPI_GROUPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nK = p.taps * p.cin_chunks;
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < (EPI == 2 ? ROLL_R : STAGES); ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * TC_EPI_GROUPS); }
-        for (int s = 0; s < 3 * TC_EPI_GROUPS; ++s) mbar_init(bar_res + 8 * s, 1);
+        for (int s = 0; s < TC_RES_BUFS * TC_EPI_GROUPS; ++s) mbar_init(bar_res + 8 * s, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -574,22 +576,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // (single-fp16 mode has no lo planes: nothing is loaded, staged or stored for them)
         if (eall == 0 && p.tma_store) { tma_prefetch_desc(&p.o[0]); if (SPLIT) tma_prefetch_desc(&p.o[1]); }
         if (eall == 32 && p.tma_res) { tma_prefetch_desc(&p.r[0]); if (SPLIT) tma_prefetch_desc(&p.r[1]); }
-        // TMA-prefetched residual: the group's leader requests chunk j+1 into staging buffer (j+1) % 3 while chunk j is being
-        // processed; that buffer was last used by chunk j-2, whose bulk store has finished reading when wait_group.read 1 returns.
-        auto issue_res = [&](int t, int c0, uint32_t b) {
+        // TMA-prefetched residual: with NB = p.nbuf staging buffers per group and a look-ahead of D = p.res_ahead chunks, the group's
+        // leader requests chunk j+D into buffer (j+D) % NB when chunk j starts; that buffer was last used by chunk j+D-NB, whose bulk
+        // store has finished reading shared memory once at most NB-D-1 stores are still pending (wait_group.read NB-D-1).
+        // (NB = 3, D = 1 is the default.  D = NB-1 -- wait for the store issued one chunk ago instead, double the distance -- was measured
+        //  to change nothing on the 1x1 + residual layers: they are not bound by the residual's latency.  Kept as tunable tc_res_ahead = 2.)
+        const int NB = p.nbuf, RD = p.res_ahead, cpt = BN / (32 * TC_EPI_GROUPS);   // chunks per tile per group
+        auto issue_res_k = [&](uint32_t k) {   // k-th chunk of this group's sequence over the CTA's tiles
+            const int t = blockIdx.x + (int)(k / cpt) * gridDim.x;
+            if (t >= p.num_tiles) return;
+            const int c0 = eg * 32 + (int)(k % cpt) * 32 * TC_EPI_GROUPS;
+            const uint32_t b = k % NB;
             const int nb_ = t % p.n_tiles_n;
             int mt_ = t / p.n_tiles_n;
             const int tw_ = mt_ % p.tiles_w; mt_ /= p.tiles_w;
             const int th_ = mt_ % p.tiles_h;
             const int img_ = (mt_ / p.tiles_h) * p.bimg;
-            const uint32_t dst = s_out_u32 + (eg * p.nbuf + b) * Cfg::BUF_BYTES, rb = bar_res + 8 * (eg * 3 + b);
+            const uint32_t dst = s_out_u32 + (eg * p.nbuf + b) * Cfg::BUF_BYTES, rb = bar_res + 8 * (eg * TC_RES_BUFS + b);
             mbar_expect_tx(rb, (SPLIT ? 2u : 1u) * p.bw * p.bh * p.bimg * 64u);
             tma_load_4d(dst, &p.r[0], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
             if (SPLIT) tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
         };
         // (single-thread TMA work of a group: one ELECTED lane of its first warp -- elect.sync picks the same lane every time, so the bulk
         //  async-groups it commits are the ones it later waits for; see elect_one() in tc_ptx.cuh for why not `if (et == 0)`)
-        if (p.tma_res && et < 32 && (int)blockIdx.x < p.num_tiles && eg * 32 < BN) { if (elect_one()) issue_res(blockIdx.x, eg * 32, 0); __syncwarp(); }
+        if (p.tma_res && et < 32 && eg * 32 < BN) { if (elect_one()) for (int k = 0; k < RD; ++k) issue_res_k(k); __syncwarp(); }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int nb = tile % p.n_tiles_n;
@@ -630,10 +640,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     int nc0 = c0 + cstep, ntile = tile;
                     const bool wrap = nc0 >= BN;
                     if (wrap) { nc0 = cfirst; ntile = tile + gridDim.x; }
-                    if (ntile < p.num_tiles && elect_one()) {
-                        bulk_wait_read<1>();
-                        issue_res(ntile, nc0, (gc + 1) % 3);
-                        if (wrap && p.l2_prefetch) {
+                    if (elect_one()) {
+                        const int pending = NB - RD - 1;   // stores that may still be reading their staging buffer
+                        if (pending <= 0) bulk_wait_read<0>(); else if (pending == 1) bulk_wait_read<1>(); else bulk_wait_read<2>();
+                        issue_res_k(gc + RD);
+                        if (wrap && p.l2_prefetch && ntile < p.num_tiles) {
                             // the first chunk of the next tile is on its way; its REMAINING chunks start their trip from HBM to L2
                             // now (behind that demand load), so the per-chunk loads one chunk ahead no longer pay DRAM latency each
                             const int nb2 = ntile % p.n_tiles_n;
@@ -697,7 +708,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         // map and let ONE thread issue the two bulk tensor stores: no per-thread global stores, rows beyond the
                         // image / patch are clipped by the TMA unit.  Two staging buffers alternate; a buffer is reused only after
                         // the stores issued from it have finished reading shared memory.
-                        const uint32_t buf = eg * p.nbuf + (p.tma_res ? gc % 3 : 0);
+                        const uint32_t buf = eg * p.nbuf + (p.tma_res ? gc % NB : 0);
                         uint8_t* rp = s_out + buf * Cfg::BUF_BYTES + row * 64;
                         const int sw = (row >> 1) & 3;
                         if (p.tma_f32) {
@@ -723,7 +734,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             continue;
                         }
                         if (p.tma_res) {
-                            mbar_wait(bar_res + 8 * (eg * 3 + gc % 3), (gc / 3) & 1);
+                            mbar_wait(bar_res + 8 * (eg * TC_RES_BUFS + gc % NB), (gc / NB) & 1);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint4 a = *reinterpret_cast<const uint4*>(rp + ((q ^ sw) << 4));
@@ -858,6 +869,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
 // bimg consecutive images (one 4-D TMA box {64 ch, bw, bh, bimg}).  With one image per tile a 31-wide map fills 124 of 128 rows and its
 // last row tile is 3/4 full (93.8 % overall; the 29 x 29 encoder maps: 82 %); ONE row of FOUR images fills the same 124 rows with no ragged
 // last tile (96.9 %; 29 x 29: 90.6 %).  Every output element keeps its own accumulation order, so results do not depend on the choice.
+Tunable g_tc_res_ahead = 1;          // tunable "tc_res_ahead": 1 = residual chunks requested one chunk ahead (3 staging buffers); 2 = NB-1 chunks ahead (measured: no gain; same results)
 Tunable g_tc_skip_pad_rows = 1;       // tunable "tc_skip_pad_rows": one-row tiles skip the K-steps of filter rows that lie in the zero padding (A/B switch; same results)
 Tunable g_tc_multi_image_tiles = 1;   // tunable "tc_multi_image_tiles": 0 = one image per tile (A/B switch; same arithmetic)
 static void choose_tiling(int n, int ho, int wo, bool multi, double skip_frac_one_row, int* tiles_w, int* bw, int* bh, int* bimg) {
@@ -884,9 +896,18 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT, EPI>, 227 * 1024)) return rc;
     if (!Cfg::TMA_OUT || EPI != 0) { p.tma_store = 0; p.tma_res = 0; }
     if (p.tma_res && Cfg::STAGES_RES < 2) p.tma_res = 0;
-    p.nbuf = EPI == 1 ? 0 : (p.tma_res ? 3 : 1);   // (the fused Conf_Fusion epilogue stores from registers: no staging buffers; the
+    // residual pipeline: 3 buffers / look-ahead 1 (tc_res_ahead = 1, the first version) or look-ahead NB-1 with as many buffers (<= 4) as
+    // still leave a two-stage operand ring (split mode: 3 buffers; single-fp16, whose stages are smaller: 4)
+    int res_bufs = 3;
+    if (p.tma_res && g_tc_res_ahead >= 2) {
+        if (Cfg::stages_with_bufs(4) >= 2) res_bufs = 4;
+        p.res_ahead = res_bufs - 1;
+    } else {
+        p.res_ahead = 1;
+    }
+    p.nbuf = EPI == 1 ? 0 : (p.tma_res ? res_bufs : 1);   // (the fused Conf_Fusion epilogue stores from registers: no staging buffers; the
                                                    //  stem + max-pool epilogue uses the two 16 KiB buffers of nbuf = 1 as its row buffer)
-    p.stages = p.tma_res ? (Cfg::STAGES_RES < Cfg::STAGES ? Cfg::STAGES_RES : Cfg::STAGES) : Cfg::STAGES;
+    p.stages = p.tma_res ? std::min(Cfg::stages_with_bufs(p.nbuf), Cfg::STAGES) : Cfg::STAGES;
     int smem = Cfg::smem_bytes(p.stages, p.nbuf);
     if (EPI == 2) {   // rolling activation rows + resident filter + edge buffer (must match the kernel's carve-up)
         constexpr int ROLL_R = SPLIT ? 5 : 6;
@@ -996,7 +1017,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     memcpy(key.geom, kg, sizeof(kg));
     key.K = w.K; key.relu = ep.relu; key.split = split ? 1 : 0; key.group = fuse_group;
     key.knobs[0] = g_tc_bn_max; key.knobs[1] = g_tc_split_bn_max; key.knobs[2] = g_tc_tma_store; key.knobs[3] = g_tc_tma_res;
-    key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch | (g_tc_multi_image_tiles << 1) | (g_tc_skip_pad_rows << 2); key.knobs[7] = g_tc_latency_split;
+    key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch | (g_tc_multi_image_tiles << 1) | (g_tc_skip_pad_rows << 2) | (g_tc_res_ahead << 3); key.knobs[7] = g_tc_latency_split;
     key.knobs[8] = g_tc_pdl;
     USOT_CUDA_OK(cudaGetDevice(&key.device));
     {

@@ -13,7 +13,8 @@ struct TcParams {
     CUtensorMap r[2];     // residual maps [plane], same box/swizzle as o[]: the residual chunk is TMA-loaded INTO the staging buffer
     int tma_res;          // 1: residual arrives by TMA (requires tma_store)
     int stages;           // operand ring depth used by this launch (<= the config's maximum)
-    int nbuf;             // staging buffers per epilogue group: 1, or 3 when the residual is prefetched by TMA
+    int nbuf;             // staging buffers per epilogue group: 1, or 3-4 when the residual is prefetched by TMA
+    int res_ahead;        // residual chunks requested ahead of the one being processed (1 .. nbuf-1)
     int pdl;              // 1: launched with programmatic stream serialization; the kernel runs griddepcontrol.launch_dependents / .wait
     int l2_prefetch;      // 1: cp.async.bulk.prefetch.tensor hints for the next tile (residual chunks; A boxes of 1x1 layers)
     int tma_f32;          // 1: fp32-only output through the staging buffers + TMA store (o[0] is then an fp32 map); implies tma_store
@@ -65,7 +66,7 @@ struct TcEpilogue {
 // generic cuTensorMapEncodeTiled wrapper (dtype / swizzle are CUtensorMapDataType / CUtensorMapSwizzle values)
 int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                 const cuuint32_t* box, int swizzle);
-extern Tunable g_tc_skip_pad_rows, g_tc_multi_image_tiles, g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
+extern Tunable g_tc_res_ahead, g_tc_skip_pad_rows, g_tc_multi_image_tiles, g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
 // fuse_group > 0: fused Conf_Fusion launch (connect.py:123-144).  `w` holds conf_gen / value_gen interleaved in blocks of 64 output channels
 // (rows [128 b, 128 b + 64) = conf channels [64 b, 64 b + 64), rows [128 b + 64, 128 b + 128) = the same value channels; scale / shift alike),
 // g.n = samples * fuse_group maps, and ep.out_* receive the (samples, ho, wo, cout / 2) fused map.

@@ -852,6 +852,7 @@ int usot_set_tunable(const char* name, int value) {
     if (!strcmp(name, "stem_pool_fused")) { USOT_REQUIRE(value == 0 || value == 1, "stem_pool_fused must be 0 or 1"); g_stem_pool_fused = value; return 0; }
     if (!strcmp(name, "stem_tc")) { USOT_REQUIRE(value == 0 || value == 1, "stem_tc must be 0 or 1"); g_stem_tc = value; return 0; }
     if (!strcmp(name, "tc_tma_res")) { USOT_REQUIRE(value == 0 || value == 1, "tc_tma_res must be 0 or 1"); g_tc_tma_res = value; return 0; }
+    if (!strcmp(name, "tc_res_ahead")) { USOT_REQUIRE(value == 1 || value == 2, "tc_res_ahead must be 1 or 2"); g_tc_res_ahead = value; return 0; }
     if (!strcmp(name, "tc_skip_pad_rows")) { USOT_REQUIRE(value == 0 || value == 1, "tc_skip_pad_rows must be 0 or 1"); g_tc_skip_pad_rows = value; return 0; }
     if (!strcmp(name, "tc_multi_image_tiles")) { USOT_REQUIRE(value == 0 || value == 1, "tc_multi_image_tiles must be 0 or 1"); g_tc_multi_image_tiles = value; return 0; }
     if (!strcmp(name, "tc_pdl")) { USOT_REQUIRE(value == 0 || value == 1, "tc_pdl must be 0 or 1"); g_tc_pdl = value; return 0; }
