@@ -581,12 +581,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // store has finished reading shared memory once at most NB-D-1 stores are still pending (wait_group.read NB-D-1).
         // (NB = 3, D = 1 is the default.  D = NB-1 -- wait for the store issued one chunk ago instead, double the distance -- was measured
         //  to change nothing on the 1x1 + residual layers: they are not bound by the residual's latency.  Kept as tunable tc_res_ahead = 2.)
-        const int NB = p.nbuf, RD = p.res_ahead, cpt = BN / (32 * TC_EPI_GROUPS);   // chunks per tile per group
-        auto issue_res_k = [&](uint32_t k) {   // k-th chunk of this group's sequence over the CTA's tiles
-            const int t = blockIdx.x + (int)(k / cpt) * gridDim.x;
-            if (t >= p.num_tiles) return;
-            const int c0 = eg * 32 + (int)(k % cpt) * 32 * TC_EPI_GROUPS;
-            const uint32_t b = k % NB;
+        const int NB = p.nbuf, RD = p.res_ahead;
+        // (the chunk to request next and the chunk to consume next are tracked incrementally: no division by a run-time value sits on the
+        //  issuing lane's path -- a first version that computed tile / column / buffer from the chunk index cost the residual layers 8-14 %)
+        int rq_tile = blockIdx.x, rq_c0 = eg * 32;
+        uint32_t rq_buf = 0, use_buf = 0, use_phase = 0;
+        auto issue_res = [&](int t, int c0, uint32_t b) {   // (called by the elected lane)
             const int nb_ = t % p.n_tiles_n;
             int mt_ = t / p.n_tiles_n;
             const int tw_ = mt_ % p.tiles_w; mt_ /= p.tiles_w;
@@ -599,7 +599,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         };
         // (single-thread TMA work of a group: one ELECTED lane of its first warp -- elect.sync picks the same lane every time, so the bulk
         //  async-groups it commits are the ones it later waits for; see elect_one() in tc_ptx.cuh for why not `if (et == 0)`)
-        if (p.tma_res && et < 32 && eg * 32 < BN) { if (elect_one()) for (int k = 0; k < RD; ++k) issue_res_k(k); __syncwarp(); }
+        // every lane of the group's first warp keeps the same request state; only the elected lane issues
+        auto rq_advance = [&]() {
+            rq_c0 += 32 * TC_EPI_GROUPS;
+            if (rq_c0 >= BN) { rq_c0 = eg * 32; rq_tile += gridDim.x; }
+            if (++rq_buf == (uint32_t)NB) rq_buf = 0;
+        };
+        if (p.tma_res && et < 32 && eg * 32 < BN) {
+            for (int k = 0; k < RD; ++k) {
+                if (rq_tile < p.num_tiles && elect_one()) issue_res(rq_tile, rq_c0, rq_buf);
+                __syncwarp();
+                rq_advance();
+            }
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int nb = tile % p.n_tiles_n;
@@ -643,7 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (elect_one()) {
                         const int pending = NB - RD - 1;   // stores that may still be reading their staging buffer
                         if (pending <= 0) bulk_wait_read<0>(); else if (pending == 1) bulk_wait_read<1>(); else bulk_wait_read<2>();
-                        issue_res_k(gc + RD);
+                        if (rq_tile < p.num_tiles) issue_res(rq_tile, rq_c0, rq_buf);
                         if (wrap && p.l2_prefetch && ntile < p.num_tiles) {
                             // the first chunk of the next tile is on its way; its REMAINING chunks start their trip from HBM to L2
                             // now (behind that demand load), so the per-chunk loads one chunk ahead no longer pay DRAM latency each
@@ -659,6 +671,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         }
                     }
                     __syncwarp();
+                    rq_advance();
                 }
                 uint32_t v[32];
                 tmem_ld32(taddr + c0, v);
@@ -708,7 +721,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         // map and let ONE thread issue the two bulk tensor stores: no per-thread global stores, rows beyond the
                         // image / patch are clipped by the TMA unit.  Two staging buffers alternate; a buffer is reused only after
                         // the stores issued from it have finished reading shared memory.
-                        const uint32_t buf = eg * p.nbuf + (p.tma_res ? gc % NB : 0);
+                        const uint32_t buf = eg * p.nbuf + (p.tma_res ? use_buf : 0);
                         uint8_t* rp = s_out + buf * Cfg::BUF_BYTES + row * 64;
                         const int sw = (row >> 1) & 3;
                         if (p.tma_f32) {
@@ -734,7 +747,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             continue;
                         }
                         if (p.tma_res) {
-                            mbar_wait(bar_res + 8 * (eg * TC_RES_BUFS + gc % NB), (gc / NB) & 1);
+                            mbar_wait(bar_res + 8 * (eg * TC_RES_BUFS + use_buf), use_phase);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint4 a = *reinterpret_cast<const uint4*>(rp + ((q ^ sw) << 4));
@@ -784,6 +797,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             __syncwarp();
                         }
                         ++gc;
+                        if (p.tma_res && ++use_buf == (uint32_t)NB) { use_buf = 0; use_phase ^= 1; }
                     } else if (p.out_hi) {
                         uint4* oh4 = reinterpret_cast<uint4*>(p.out_hi + off);
                         uint4* ol4 = reinterpret_cast<uint4*>(p.out_lo + off);
