@@ -64,6 +64,11 @@ USOT_API int usot_abi_version(void);
  * "tc_pdl" = 0 | 1 (programmatic dependent launch of the conv kernels when every tile has its own SM, default 1), "tc_latency_split" = 0 | 1 (small grids use narrower N tiles so more SMs work on a layer, default 1), "tc_l2_prefetch" = 0 | 1 (TMA L2-prefetch hints for the next tile's residual / 1x1 activations, default 0), "tc_tma_f32" = 0 | 1 (fp32-only conv outputs through smem staging + TMA store, default 1), "tc_fuse_cross" = 0 | 1 (split mode: a_hi x [w_hi|w_lo] as one N = 2*BN MMA, default 1), "tc_tma_store" = 0 | 1 (TMA-store epilogue), "tc_tma_res" = 0 | 1 (residual loaded by TMA), "stem_tc" = 0 | 1 (tensor-core stem),
  * "groupdw_tma" = 0 | 1 | 2 (register-staged / TMA ring + scalar FMA / TMA ring + packed FFMA2, default 2),
  * "groupdw_warps4" = 0 | 1 (FFMA2 GroupDW kernel with four consumer warps = one per SM sub-partition, default 1),
+ * "stem_pool_fused" = 0 | 1 (stem + max-pool as one TMA-fed tensor-core kernel over the space-to-depth image, default 1; results differ from
+ * the two-kernel path by summation order only), "conf_fusion_fused" = 0 | 1 (fp16x3: conf_gen || value_gen as one conv with the Conf_Fusion
+ * reduction in its epilogue, default 1), "tc_multi_image_tiles" = 0 | 1 (conv M tiles may span several images, default 1),
+ * "tc_skip_pad_rows" = 0 | 1 (one-row tiles skip filter rows inside the zero padding, default 1), "tc_res_ahead" = 1 | 2 (residual chunks
+ * requested 1 / NB-1 chunks ahead, default 1),
  * "groupdw_row_split" = 0 | 1 (small batches split one map's output rows over several CTAs, default 1), "pred_tma_min_batch" = 0.. (batches >= this use the TMA-streamed per-image pred-conv kernel, default 48; 0 = never), "graph_max_batch" = 0..64 (track() with n <= this replays a CUDA graph).
  * One accuracy knob: "tc_split_bn_max" = 64 | 128 (default; separate cross-term accumulator) | 256 (single accumulator). */
 USOT_API int usot_set_tunable(const char* name, int value);
