@@ -61,6 +61,7 @@ enum {
 USOT_API const char* usot_last_error(void);
 USOT_API int usot_abi_version(void);
 /* Process-wide performance knobs (never change results): "groupdw_strips" = 2 | 3; "tc_bn_max" = 64 | 128 | 256;
+ * "tc_cta_pair" = 0..7 (bit 0: single-fp16, bit 1: fp16x3 conv launches of the MMA-bound layers with large grids run as clusters of two CTAs executing tcgen05.mma.cta_group::2 with M = 256, bit 2: every eligible layer; same results bit for bit),
  * "tc_pdl" = 0 | 1 (programmatic dependent launch of the conv kernels when every tile has its own SM, default 1), "tc_latency_split" = 0 | 1 (small grids use narrower N tiles so more SMs work on a layer, default 1), "tc_l2_prefetch" = 0 | 1 (TMA L2-prefetch hints for the next tile's residual / 1x1 activations, default 0), "tc_tma_f32" = 0 | 1 (fp32-only conv outputs through smem staging + TMA store, default 1), "tc_fuse_cross" = 0 | 1 (split mode: a_hi x [w_hi|w_lo] as one N = 2*BN MMA, default 1), "tc_tma_store" = 0 | 1 (TMA-store epilogue), "tc_tma_res" = 0 | 1 (residual loaded by TMA), "stem_tc" = 0 | 1 (tensor-core stem),
  * "groupdw_tma" = 0 | 1 | 2 (register-staged / TMA ring + scalar FMA / TMA ring + packed FFMA2, default 2),
  * "groupdw_warps4" = 0 | 1 (FFMA2 GroupDW kernel with four consumer warps = one per SM sub-partition, default 1),

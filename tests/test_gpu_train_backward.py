@@ -86,7 +86,10 @@ def test_cuda_graphed_training_step_matches_eager_steps():
     assert float(eager[4].sum()) < float(eager[0].sum())                  # the loss goes down over the five SGD steps
     pe, pg = dict(net_e.named_parameters()), dict(net_g.named_parameters())
     for k in ("connect_model.cls_pred.weight", "features.features.layer3.5.conv3.weight", "features.features.conv1.weight", "neck.downsample.1.weight"):
-        assert rel_err_t(pg[k], pe[k]) <= 1e-4, k
+        # (the split-K weight-gradient atomics land in a run-dependent order: five SGD steps later the stem filter -- the end of the backward
+        #  chain of this ill-conditioned random network -- differs by 0.7e-4 ... 1.2e-4 from run to run, the other tensors by < 1e-6)
+        print("graphed vs eager parameter", k, f"{rel_err_t(pg[k], pe[k]):.3e}")
+        assert rel_err_t(pg[k], pe[k]) <= (4e-4 if k.endswith("features.conv1.weight") else 1e-4), k
 
 
 def rel_err_t(a, b):

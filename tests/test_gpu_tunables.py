@@ -14,7 +14,7 @@ def _set(name, v):
     _lib.check(_lib.load().usot_set_tunable(name.encode(), v))
 
 
-DEFAULTS = {"tc_pdl": 1, "groupdw_row_split": 1, "tc_latency_split": 1, "tc_l2_prefetch": 0, "tc_tma_f32": 1, "tc_fuse_cross": 1, "tc_tma_store": 1, "tc_tma_res": 1, "stem_tc": 1, "groupdw_tma": 2, "pred_tma_min_batch": 48, "tc_bn_max": 256, "tc_split_bn_max": 128, "groupdw_warps4": 1, "conf_fusion_fused": 1, "tc_multi_image_tiles": 1, "tc_skip_pad_rows": 1, "tc_res_ahead": 1, "stem_pool_fused": 1, "graph_max_batch": 8}
+DEFAULTS = {"tc_pdl": 1, "groupdw_row_split": 1, "tc_latency_split": 1, "tc_l2_prefetch": 0, "tc_tma_f32": 1, "tc_fuse_cross": 1, "tc_tma_store": 1, "tc_tma_res": 1, "stem_tc": 1, "groupdw_tma": 2, "pred_tma_min_batch": 48, "tc_bn_max": 256, "tc_split_bn_max": 128, "groupdw_warps4": 1, "conf_fusion_fused": 1, "tc_multi_image_tiles": 1, "tc_skip_pad_rows": 1, "tc_res_ahead": 1, "stem_pool_fused": 1, "graph_max_batch": 8, "tc_cta_pair": 3}
 
 
 @pytest.fixture()
@@ -154,3 +154,69 @@ def test_multi_image_tiles_keep_results_bit_identical(precision, batch):
     finally:
         for k, v in DEFAULTS.items():
             _set(k, v)
+
+
+PAIR_OPS = {  # name: (cin, cout, k, stride, pad, dil, h, residual, relu, n) -- n chosen so that every SM pair gets a pair tile
+    "l3_down": (512, 1024, 3, 1, 1, 1, 31, False, False, 16),
+    "l3_conv3_res": (256, 1024, 1, 1, 0, 1, 31, True, True, 16),
+    "l3_conv2_dil2": (256, 256, 3, 1, 2, 2, 31, False, True, 24),
+    "tower_odd_groups": (256, 256, 3, 1, 1, 1, 25, False, True, 25),
+    "l2_conv2_s2": (128, 128, 3, 2, 1, 1, 63, False, True, 32),
+    "ragged_last_group": (256, 256, 3, 1, 1, 1, 31, False, True, 30),
+}
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+@pytest.mark.parametrize("case", sorted(PAIR_OPS))
+def test_cta_pair_conv_launches_are_bit_identical(precision, case):
+    """tcgen05.mma.cta_group::2 (clusters of two CTAs, M = 256, each CTA staging half of the weight rows; conv_tc.cu PAIR = true) vs the
+    one-CTA kernel: same K order and accumulators per output element, so the stand-alone conv op must agree bit for bit -- 3x3 / 1x1,
+    stride 2, dilation, residual, an odd number of image groups (phantom partner tile) and a ragged last image group."""
+    from usot_b200 import ops
+    cin, cout, k, s, p, d, h, res, relu, n = PAIR_OPS[case]
+    try:
+        g = torch.Generator(device="cuda").manual_seed(len(case) * 131 + cin)
+        x = torch.randn(n, h, h, cin, device="cuda", generator=g).relu_()
+        w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
+        sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+        sh = torch.randn(cout, device="cuda", generator=g) * 0.1
+        ho = (h + 2 * p - d * (k - 1) - 1) // s + 1
+        r = torch.randn(n, ho, ho, cout, device="cuda", generator=g) if res else None
+        _set("tc_cta_pair", 0)
+        y0 = ops.conv2d_nhwc(x, w, sc, sh, s, p, d, r, relu, precision)
+        _set("tc_cta_pair", 7)
+        y1 = ops.conv2d_nhwc(x, w, sc, sh, s, p, d, r, relu, precision)
+        assert torch.isfinite(y1).all() and torch.equal(y0, y1), float((y0 - y1).abs().max())
+    finally:
+        for kk, v in DEFAULTS.items():
+            _set(kk, v)
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+@pytest.mark.parametrize("batch,nq", [(64, 0), (37, 0), (48, 3)])
+def test_cta_pair_track_is_bit_identical(precision, batch, nq):
+    """The whole track() call (split-plane TMA-store epilogue, TMA-prefetched residual, fp32 outputs) with every eligible conv launch
+    running as CTA pairs vs none: identical outputs, with and without a memory queue, also when image-group counts are odd."""
+    from usot_b200 import USOT
+    net = USOT(precision=precision)
+    net.load_state_dict(load_weights("damp025"))
+    net = net.eval().cuda()
+    try:
+        _set("graph_max_batch", 0)
+        z, x, tb, sb = O.synth_inputs(95, batch=2)
+        xb = torch.cat([x * (1.0 + 0.01 * i) + i for i in range((batch + 1) // 2)])[:batch].cuda()
+        outs = []
+        for knob in (0, 7):
+            _set("tc_cta_pair", knob)
+            net.template(z[:1].cuda(), tb[:1].cuda())
+            if nq:
+                mem = net.extract_memory_feature(ori_x=xb[:1].repeat(batch * nq, 1, 1, 1), search_bbox=sb[:1].repeat(batch * nq, 1).cuda())
+                out = net.track(xb, mem, torch.full((batch, nq), 0.9).cuda())
+            else:
+                out = net.track(xb)
+            outs.append([t.clone() for t in out if torch.is_tensor(t)])
+        for a, b in zip(*outs):
+            assert torch.isfinite(a).all() and torch.equal(a, b), float((a - b).abs().max())
+    finally:
+        for kk, v in DEFAULTS.items():
+            _set(kk, v)

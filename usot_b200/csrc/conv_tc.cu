@@ -45,11 +45,19 @@ constexpr int TC_EPI_GROUPS = 2;                          // epilogue warp group
 constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;     // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4..: epilogue
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB per plane per stage
 
-template <int BN, bool SPLIT>
+// PAIR (cta_group::2): a CTA stages only ITS half of the weight rows of the N block (the pair's MMA reads both halves), see conv_tc_kernel.
+// PAIR = 2 (split mode): the pair variant of the fused cross-term MMA.  The hardware takes rows [0, N/2) of an MMA's B operand from the leader
+// and rows [N/2, N) from the peer, at the SAME shared-memory offset: region X (BN rows) holds w_hi in the leader and w_lo in the peer, so ONE
+// N = 2*BN MMA computes a_hi*w_hi -> main | a_hi*w_lo -> cross; region Y (BN/2 rows) holds w_hi rows [0, BN/2) in the leader and [BN/2, BN)
+// in the peer for the a_lo*w_hi -> cross MMA.  A stage is 32 + 24 KiB.
+template <int BN, bool SPLIT, int PAIR = 0>
 struct TcCfg {
+    static_assert(PAIR != 2 || SPLIT, "the fused-cross pair layout exists in split mode only");
     static constexpr int PLANES = SPLIT ? 2 : 1;
-    static constexpr int B_BYTES = BN * TC_BK * 2;
-    static constexpr int STAGE_BYTES = PLANES * (TC_A_BYTES + B_BYTES);
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;     // weight rows staged by one CTA per K-step and plane
+    static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
+    static constexpr int B_REGION = PAIR == 2 ? 3 * B_BYTES : PLANES * B_BYTES;   // PAIR = 2: X (2 * B_BYTES) + Y (B_BYTES)
+    static constexpr int STAGE_BYTES = PLANES * TC_A_BYTES + B_REGION;
     static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;  // alignment slack + barriers
     static constexpr bool TMA_OUT = !(SPLIT && BN == 256);  // (the 2-stage 96 KiB ring of that config leaves no room for staging)
     static constexpr int OUT_STAGE_BYTES = TMA_OUT ? 2 * 2 * TC_BM * 64 : 0;  // 2 buffers x 2 planes x 128 rows x 64 B
@@ -103,9 +111,29 @@ static __device__ __forceinline__ TileSeq decode_seq(const TcParams& p, int tile
 //          BN/2 channels of value_gen, a CTA walks the p.group (= N_q) memory maps of one sample back to back for a fixed (patch, nb),
 //          and the epilogue warps keep  sum_q e_q * v_q  and  sum_q e_q  (e = exp(clamp(conf)), v = value) in registers: neither the
 //          confidence nor the value maps ever reach HBM.  Same arithmetic, in the same order, as the two convs + conf_fusion_kernel.
-template <int BN, bool SPLIT, int EPI>
+// PAIR = true (EPI = 0 only): the kernel is launched in clusters of two CTAs (the two SMs of a TPC) that execute every MMA together
+// (tcgen05.mma.cta_group::2, M = 256): CTA rank r of the pair owns the M tile of image group 2*gp + r at the same (patch, N block), loads
+// its own activation boxes and rows [r*BN/2, (r+1)*BN/2) of the weight tile; the leader (rank 0) issues the MMAs for both.  A weight byte
+// then crosses L2 -> SM once per PAIR of M tiles and each SM reads only half of the B operand from its shared memory; the operand ring gets
+// deeper (a stage is 16 + 16 KiB instead of 16 + 32 in single-fp16 mode, 32 + 16 instead of 32 + 32 in split mode).  Every output element
+// sees the same K order and the same accumulators as in the one-CTA kernel: results are bit-identical (tests/test_gpu_tunables.py).
+template <int BN, bool SPLIT, int EPI, int PAIR = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    using Cfg = TcCfg<BN, SPLIT>;
+    static_assert(!PAIR || EPI == 0, "the CTA-pair variant exists for the ordinary epilogue only");
+    using Cfg = TcCfg<BN, SPLIT, PAIR>;
+    // pair mode: tile-loop indices count PAIR tiles; tile_of() gives this CTA's ordinary tile index (possibly a phantom tile past the
+    // last image group when the group count is odd: its loads are zero-filled by TMA, its stores clipped)
+    // (macros, not variables: each warp role evaluates them where it needs them, so the one-CTA kernels keep their register allocation)
+#define cta_rank (PAIR ? cluster_ctarank() : 0u)
+#define t_first (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x)
+#define t_step (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x)
+#define t_count (PAIR ? p.num_pair_tiles : p.num_tiles)
+    auto tile_of = [&p](int t) -> int {
+        if constexpr (!PAIR) return t;
+        const int nb_ = t % p.n_tiles_n, r_ = t / p.n_tiles_n;
+        const int sp_ = p.tiles_w * p.tiles_h, s_ = r_ % sp_, gp_ = r_ / sp_;
+        return ((2 * gp_ + (int)cta_rank) * sp_ + s_) * p.n_tiles_n + nb_;
+    };
     const int STAGES = p.stages;
     constexpr int MAXST = 6;  // barrier slots
     extern __shared__ uint8_t smem_raw[];
@@ -135,16 +163,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < (EPI == 2 ? ROLL_R : STAGES); ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * TC_EPI_GROUPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, (PAIR ? 2 : 1) * 4 * TC_EPI_GROUPS); }   // (pair: the epilogue warps of BOTH CTAs release the leader's accumulator)
         for (int s = 0; s < TC_RES_BUFS * TC_EPI_GROUPS; ++s) mbar_init(bar_res + 8 * s, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {   // (the same warp of both CTAs allocates; each CTA gets its own 128 lanes x TMEM_COLS columns at the same base)
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA completion targets them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (p.pdl) {
@@ -247,10 +281,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ================================ TMA producer ================================
         {   // (all 32 lanes walk the loop; the single-thread instructions are predicated on elect_one(), see tc_ptx.cuh)
             const uint32_t a_box_bytes = (uint32_t)p.bw * p.bh * p.bimg * TC_BK * 2;
-            const uint32_t tx = Cfg::PLANES * (a_box_bytes + Cfg::B_BYTES);
+            const uint32_t tx = (PAIR ? 2u : 1u) * (Cfg::PLANES * a_box_bytes + Cfg::B_REGION);   // (pair: the leader's barrier counts both CTAs' bytes)
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tidx = t_first; tidx < t_count; tidx += t_step) {
+                const int tile = tile_of(tidx);
                 const TileSeq sq = decode_seq(p, tile);
                 const int nb = sq.nb, w0 = sq.tw * p.bw;
                 for (int q = 0; q < sq.count; ++q) {   // (count == 1 except in the fused Conf_Fusion / stem + max-pool launches)
@@ -274,7 +309,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::PLANES * TC_A_BYTES;
-                    if (elect_one()) {
+                    if constexpr (PAIR) {
+                        // own activation boxes + own half of the weight rows -> own shared memory; the bytes complete on the LEADER's barrier
+                        const uint32_t lfull = mapa_cluster(full, 0);
+                        const int brow = nb * BN + (int)cta_rank * Cfg::B_ROWS;
+                        if (elect_one()) {
+                            if (cta_rank == 0) mbar_expect_tx(full, tx);
+                            tma_load_4d_pair(sa, &p.a[0][par], lfull, cc * TC_BK, w0 + offw, h0 + offh, img);
+                            if constexpr (PAIR == 2) {
+                                // X: the BN rows of w_hi (leader) / w_lo (peer); Y: this CTA's half of the w_hi rows
+                                tma_load_4d_pair(sa + TC_A_BYTES, &p.a[1][par], lfull, cc * TC_BK, w0 + offw, h0 + offh, img);
+                                tma_load_2d_pair(sb, cta_rank ? &p.bx[1] : &p.bx[0], lfull, ks * TC_BK, nb * BN);
+                                tma_load_2d_pair(sb + 2 * Cfg::B_BYTES, &p.b[0], lfull, ks * TC_BK, brow);
+                            } else {
+                                tma_load_2d_pair(sb, &p.b[0], lfull, ks * TC_BK, brow);
+                                if (SPLIT) {
+                                    tma_load_4d_pair(sa + TC_A_BYTES, &p.a[1][par], lfull, cc * TC_BK, w0 + offw, h0 + offh, img);
+                                    tma_load_2d_pair(sb + Cfg::B_BYTES, &p.b[1], lfull, ks * TC_BK, brow);
+                                }
+                            }
+                        }
+                    } else if (elect_one()) {
                         mbar_expect_tx(full, tx);
                         tma_load_4d(sa, &p.a[0][par], full, cc * TC_BK, w0 + offw, h0 + offh, img);
                         tma_load_2d(sb, &p.b[0], full, ks * TC_BK, nb * BN);
@@ -290,7 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 // DRAM-bound 1x1 layers (K <= 1024, ring only 2-4 stages deep): once every load of THIS tile is queued, pull the NEXT
                 // tile's activation boxes into L2 (hints queue behind the demand loads), so its ring loads are L2 hits; every byte
                 // is still fetched from HBM once.  (3x3 layers re-read A from L2 per tap anyway.)
-                if (p.l2_prefetch && p.group == 1 && p.pool_bands == 0 && p.taps == 1 && p.stride == 1 && nb == p.n_tiles_n - 1) {
+                if (!PAIR && p.l2_prefetch && p.group == 1 && p.pool_bands == 0 && p.taps == 1 && p.stride == 1 && nb == p.n_tiles_n - 1) {
                     const int nt = tile + gridDim.x;  // same M tile is shared by the n_tiles_n consecutive tiles: prefetch once
                     if (nt < p.num_tiles) {
                         int mt2 = nt / p.n_tiles_n;
@@ -306,21 +361,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                 }
             }
+            if constexpr (PAIR) {
+                // tail: the leader's commits arrive on THIS CTA's slot barriers too; wait for the last one of every slot so that no
+                // multicast arrival is still in flight towards a CTA that has already exited
+                for (int s2 = 0; s2 < STAGES; ++s2) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        {   // (all 32 lanes walk the loop and wait on the barriers; one elected lane issues the MMAs and commits of a K-step)
-            const uint32_t idesc = make_idesc(TC_BM, BN);
+        if (!PAIR || cta_rank == 0) {   // (pair: the leader issues for both CTAs; all 32 lanes walk the loop and wait on the barriers; one elected lane issues the MMAs and commits of a K-step)
+            const uint32_t idesc = make_idesc(PAIR ? 2 * TC_BM : TC_BM, BN);
             // Fused cross term: the lo weight tile sits right behind the hi tile in the stage and `cross` right behind `main` in
             // TMEM, so ONE MMA with N = 2*BN computes a_hi*w_hi -> main and a_hi*w_lo -> cross while reading a_hi from shared
             // memory once (the operand reads of three N=128 MMAs per k-step saturate the 128 B/clk shared-memory port).
-            const uint32_t idesc2 = make_idesc(TC_BM, 2 * BN);
-            const bool fuse = Cfg::XACC && p.fuse_cross;
+            const uint32_t idesc2 = make_idesc(PAIR ? 2 * TC_BM : TC_BM, 2 * BN);
+            // (pair: [w_hi | w_lo] of one CTA are not the two halves of an N = 2*BN operand -- the hardware takes rows [0, N/2) from the
+            //  leader and [N/2, N) from the peer -- so the three products are issued as three N = BN MMAs, the tc_fuse_cross = 0 sequence)
+            const bool fuse = !PAIR && Cfg::XACC && p.fuse_cross;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const TileSeq sq = decode_seq(p, tile);
+            for (int tidx = t_first; tidx < t_count; tidx += t_step) {
+            const TileSeq sq = decode_seq(p, tile_of(tidx));   // (pair: the peer's tile has the same patch row, hence the same skipped K-steps)
             for (int q = 0; q < sq.count; ++q, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
@@ -347,6 +412,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t a_hi = a0 + 2 * k, b_hi = b0 + 2 * k;
                             const uint32_t acc = (started | k) ? 1u : 0u;
+                            if constexpr (PAIR == 2) {   // fused cross term of the pair: X = [w_hi (leader) | w_lo (peer)], Y = the w_hi halves
+                                umma_f16_pair(tmem_d, a_hi, b_hi, idesc2, acc);
+                                umma_f16_pair(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi + ((2 * Cfg::B_BYTES) >> 4), idesc, 1u);
+                                continue;
+                            }
+                            if constexpr (PAIR) {
+                                umma_f16_pair(tmem_d, a_hi, b_hi, idesc, acc);
+                                if (SPLIT) {
+                                    umma_f16_pair(tmem_x, a_hi, b_hi + (Cfg::B_BYTES >> 4), idesc, Cfg::XACC ? acc : 1u);
+                                    umma_f16_pair(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
+                                }
+                                continue;
+                            }
                             if (SPLIT && fuse) {
                                 umma_f16(tmem_d, a_hi, b_hi, idesc2, acc);
                                 umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
@@ -358,14 +436,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                 umma_f16(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi, idesc, 1u);
                             }
                         }
-                        umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
+                        if constexpr (PAIR) umma_commit_pair(bar_empty + 8 * stage);   // frees the slot in BOTH CTAs
+                        else umma_commit(bar_empty + 8 * stage);  // frees the smem slot once these MMAs have read it
                     }
                     __syncwarp();
                     started = 1;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 }
-                if (elect_one()) umma_commit(bar_tfull + 8 * as);  // accumulator complete (tracks every MMA issued above)
+                if (elect_one()) { if constexpr (PAIR) umma_commit_pair(bar_tfull + 8 * as); else umma_commit(bar_tfull + 8 * as); }  // accumulator complete (tracks every MMA issued above)
                 __syncwarp();
             }
             }
@@ -584,9 +663,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int NB = p.nbuf, RD = p.res_ahead;
         // (the chunk to request next and the chunk to consume next are tracked incrementally: no division by a run-time value sits on the
         //  issuing lane's path -- a first version that computed tile / column / buffer from the chunk index cost the residual layers 8-14 %)
-        int rq_tile = blockIdx.x, rq_c0 = eg * 32;
+        int rq_tile = t_first, rq_c0 = eg * 32;   // (pair mode: counted in pair tiles like the tile loop)
         uint32_t rq_buf = 0, use_buf = 0, use_phase = 0;
-        auto issue_res = [&](int t, int c0, uint32_t b) {   // (called by the elected lane)
+        auto issue_res = [&](int tq, int c0, uint32_t b) {   // (called by the elected lane)
+            const int t = tile_of(tq);
             const int nb_ = t % p.n_tiles_n;
             int mt_ = t / p.n_tiles_n;
             const int tw_ = mt_ % p.tiles_w; mt_ /= p.tiles_w;
@@ -602,18 +682,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // every lane of the group's first warp keeps the same request state; only the elected lane issues
         auto rq_advance = [&]() {
             rq_c0 += 32 * TC_EPI_GROUPS;
-            if (rq_c0 >= BN) { rq_c0 = eg * 32; rq_tile += gridDim.x; }
+            if (rq_c0 >= BN) { rq_c0 = eg * 32; rq_tile += t_step; }
             if (++rq_buf == (uint32_t)NB) rq_buf = 0;
         };
         if (p.tma_res && et < 32 && eg * 32 < BN) {
             for (int k = 0; k < RD; ++k) {
-                if (rq_tile < p.num_tiles && elect_one()) issue_res(rq_tile, rq_c0, rq_buf);
+                if (rq_tile < t_count && elect_one()) issue_res(rq_tile, rq_c0, rq_buf);
                 __syncwarp();
                 rq_advance();
             }
         }
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t bar_tempty_arrive = PAIR ? mapa_cluster(bar_tempty, 0) : bar_tempty;   // (pair: the LEADER's MMA issuer waits for both epilogues)
+        for (int tidx = t_first; tidx < t_count; tidx += t_step, ++it) {
+            const int tile = tile_of(tidx);
             const int nb = tile % p.n_tiles_n;
             int mt = tile / p.n_tiles_n;
             const int tw = mt % p.tiles_w; mt /= p.tiles_w;
@@ -651,11 +733,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (p.tma_res && et < 32) {
                     int nc0 = c0 + cstep, ntile = tile;
                     const bool wrap = nc0 >= BN;
-                    if (wrap) { nc0 = cfirst; ntile = tile + gridDim.x; }
+                    if (wrap) { nc0 = cfirst; ntile = tile + gridDim.x; }   // (l2_prefetch is never set in pair mode)
                     if (elect_one()) {
                         const int pending = NB - RD - 1;   // stores that may still be reading their staging buffer
                         if (pending <= 0) bulk_wait_read<0>(); else if (pending == 1) bulk_wait_read<1>(); else bulk_wait_read<2>();
-                        if (rq_tile < p.num_tiles) issue_res(rq_tile, rq_c0, rq_buf);
+                        if (rq_tile < t_count) issue_res(rq_tile, rq_c0, rq_buf);
                         if (wrap && p.l2_prefetch && ntile < p.num_tiles) {
                             // the first chunk of the next tile is on its way; its REMAINING chunks start their trip from HBM to L2
                             // now (behind that demand load), so the per-chunk loads one chunk ahead no longer pay DRAM latency each
@@ -827,18 +909,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(bar_tempty_arrive + 8 * as); else mbar_arrive(bar_tempty + 8 * as); }
             asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");  // scale/shift staging may be overwritten next iteration
         }
       }
     }
     if (threadIdx.x >= 128 && ((threadIdx.x - 128) & 127) < 32 && p.tma_store) { if (elect_one()) bulk_wait_read<0>(); __syncwarp(); }  // staging must outlive the stores' reads
-    __syncthreads();
+    if constexpr (PAIR) { tc_fence_before(); cluster_sync_all(); }   // neither CTA exits (or frees TMEM) while the pair's MMAs / remote arrivals may still touch it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
+#undef cta_rank
+#undef t_first
+#undef t_step
+#undef t_count
 
 // =============================================================================================
 // Host side: tensor maps, tiling, launch
@@ -902,18 +990,22 @@ static void choose_tiling(int n, int ho, int wo, bool multi, double skip_frac_on
         }
 }
 
-template <int BN, bool SPLIT, int EPI = 0>
+template <int BN, bool SPLIT, int EPI = 0, int PAIR = 0>
 static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
-    using Cfg = TcCfg<BN, SPLIT>;
+    using Cfg = TcCfg<BN, SPLIT, PAIR>;
     static_assert(Cfg::STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
+    extern Tunable g_tc_cta_pair;
     static SmemAttrCache attr;
-    if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT, EPI>, 227 * 1024)) return rc;
+    if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT, EPI, PAIR>, 227 * 1024)) return rc;
     if (!Cfg::TMA_OUT || EPI != 0) { p.tma_store = 0; p.tma_res = 0; }
     if (p.tma_res && Cfg::STAGES_RES < 2) p.tma_res = 0;
     // residual pipeline: 3 buffers / look-ahead 1 (tc_res_ahead = 1, the first version) or look-ahead NB-1 with as many buffers (<= 4) as
     // still leave a two-stage operand ring (split mode: 3 buffers; single-fp16, whose stages are smaller: 4)
     int res_bufs = 3;
-    if (p.tma_res && g_tc_res_ahead >= 2) {
+    if (PAIR && p.tma_res && (g_tc_cta_pair & 8) && Cfg::stages_with_bufs(3) < 3 && Cfg::stages_with_bufs(2) >= 3) {
+        res_bufs = 2;   // experiment (bit 3 of tc_cta_pair): a pair's residual layers trade one staging buffer per group for a third ring stage
+        p.res_ahead = 1;
+    } else if (p.tma_res && g_tc_res_ahead >= 2) {
         if (Cfg::stages_with_bufs(4) >= 2) res_bufs = 4;
         p.res_ahead = res_bufs - 1;
     } else {
@@ -930,6 +1022,23 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
         smem = ROLL_R * Cfg::PLANES * TC_A_BYTES + 4 * Cfg::PLANES * Cfg::B_BYTES + 768 + Cfg::MISC_BYTES;
     }
     USOT_REQUIRE(smem <= 227 * 1024, "conv_tc: shared memory plan exceeds 227 KiB");
+    if (PAIR) {   // clusters of two CTAs = the two SMs of a TPC
+        USOT_REQUIRE(grid % 2 == 0 && p.num_pair_tiles > 0 && !p.pdl, "conv_tc: malformed CTA-pair launch");
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute cattr;
+        memset(&cattr, 0, sizeof(cattr));
+        cattr.id = cudaLaunchAttributeClusterDimension;
+        cattr.val.clusterDim.x = 2; cattr.val.clusterDim.y = 1; cattr.val.clusterDim.z = 1;
+        cfg.attrs = &cattr;
+        cfg.numAttrs = 1;
+        USOT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, EPI, PAIR>, p));
+        return 0;
+    }
     if (p.pdl) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -943,10 +1052,10 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
         attr.val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = &attr;
         cfg.numAttrs = 1;
-        USOT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, EPI>, p));
+        USOT_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SPLIT, EPI, PAIR>, p));
         return 0;
     }
-    conv_tc_kernel<BN, SPLIT, EPI><<<grid, TC_THREADS, smem, st>>>(p);
+    conv_tc_kernel<BN, SPLIT, EPI, PAIR><<<grid, TC_THREADS, smem, st>>>(p);
     USOT_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -960,6 +1069,10 @@ Tunable g_tc_l2_prefetch = 0;     // TMA L2-prefetch hints for the next tile's r
 Tunable g_tc_tma_f32 = 1;         // fp32-only outputs leave through smem staging + one bulk tensor store per chunk (needs tc_tma_store)
 Tunable g_tc_fuse_cross = 1;       // split mode with two accumulators: a_hi*[w_hi|w_lo] as ONE N = 2*BN MMA (A/B switch; same arithmetic)
 Tunable g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cross-term accumulator (accuracy); 256 trades it for reuse
+// tunable "tc_cta_pair": large grids run as clusters of two CTAs that execute every MMA together (cta_group::2, M = 256; see conv_tc_kernel).
+//   bit 0: single-fp16 launches with the 256- / 128-wide N tile, bit 1: split (fp16x3) launches with the 128-wide N tile, bit 2: also the
+//   layers where the pair does not pay (short-K 1x1, residual; used by the tests).  Same results bit for bit.
+Tunable g_tc_cta_pair = 3;
 
 struct PlanKey {  // plain words only (no padding: the key is hashed and compared as raw bytes)
     const void* ptr[11];
@@ -997,6 +1110,11 @@ static void plan_store(const PlanKey& k, const Plan& pl) {
 static int launch_plan(Plan& pl, bool split, cudaStream_t st) {
     if (pl.p.pool_bands > 0) return split ? launch_cfg<64, true, 2>(pl.p, pl.grid, st) : launch_cfg<64, false, 2>(pl.p, pl.grid, st);
     if (pl.p.group > 1 || pl.p.fuse_cout) return split ? launch_cfg<128, true, 1>(pl.p, pl.grid, st) : launch_cfg<128, false, 1>(pl.p, pl.grid, st);
+    if (pl.p.num_pair_tiles > 0) {
+        if (split) return pl.p.pair_fused ? launch_cfg<128, true, 0, 2>(pl.p, pl.grid, st) : launch_cfg<128, true, 0, 1>(pl.p, pl.grid, st);
+        if (pl.bn == 256) return launch_cfg<256, false, 0, 1>(pl.p, pl.grid, st);
+        return launch_cfg<128, false, 0, 1>(pl.p, pl.grid, st);
+    }
     if (split) {
         if (pl.bn == 256) return launch_cfg<256, true>(pl.p, pl.grid, st);
         if (pl.bn == 128) return launch_cfg<128, true>(pl.p, pl.grid, st);
@@ -1032,7 +1150,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     key.K = w.K; key.relu = ep.relu; key.split = split ? 1 : 0; key.group = fuse_group;
     key.knobs[0] = g_tc_bn_max; key.knobs[1] = g_tc_split_bn_max; key.knobs[2] = g_tc_tma_store; key.knobs[3] = g_tc_tma_res;
     key.knobs[4] = g_tc_fuse_cross; key.knobs[5] = g_tc_tma_f32; key.knobs[6] = g_tc_l2_prefetch | (g_tc_multi_image_tiles << 1) | (g_tc_skip_pad_rows << 2) | (g_tc_res_ahead << 3); key.knobs[7] = g_tc_latency_split;
-    key.knobs[8] = g_tc_pdl;
+    key.knobs[8] = g_tc_pdl | (g_tc_cta_pair << 1);
     USOT_CUDA_OK(cudaGetDevice(&key.device));
     {
         Plan hit;
@@ -1074,6 +1192,21 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     p.group = fuse_group > 0 ? fuse_group : 1;
     p.fuse_cout = fuse_group > 0 ? g.cout / 2 : 0;
     p.num_tiles = img_tiles * p.tiles_h * p.tiles_w * p.n_tiles_n;   // fused launch: one tile index = the `group` maps of a sample
+    // CTA pairs (cta_group::2): large grids only (every pair of SMs gets a pair tile; small grids keep the latency-mode plan), ordinary epilogue,
+    // the N tiles whose pair kernels exist.  The pair = image groups 2*gp and 2*gp + 1 at the same (patch, N block).
+    bool pair = false;
+    if (fuse_group == 0) {
+        const int want = split ? (g_tc_cta_pair & 2) : (g_tc_cta_pair & 1);
+        const bool bn_ok = split ? bn == 128 : (bn == 256 || bn == 128);
+        // Where it pays (ncu launch lists of one batch-256 step, profiles/r02c_pair_*): the MMA-bound layers -- every 3x3 and the K = 1024
+        // 1x1 layers: tensor pipe 84-91 % -> 91-96 % in fp16x3, -3 ... -8 % time -- but NOT the short-K 1x1 (+ residual) layers, whose
+        // two-stage ring cannot hide the extra leader <-> peer barrier hops (+30 %).  Bit 2 of the tunable overrides the rule (tests).
+        const int k_steps = g.kh * g.kw * (g.cin / TC_BK);
+        const bool pays = split ? (k_steps >= 12 && !ep.res_hi) : (k_steps >= 16 && !ep.res_hi && bn == 256 && !(ep.out_hi && ep.out_f32));
+        const int pair_tiles = ((img_tiles + 1) / 2) * p.tiles_h * p.tiles_w * p.n_tiles_n;
+        if (want && bn_ok && (pays || (g_tc_cta_pair & 4)) && img_tiles >= 2 && pair_tiles >= num_sms / 2) { pair = true; p.num_pair_tiles = pair_tiles; }
+        p.pair_fused = (pair && split && g_tc_fuse_cross && (g_tc_cta_pair & 16)) ? 1 : 0;   // bit 4: the pair keeps the fused cross-term MMA (TcCfg PAIR = 2)
+    }
     p.taps = g.kh * g.kw; p.kw = g.kw; p.cin_chunks = g.cin / TC_BK;
     p.stride = g.stride; p.ph = g.ph; p.pw = g.pw; p.dh = g.dh; p.dw = g.dw;
     p.scale = w.scale; p.shift = ep.shift;
@@ -1106,12 +1239,16 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         }
         // ---- weight map: dims {K, Cout} ----
         cuuint64_t wd[2] = {(cuuint64_t)w.K, (cuuint64_t)g.cout}, ws[1] = {(cuuint64_t)w.K * 2};
-        cuuint32_t wb[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+        cuuint32_t wb[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(pair ? bn / 2 : bn)};   // (pair: each CTA loads its half of the rows)
         if (int rc = encode_map(&p.b[pl], pl == 0 ? w.hi : w.lo, 2, wd, ws, wb)) return rc;
+        if (p.pair_fused) {   // region X of the fused pair layout: all bn rows of one plane
+            cuuint32_t wx[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+            if (int rc = encode_map(&p.bx[pl], pl == 0 ? w.hi : w.lo, 2, wd, ws, wx)) return rc;
+        }
     }
 
     p.fuse_cross = g_tc_fuse_cross;
-    p.l2_prefetch = g_tc_l2_prefetch;
+    p.l2_prefetch = pair ? 0 : g_tc_l2_prefetch.load();
     p.pdl = 0;  // decided below, once the tile count is known
     p.tma_store = (g_tc_tma_store && p.out_hi && !(split && bn == 256) && fuse_group == 0) ? 1 : 0;
     p.tma_f32 = 0;
@@ -1142,10 +1279,10 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     Plan plan;
     plan.p = p;
     plan.bn = bn;
-    plan.grid = std::min(p.num_tiles, num_sms);
+    plan.grid = pair ? 2 * std::min(p.num_pair_tiles, num_sms / 2) : std::min(p.num_tiles, num_sms);
     // Programmatic dependent launch pays in the latency regime (every tile has its own SM, idle SMs host the successor's prologue):
     // batch 1: -7 % per track() call.  At batch 256 it measured -1.6 % (within clock noise, no possible gain): not used there.
-    plan.p.pdl = (g_tc_pdl && p.num_tiles * p.group <= num_sms) ? 1 : 0;
+    plan.p.pdl = (!pair && g_tc_pdl && p.num_tiles * p.group <= num_sms) ? 1 : 0;
     plan_store(key, plan);
     return launch_plan(plan, split, st);
 }

@@ -25,6 +25,9 @@ struct TcParams {
     int hin, skip_pad_rows;        // input height; 1: one-row tiles skip the K-steps whose filter row lies in the zero padding
     int bimg;                      // images per M tile (bw*bh*bimg <= 128 rows; one TMA box {64 ch, bw, bh, bimg})
     int n_tiles_n, num_tiles;
+    CUtensorMap bx[2];    // CTA pairs with the fused cross-term MMA: weight maps [plane] with a box of ALL bn rows (region X, see TcCfg)
+    int pair_fused;       // 1: CTA-pair launch that keeps the fused cross-term MMA (split mode; kernel variant PAIR = 2)
+    int num_pair_tiles;   // > 0: CTA-pair launch (cta_group::2, clusters of two CTAs): ceil(image groups / 2) * patches * N blocks
     int group;            // maps walked back to back per (patch, N block): 1, or N_q in the fused Conf_Fusion launch (image = sample * group + q)
     int fuse_cout;        // fused Conf_Fusion: channels of the fused output map (= cout / 2)
     int a_rank5;          // fused stem: the activation maps are 5-D {16 ch, 4 kx, ox, row, image} (fallback when the driver rejects the overlapping 4-D view)
@@ -66,7 +69,7 @@ struct TcEpilogue {
 // generic cuTensorMapEncodeTiled wrapper (dtype / swizzle are CUtensorMapDataType / CUtensorMapSwizzle values)
 int encode_tmap(CUtensorMap* m, int dtype, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                 const cuuint32_t* box, int swizzle);
-extern Tunable g_tc_res_ahead, g_tc_skip_pad_rows, g_tc_multi_image_tiles, g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl;
+extern Tunable g_tc_res_ahead, g_tc_skip_pad_rows, g_tc_multi_image_tiles, g_tc_bn_max, g_tc_split_bn_max, g_tc_tma_store, g_tc_tma_res, g_tc_fuse_cross, g_tc_tma_f32, g_tc_l2_prefetch, g_tc_latency_split, g_tc_pdl, g_tc_cta_pair;
 // fuse_group > 0: fused Conf_Fusion launch (connect.py:123-144).  `w` holds conf_gen / value_gen interleaved in blocks of 64 output channels
 // (rows [128 b, 128 b + 64) = conf channels [64 b, 64 b + 64), rows [128 b + 64, 128 b + 128) = the same value channels; scale / shift alike),
 // g.n = samples * fuse_group maps, and ep.out_* receive the (samples, ho, wo, cout / 2) fused map.
