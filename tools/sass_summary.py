@@ -1,4 +1,4 @@
-"""Write profiles/r02_sass_summary.txt: per-kernel counts of the SASS mnemonics that prove what the built library runs on
+"""Write profiles/r02c_sass_summary.txt (or the path given as the first argument): per-kernel counts of the SASS mnemonics that prove what the built library runs on
 (UTCHMMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor loads / stores, LDTM = tcgen05.ld from TMEM, FFMA2 = packed fma.rn.f32x2,
 SYNCS / UTCBAR = mbarrier / tcgen05.commit).  Run where the library was built:   python tools/sass_summary.py
 """
@@ -41,7 +41,7 @@ def main():
         lines.append(k[:57].ljust(58) + "".join(str(c.get(m, 0)).rjust(9) for m in MNEMONICS) + str(c["_total"]).rjust(8))
         tot.update(c)
     lines.append("ALL KERNELS".ljust(58) + "".join(str(tot.get(m, 0)).rjust(9) for m in MNEMONICS) + str(tot["_total"]).rjust(8))
-    path = os.path.join(ROOT, "profiles", "r02_sass_summary.txt")
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02c_sass_summary.txt")
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines[:3] + lines[-1:]))

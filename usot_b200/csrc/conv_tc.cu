@@ -46,17 +46,12 @@ constexpr int TC_THREADS = 128 + 128 * TC_EPI_GROUPS;     // warps 0-3: TMA / MM
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB per plane per stage
 
 // PAIR (cta_group::2): a CTA stages only ITS half of the weight rows of the N block (the pair's MMA reads both halves), see conv_tc_kernel.
-// PAIR = 2 (split mode): the pair variant of the fused cross-term MMA.  The hardware takes rows [0, N/2) of an MMA's B operand from the leader
-// and rows [N/2, N) from the peer, at the SAME shared-memory offset: region X (BN rows) holds w_hi in the leader and w_lo in the peer, so ONE
-// N = 2*BN MMA computes a_hi*w_hi -> main | a_hi*w_lo -> cross; region Y (BN/2 rows) holds w_hi rows [0, BN/2) in the leader and [BN/2, BN)
-// in the peer for the a_lo*w_hi -> cross MMA.  A stage is 32 + 24 KiB.
 template <int BN, bool SPLIT, int PAIR = 0>
 struct TcCfg {
-    static_assert(PAIR != 2 || SPLIT, "the fused-cross pair layout exists in split mode only");
     static constexpr int PLANES = SPLIT ? 2 : 1;
     static constexpr int B_ROWS = PAIR ? BN / 2 : BN;     // weight rows staged by one CTA per K-step and plane
     static constexpr int B_BYTES = B_ROWS * TC_BK * 2;
-    static constexpr int B_REGION = PAIR == 2 ? 3 * B_BYTES : PLANES * B_BYTES;   // PAIR = 2: X (2 * B_BYTES) + Y (B_BYTES)
+    static constexpr int B_REGION = PLANES * B_BYTES;
     static constexpr int STAGE_BYTES = PLANES * TC_A_BYTES + B_REGION;
     static constexpr int SMEM_BUDGET = 227 * 1024 - 1024 - 256;  // alignment slack + barriers
     static constexpr bool TMA_OUT = !(SPLIT && BN == 256);  // (the 2-stage 96 KiB ring of that config leaves no room for staging)
@@ -316,17 +311,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         if (elect_one()) {
                             if (cta_rank == 0) mbar_expect_tx(full, tx);
                             tma_load_4d_pair(sa, &p.a[0][par], lfull, cc * TC_BK, w0 + offw, h0 + offh, img);
-                            if constexpr (PAIR == 2) {
-                                // X: the BN rows of w_hi (leader) / w_lo (peer); Y: this CTA's half of the w_hi rows
+                            tma_load_2d_pair(sb, &p.b[0], lfull, ks * TC_BK, brow);
+                            if (SPLIT) {
                                 tma_load_4d_pair(sa + TC_A_BYTES, &p.a[1][par], lfull, cc * TC_BK, w0 + offw, h0 + offh, img);
-                                tma_load_2d_pair(sb, cta_rank ? &p.bx[1] : &p.bx[0], lfull, ks * TC_BK, nb * BN);
-                                tma_load_2d_pair(sb + 2 * Cfg::B_BYTES, &p.b[0], lfull, ks * TC_BK, brow);
-                            } else {
-                                tma_load_2d_pair(sb, &p.b[0], lfull, ks * TC_BK, brow);
-                                if (SPLIT) {
-                                    tma_load_4d_pair(sa + TC_A_BYTES, &p.a[1][par], lfull, cc * TC_BK, w0 + offw, h0 + offh, img);
-                                    tma_load_2d_pair(sb + Cfg::B_BYTES, &p.b[1], lfull, ks * TC_BK, brow);
-                                }
+                                tma_load_2d_pair(sb + Cfg::B_BYTES, &p.b[1], lfull, ks * TC_BK, brow);
                             }
                         }
                     } else if (elect_one()) {
@@ -377,9 +365,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // Fused cross term: the lo weight tile sits right behind the hi tile in the stage and `cross` right behind `main` in
             // TMEM, so ONE MMA with N = 2*BN computes a_hi*w_hi -> main and a_hi*w_lo -> cross while reading a_hi from shared
             // memory once (the operand reads of three N=128 MMAs per k-step saturate the 128 B/clk shared-memory port).
-            const uint32_t idesc2 = make_idesc(PAIR ? 2 * TC_BM : TC_BM, 2 * BN);
+            const uint32_t idesc2 = make_idesc(TC_BM, 2 * BN);
             // (pair: [w_hi | w_lo] of one CTA are not the two halves of an N = 2*BN operand -- the hardware takes rows [0, N/2) from the
-            //  leader and [N/2, N) from the peer -- so the three products are issued as three N = BN MMAs, the tc_fuse_cross = 0 sequence)
+            //  leader and [N/2, N) from the peer -- so the three products are issued as three N = BN MMAs, the tc_fuse_cross = 0 sequence.
+            //  A fused pair layout was built and measured: region X = w_hi in the leader / w_lo in the peer for ONE N = 2*BN MMA, region Y =
+            //  the w_hi halves for a_lo*w_hi, 56 KiB stages, three of them.  Bit-identical, but 2-3 % MORE cycles on the MMA-bound layers than
+            //  this version with its four 48 KiB stages (layer3.0.downsample 6282 k vs 6175 k cycles; profiles/r02c_pair_*): removed.)
             const bool fuse = !PAIR && Cfg::XACC && p.fuse_cross;
             int stage = 0;
             uint32_t phase = 0;
@@ -412,11 +403,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t a_hi = a0 + 2 * k, b_hi = b0 + 2 * k;
                             const uint32_t acc = (started | k) ? 1u : 0u;
-                            if constexpr (PAIR == 2) {   // fused cross term of the pair: X = [w_hi (leader) | w_lo (peer)], Y = the w_hi halves
-                                umma_f16_pair(tmem_d, a_hi, b_hi, idesc2, acc);
-                                umma_f16_pair(tmem_x, a_hi + (TC_A_BYTES >> 4), b_hi + ((2 * Cfg::B_BYTES) >> 4), idesc, 1u);
-                                continue;
-                            }
                             if constexpr (PAIR) {
                                 umma_f16_pair(tmem_d, a_hi, b_hi, idesc, acc);
                                 if (SPLIT) {
@@ -994,7 +980,6 @@ template <int BN, bool SPLIT, int EPI = 0, int PAIR = 0>
 static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     using Cfg = TcCfg<BN, SPLIT, PAIR>;
     static_assert(Cfg::STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
-    extern Tunable g_tc_cta_pair;
     static SmemAttrCache attr;
     if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT, EPI, PAIR>, 227 * 1024)) return rc;
     if (!Cfg::TMA_OUT || EPI != 0) { p.tma_store = 0; p.tma_res = 0; }
@@ -1002,10 +987,7 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     // residual pipeline: 3 buffers / look-ahead 1 (tc_res_ahead = 1, the first version) or look-ahead NB-1 with as many buffers (<= 4) as
     // still leave a two-stage operand ring (split mode: 3 buffers; single-fp16, whose stages are smaller: 4)
     int res_bufs = 3;
-    if (PAIR && p.tma_res && (g_tc_cta_pair & 8) && Cfg::stages_with_bufs(3) < 3 && Cfg::stages_with_bufs(2) >= 3) {
-        res_bufs = 2;   // experiment (bit 3 of tc_cta_pair): a pair's residual layers trade one staging buffer per group for a third ring stage
-        p.res_ahead = 1;
-    } else if (p.tma_res && g_tc_res_ahead >= 2) {
+    if (p.tma_res && g_tc_res_ahead >= 2) {
         if (Cfg::stages_with_bufs(4) >= 2) res_bufs = 4;
         p.res_ahead = res_bufs - 1;
     } else {
@@ -1111,7 +1093,7 @@ static int launch_plan(Plan& pl, bool split, cudaStream_t st) {
     if (pl.p.pool_bands > 0) return split ? launch_cfg<64, true, 2>(pl.p, pl.grid, st) : launch_cfg<64, false, 2>(pl.p, pl.grid, st);
     if (pl.p.group > 1 || pl.p.fuse_cout) return split ? launch_cfg<128, true, 1>(pl.p, pl.grid, st) : launch_cfg<128, false, 1>(pl.p, pl.grid, st);
     if (pl.p.num_pair_tiles > 0) {
-        if (split) return pl.p.pair_fused ? launch_cfg<128, true, 0, 2>(pl.p, pl.grid, st) : launch_cfg<128, true, 0, 1>(pl.p, pl.grid, st);
+        if (split) return launch_cfg<128, true, 0, 1>(pl.p, pl.grid, st);
         if (pl.bn == 256) return launch_cfg<256, false, 0, 1>(pl.p, pl.grid, st);
         return launch_cfg<128, false, 0, 1>(pl.p, pl.grid, st);
     }
@@ -1197,15 +1179,18 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
     bool pair = false;
     if (fuse_group == 0) {
         const int want = split ? (g_tc_cta_pair & 2) : (g_tc_cta_pair & 1);
-        const bool bn_ok = split ? bn == 128 : (bn == 256 || bn == 128);
+        const bool bn_ok = split ? bn == 128 : (bn == 256 || bn == 128);   // (64-wide N tiles as pairs: measured, no gain -- layer1's 3x3 469 k vs 456 k cycles)
         // Where it pays (ncu launch lists of one batch-256 step, profiles/r02c_pair_*): the MMA-bound layers -- every 3x3 and the K = 1024
         // 1x1 layers: tensor pipe 84-91 % -> 91-96 % in fp16x3, -3 ... -8 % time -- but NOT the short-K 1x1 (+ residual) layers, whose
-        // two-stage ring cannot hide the extra leader <-> peer barrier hops (+30 %).  Bit 2 of the tunable overrides the rule (tests).
+        // pair runs 30-38 % SLOWER (also with a third ring stage bought with one staging buffer less: measured, no change -- the two epilogues
+        // of a pair are coupled through the leader's accumulator hand-over).  Bit 2 of the tunable overrides the rule (tests).
         const int k_steps = g.kh * g.kw * (g.cin / TC_BK);
         const bool pays = split ? (k_steps >= 12 && !ep.res_hi) : (k_steps >= 16 && !ep.res_hi && bn == 256 && !(ep.out_hi && ep.out_f32));
         const int pair_tiles = ((img_tiles + 1) / 2) * p.tiles_h * p.tiles_w * p.n_tiles_n;
-        if (want && bn_ok && (pays || (g_tc_cta_pair & 4)) && img_tiles >= 2 && pair_tiles >= num_sms / 2) { pair = true; p.num_pair_tiles = pair_tiles; }
-        p.pair_fused = (pair && split && g_tc_fuse_cross && (g_tc_cta_pair & 16)) ? 1 : 0;   // bit 4: the pair keeps the fused cross-term MMA (TcCfg PAIR = 2)
+        // (single-fp16 mode gains least -- its 3x3 layers are not feed-bound after all: tensor pipe 66-72 % with or without the pair -- and
+        //  at batch 64 the pairs measured 4 % slower: there only grids of at least eight waves run as pairs)
+        const int min_tiles = (split || (g_tc_cta_pair & 4)) ? num_sms / 2 : 8 * (num_sms / 2);
+        if (want && bn_ok && (pays || (g_tc_cta_pair & 4)) && img_tiles >= 2 && pair_tiles >= min_tiles) { pair = true; p.num_pair_tiles = pair_tiles; }
     }
     p.taps = g.kh * g.kw; p.kw = g.kw; p.cin_chunks = g.cin / TC_BK;
     p.stride = g.stride; p.ph = g.ph; p.pw = g.pw; p.dh = g.dh; p.dw = g.dw;
@@ -1241,10 +1226,6 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         cuuint64_t wd[2] = {(cuuint64_t)w.K, (cuuint64_t)g.cout}, ws[1] = {(cuuint64_t)w.K * 2};
         cuuint32_t wb[2] = {(cuuint32_t)TC_BK, (cuuint32_t)(pair ? bn / 2 : bn)};   // (pair: each CTA loads its half of the rows)
         if (int rc = encode_map(&p.b[pl], pl == 0 ? w.hi : w.lo, 2, wd, ws, wb)) return rc;
-        if (p.pair_fused) {   // region X of the fused pair layout: all bn rows of one plane
-            cuuint32_t wx[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
-            if (int rc = encode_map(&p.bx[pl], pl == 0 ? w.hi : w.lo, 2, wd, ws, wx)) return rc;
-        }
     }
 
     p.fuse_cross = g_tc_fuse_cross;

@@ -25,8 +25,6 @@ struct TcParams {
     int hin, skip_pad_rows;        // input height; 1: one-row tiles skip the K-steps whose filter row lies in the zero padding
     int bimg;                      // images per M tile (bw*bh*bimg <= 128 rows; one TMA box {64 ch, bw, bh, bimg})
     int n_tiles_n, num_tiles;
-    CUtensorMap bx[2];    // CTA pairs with the fused cross-term MMA: weight maps [plane] with a box of ALL bn rows (region X, see TcCfg)
-    int pair_fused;       // 1: CTA-pair launch that keeps the fused cross-term MMA (split mode; kernel variant PAIR = 2)
     int num_pair_tiles;   // > 0: CTA-pair launch (cta_group::2, clusters of two CTAs): ceil(image groups / 2) * patches * N blocks
     int group;            // maps walked back to back per (patch, N block): 1, or N_q in the fused Conf_Fusion launch (image = sample * group + q)
     int fuse_cout;        // fused Conf_Fusion: channels of the fused output map (= cout / 2)

@@ -855,7 +855,7 @@ int usot_set_tunable(const char* name, int value) {
     if (!strcmp(name, "tc_res_ahead")) { USOT_REQUIRE(value == 1 || value == 2, "tc_res_ahead must be 1 or 2"); g_tc_res_ahead = value; return 0; }
     if (!strcmp(name, "tc_skip_pad_rows")) { USOT_REQUIRE(value == 0 || value == 1, "tc_skip_pad_rows must be 0 or 1"); g_tc_skip_pad_rows = value; return 0; }
     if (!strcmp(name, "tc_multi_image_tiles")) { USOT_REQUIRE(value == 0 || value == 1, "tc_multi_image_tiles must be 0 or 1"); g_tc_multi_image_tiles = value; return 0; }
-    if (!strcmp(name, "tc_cta_pair")) { USOT_REQUIRE(value >= 0 && value <= 31, "tc_cta_pair must be 0..31 (bit 0: single-fp16 launches, bit 1: fp16x3 launches run as CTA pairs, bit 2: also where it does not pay)"); g_tc_cta_pair = value; return 0; }
+    if (!strcmp(name, "tc_cta_pair")) { USOT_REQUIRE(value >= 0 && value <= 7, "tc_cta_pair must be 0..7 (bit 0: single-fp16 launches, bit 1: fp16x3 launches run as CTA pairs, bit 2: also where it does not pay)"); g_tc_cta_pair = value; return 0; }
     if (!strcmp(name, "tc_pdl")) { USOT_REQUIRE(value == 0 || value == 1, "tc_pdl must be 0 or 1"); g_tc_pdl = value; return 0; }
     if (!strcmp(name, "tc_latency_split")) { USOT_REQUIRE(value == 0 || value == 1, "tc_latency_split must be 0 or 1"); g_tc_latency_split = value; return 0; }
     if (!strcmp(name, "tc_l2_prefetch")) { USOT_REQUIRE(value == 0 || value == 1, "tc_l2_prefetch must be 0 or 1"); g_tc_l2_prefetch = value; return 0; }
