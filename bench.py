@@ -576,7 +576,7 @@ def main():
         pr_gbs = pr["bytes"] / (pr["ms"] / 1e3) / 1e9 if pr["ms"] > 0 else 0.0
         step_ms_prof = sum(f["ms"] for f in prof.values()) / nprof
         traffic = {}
-        for name in ("r02b_roofline_traffic.json", "r02_roofline_traffic.json", "r01b_roofline_traffic.json"):
+        for name in ("r02c_roofline_traffic.json", "r02b_roofline_traffic.json", "r02_roofline_traffic.json", "r01b_roofline_traffic.json"):
             tp = os.path.join(ROOT, "profiles", name)
             if os.path.exists(tp):
                 with open(tp) as f:
@@ -598,7 +598,7 @@ def main():
                          "bound": "tensor", "achieved": conv_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": conv_tflops / pk["tflops_sustained"],
                          "traffic": traffic.get("conv_tc_kernel", {}).get("traffic_bytes_per_launch"),
-                         "traffic_note": f"dram bytes of the dominant launch (layer3.0.downsample) from {traffic_src if traffic else 'n/a'} (ncu --set full); equals its algorithmic bytes",
+                         "traffic_note": f"dram bytes of the dominant launch (layer3.0.downsample) from {traffic_src if traffic else 'n/a'} (ncu --set full); algorithmic bytes of that launch: 1.51 GB",
                          "peak_source": pk["source"] + ", bf16 dense sustained",
                          "achieved_is": "ALGORITHMIC conv FLOPs / summed CUDA-event time of the family's launches (profiled pass of the same step)",
                          "executed_mma_tflops": conv_tflops * mma_per_flop, "executed_mma_frac": conv_tflops * mma_per_flop / pk["tflops_sustained"],
