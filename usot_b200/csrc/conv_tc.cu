@@ -26,8 +26,10 @@
 
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <mutex>
@@ -1056,6 +1058,39 @@ Tunable g_tc_split_bn_max = 128;  // split mode: N <= 128 keeps the separate cro
 //   layers where the pair does not pay (short-K 1x1, residual; used by the tests).  Same results bit for bit.
 Tunable g_tc_cta_pair = 3;
 
+// Can this device keep one CTA pair per SM pair resident?  (cudaOccupancyMaxActiveClusters of the split pair kernel with its full shared-memory
+// footprint; a GPU whose floor-swept GPCs strand SMs, or a context that refuses cluster launches, keeps the one-CTA kernels.)
+static bool pair_launch_supported(int num_sms) {
+    static std::atomic<int> cached[64];   // 0 = unknown, 1 = yes, 2 = no; per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    int c = cached[dev].load();
+    if (c == 0) {
+        int clusters = 0;
+        auto kern = conv_tc_kernel<128, true, 0, 1>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(num_sms & ~1));
+            cfg.blockDim = dim3(TC_THREADS);
+            cfg.dynamicSmemBytes = (size_t)TcCfg<128, true, 1>::smem_bytes(TcCfg<128, true, 1>::STAGES, 1);
+            cudaLaunchAttribute cattr;
+            memset(&cattr, 0, sizeof(cattr));
+            cattr.id = cudaLaunchAttributeClusterDimension;
+            cattr.val.clusterDim.x = 2; cattr.val.clusterDim.y = 1; cattr.val.clusterDim.z = 1;
+            cfg.attrs = &cattr;
+            cfg.numAttrs = 1;
+            e = cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+        c = clusters >= num_sms / 2 ? 1 : 2;
+        if (getenv("USOT_B200_DEBUG")) fprintf(stderr, "usot_b200: device %d keeps %d CTA pairs resident (%d SMs): pair kernels %s\n", dev, clusters, num_sms, c == 1 ? "on" : "off");
+        cached[dev].store(c);
+    }
+    return c == 1;
+}
+
 struct PlanKey {  // plain words only (no padding: the key is hashed and compared as raw bytes)
     const void* ptr[11];
     int geom[14];
@@ -1190,7 +1225,7 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         // (single-fp16 mode gains least -- its 3x3 layers are not feed-bound after all: tensor pipe 66-72 % with or without the pair -- and
         //  at batch 64 the pairs measured 4 % slower: there only grids of at least eight waves run as pairs)
         const int min_tiles = (split || (g_tc_cta_pair & 4)) ? num_sms / 2 : 8 * (num_sms / 2);
-        if (want && bn_ok && (pays || (g_tc_cta_pair & 4)) && img_tiles >= 2 && pair_tiles >= min_tiles) { pair = true; p.num_pair_tiles = pair_tiles; }
+        if (want && bn_ok && (pays || (g_tc_cta_pair & 4)) && img_tiles >= 2 && pair_tiles >= min_tiles && pair_launch_supported(num_sms)) { pair = true; p.num_pair_tiles = pair_tiles; }
     }
     p.taps = g.kh * g.kw; p.kw = g.kw; p.cin_chunks = g.cin / TC_BK;
     p.stride = g.stride; p.ph = g.ph; p.pw = g.pw; p.dh = g.dh; p.dw = g.dw;
