@@ -8,7 +8,7 @@ import re
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libusot_b200.so")
+LIB_PATH = os.environ.get("USOT_B200_LIB") or os.path.join(_HERE, "libusot_b200.so")   # (the override exists for same-job A/B runs of two builds)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "usot_b200.h")
 
 PREC_FP32_SIMT, PREC_FP16X3_TC, PREC_FP16_TC = 0, 1, 2
