@@ -642,7 +642,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         uint32_t gc = 0;                      // running chunk counter: selects the store-staging buffer
         // (single-fp16 mode has no lo planes: nothing is loaded, staged or stored for them)
         if (eall == 0 && p.tma_store) { tma_prefetch_desc(&p.o[0]); if (SPLIT) tma_prefetch_desc(&p.o[1]); }
-        if (eall == 32 && p.tma_res) { tma_prefetch_desc(&p.r[0]); if (SPLIT) tma_prefetch_desc(&p.r[1]); }
+        // (pair kernels never take the TMA-residual path -- the launch rule keeps residual layers on the one-CTA kernel, a forced pair reads its
+        //  residual per thread -- so that machinery, and its registers, are compiled out of them)
+#define tma_res_k (!PAIR && p.tma_res)
+        if (eall == 32 && tma_res_k) { tma_prefetch_desc(&p.r[0]); if (SPLIT) tma_prefetch_desc(&p.r[1]); }
         // TMA-prefetched residual: with NB = p.nbuf staging buffers per group and a look-ahead of D = p.res_ahead chunks, the group's
         // leader requests chunk j+D into buffer (j+D) % NB when chunk j starts; that buffer was last used by chunk j+D-NB, whose bulk
         // store has finished reading shared memory once at most NB-D-1 stores are still pending (wait_group.read NB-D-1).
@@ -653,29 +656,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         //  issuing lane's path -- a first version that computed tile / column / buffer from the chunk index cost the residual layers 8-14 %)
         int rq_tile = t_first, rq_c0 = eg * 32;   // (pair mode: counted in pair tiles like the tile loop)
         uint32_t rq_buf = 0, use_buf = 0, use_phase = 0;
-        auto issue_res = [&](int tq, int c0, uint32_t b) {   // (called by the elected lane)
-            const int t = tile_of(tq);
-            const int nb_ = t % p.n_tiles_n;
+        // (the tile coordinates of the request are decoded once per tile, AFTER the request for the previous tile's last chunk has gone out --
+        //  the four divisions used to sit in front of every chunk's TMA request on the warp the rest of the group waits for at the chunk barrier)
+        int rq_n0 = 0, rq_x0 = 0, rq_y0 = 0, rq_i0 = 0;
+        auto rq_decode = [&]() {
+            const int t = tile_of(rq_tile);
             int mt_ = t / p.n_tiles_n;
+            rq_n0 = (t - mt_ * p.n_tiles_n) * BN;
             const int tw_ = mt_ % p.tiles_w; mt_ /= p.tiles_w;
-            const int th_ = mt_ % p.tiles_h;
-            const int img_ = (mt_ / p.tiles_h) * p.bimg;
+            rq_x0 = tw_ * p.bw;
+            const int im_ = mt_ / p.tiles_h;
+            rq_y0 = (mt_ - im_ * p.tiles_h) * p.bh;
+            rq_i0 = im_ * p.bimg;
+        };
+        auto issue_res = [&](int c0, uint32_t b) {   // (called by the elected lane)
             const uint32_t dst = s_out_u32 + (eg * p.nbuf + b) * Cfg::BUF_BYTES, rb = bar_res + 8 * (eg * TC_RES_BUFS + b);
             mbar_expect_tx(rb, (SPLIT ? 2u : 1u) * p.bw * p.bh * p.bimg * 64u);
-            tma_load_4d(dst, &p.r[0], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
-            if (SPLIT) tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, nb_ * BN + c0, tw_ * p.bw, th_ * p.bh, img_);
+            tma_load_4d(dst, &p.r[0], rb, rq_n0 + c0, rq_x0, rq_y0, rq_i0);
+            if (SPLIT) tma_load_4d(dst + TC_BM * 64, &p.r[1], rb, rq_n0 + c0, rq_x0, rq_y0, rq_i0);
         };
         // (single-thread TMA work of a group: one ELECTED lane of its first warp -- elect.sync picks the same lane every time, so the bulk
         //  async-groups it commits are the ones it later waits for; see elect_one() in tc_ptx.cuh for why not `if (et == 0)`)
         // every lane of the group's first warp keeps the same request state; only the elected lane issues
         auto rq_advance = [&]() {
             rq_c0 += 32 * TC_EPI_GROUPS;
-            if (rq_c0 >= BN) { rq_c0 = eg * 32; rq_tile += t_step; }
+            if (rq_c0 >= BN) { rq_c0 = eg * 32; rq_tile += t_step; if (rq_tile < t_count) rq_decode(); }
             if (++rq_buf == (uint32_t)NB) rq_buf = 0;
         };
-        if (p.tma_res && et < 32 && eg * 32 < BN) {
+        if (tma_res_k && et < 32 && eg * 32 < BN) {
+            if (rq_tile < t_count) rq_decode();
             for (int k = 0; k < RD; ++k) {
-                if (rq_tile < t_count && elect_one()) issue_res(rq_tile, rq_c0, rq_buf);
+                if (rq_tile < t_count && elect_one()) issue_res(rq_c0, rq_buf);
                 __syncwarp();
                 rq_advance();
             }
@@ -705,7 +716,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // Residual loads are software-pipelined one 32-column chunk ahead and the first chunk is requested BEFORE waiting
             // for the accumulator, so their DRAM latency hides behind the MMAs / the previous chunk's math.
             uint4 rh[4], rl[4];
-            const bool has_res = p.res_hi != nullptr && valid && !p.tma_res;
+            const bool has_res = p.res_hi != nullptr && valid && !tma_res_k;
             if (has_res) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -718,14 +729,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * Cfg::ACC_COLS;
 #pragma unroll 1
             for (int c0 = cfirst; c0 < BN; c0 += cstep) {
-                if (p.tma_res && et < 32) {
+                if (tma_res_k && et < 32) {
                     int nc0 = c0 + cstep, ntile = tile;
                     const bool wrap = nc0 >= BN;
                     if (wrap) { nc0 = cfirst; ntile = tile + gridDim.x; }   // (l2_prefetch is never set in pair mode)
                     if (elect_one()) {
                         const int pending = NB - RD - 1;   // stores that may still be reading their staging buffer
                         if (pending <= 0) bulk_wait_read<0>(); else if (pending == 1) bulk_wait_read<1>(); else bulk_wait_read<2>();
-                        if (rq_tile < t_count) issue_res(rq_tile, rq_c0, rq_buf);
+                        if (rq_tile < t_count) issue_res(rq_c0, rq_buf);
                         if (wrap && p.l2_prefetch && ntile < p.num_tiles) {
                             // the first chunk of the next tile is on its way; its REMAINING chunks start their trip from HBM to L2
                             // now (behind that demand load), so the per-chunk loads one chunk ahead no longer pay DRAM latency each
@@ -782,7 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             }
                         }
                     }
-                    if (p.relu && !p.tma_res) {  // (with a TMA residual the add + ReLU happen after the chunk has landed, below)
+                    if (p.relu && !tma_res_k) {  // (with a TMA residual the add + ReLU happen after the chunk has landed, below)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
                     }
@@ -791,7 +802,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         // map and let ONE thread issue the two bulk tensor stores: no per-thread global stores, rows beyond the
                         // image / patch are clipped by the TMA unit.  Two staging buffers alternate; a buffer is reused only after
                         // the stores issued from it have finished reading shared memory.
-                        const uint32_t buf = eg * p.nbuf + (p.tma_res ? use_buf : 0);
+                        const uint32_t buf = eg * p.nbuf + (tma_res_k ? use_buf : 0);
                         uint8_t* rp = s_out + buf * Cfg::BUF_BYTES + row * 64;
                         const int sw = (row >> 1) & 3;
                         if (p.tma_f32) {
@@ -816,7 +827,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             ++gc;
                             continue;
                         }
-                        if (p.tma_res) {
+                        if (tma_res_k) {
                             mbar_wait(bar_res + 8 * (eg * TC_RES_BUFS + use_buf), use_phase);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -867,7 +878,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             __syncwarp();
                         }
                         ++gc;
-                        if (p.tma_res && ++use_buf == (uint32_t)NB) { use_buf = 0; use_phase ^= 1; }
+                        if (tma_res_k && ++use_buf == (uint32_t)NB) { use_buf = 0; use_phase ^= 1; }
                     } else if (p.out_hi) {
                         uint4* oh4 = reinterpret_cast<uint4*>(p.out_hi + off);
                         uint4* ol4 = reinterpret_cast<uint4*>(p.out_lo + off);
@@ -911,6 +922,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
+#undef tma_res_k
 #undef cta_rank
 #undef t_first
 #undef t_step
@@ -984,7 +996,7 @@ static int launch_cfg(TcParams& p, int grid, cudaStream_t st) {
     static_assert(Cfg::STAGES >= 2, "not enough shared memory for a 2-stage pipeline");
     static SmemAttrCache attr;
     if (int rc = attr.ensure(conv_tc_kernel<BN, SPLIT, EPI, PAIR>, 227 * 1024)) return rc;
-    if (!Cfg::TMA_OUT || EPI != 0) { p.tma_store = 0; p.tma_res = 0; }
+    if (!Cfg::TMA_OUT || EPI != 0 || PAIR) { if (!Cfg::TMA_OUT || EPI != 0) p.tma_store = 0; p.tma_res = 0; }
     if (p.tma_res && Cfg::STAGES_RES < 2) p.tma_res = 0;
     // residual pipeline: 3 buffers / look-ahead 1 (tc_res_ahead = 1, the first version) or look-ahead NB-1 with as many buffers (<= 4) as
     // still leave a two-stage operand ring (split mode: 3 buffers; single-fp16, whose stages are smaller: 4)
