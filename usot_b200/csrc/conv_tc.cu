@@ -1229,8 +1229,8 @@ int launch_conv_tc(const TcTensor& in, const ConvGeom& g, const TcWeights& w, co
         const bool bn_ok = split ? bn == 128 : (bn == 256 || bn == 128);   // (64-wide N tiles as pairs: measured, no gain -- layer1's 3x3 469 k vs 456 k cycles)
         // Where it pays (ncu launch lists of one batch-256 step, profiles/r02c_pair_*): the MMA-bound layers -- every 3x3 and the K = 1024
         // 1x1 layers: tensor pipe 84-91 % -> 91-96 % in fp16x3, -3 ... -8 % time -- but NOT the short-K 1x1 (+ residual) layers, whose
-        // pair runs 30-38 % SLOWER (also with a third ring stage bought with one staging buffer less: measured, no change -- the two epilogues
-        // of a pair are coupled through the leader's accumulator hand-over).  Bit 2 of the tunable overrides the rule (tests).
+        // pair runs 30-38 % SLOWER (also with a third ring stage bought with one staging buffer less: measured, no change; these layers are
+        // epilogue-bound, and -- presumably the reason -- the two epilogues of a pair are coupled through the leader's accumulator hand-over).  Bit 2 of the tunable overrides the rule (tests).
         const int k_steps = g.kh * g.kw * (g.cin / TC_BK);
         const bool pays = split ? (k_steps >= 12 && !ep.res_hi) : (k_steps >= 16 && !ep.res_hi && bn == 256 && !(ep.out_hi && ep.out_f32));
         const int pair_tiles = ((img_tiles + 1) / 2) * p.tiles_h * p.tiles_w * p.n_tiles_n;
