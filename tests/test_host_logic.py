@@ -105,3 +105,34 @@ def test_torch_ops_namespace_is_registered_and_has_no_cpu_kernel():
         torch.ops.usot_b200.prroi_pooling_forward(torch.zeros(1, 4, 5, 5), torch.zeros(1, 5), 7, 7, 1.0)
     with pytest.raises(NotImplementedError):
         torch.ops.usot_b200.xcorr_depthwise(torch.zeros(1, 4, 9, 9), torch.zeros(1, 4, 3, 3))
+
+
+def test_cta_pair_tile_mapping_covers_every_tile_once():
+    """Model of conv_tc.cu's pair-tile mapping (tile_of() in conv_tc_kernel, num_pair_tiles in launch_conv_tc): CTA rank r of pair tile t owns the
+    ordinary tile of image group 2*gp + r at the same (patch, N block).  Every real tile must be owned exactly once, partners must share patch
+    row and N block (the MMA issuer skips the same padded K-steps for both), and only an odd group count may produce phantom tiles."""
+    import itertools
+
+    def tile_of(t, rank, n_tiles_n, tiles_w, tiles_h):
+        nb, r = t % n_tiles_n, t // n_tiles_n
+        sp = tiles_w * tiles_h
+        s, gp = r % sp, r // sp
+        return ((2 * gp + rank) * sp + s) * n_tiles_n + nb
+
+    for img_tiles, tiles_h, tiles_w, n_tiles_n in itertools.product((2, 3, 5, 8, 13), (1, 25, 31), (1, 2), (1, 2, 8)):
+        sp = tiles_w * tiles_h
+        num_tiles = img_tiles * sp * n_tiles_n
+        num_pair_tiles = ((img_tiles + 1) // 2) * sp * n_tiles_n
+        owned, phantom = [], 0
+        for t in range(num_pair_tiles):
+            a, b = (tile_of(t, r, n_tiles_n, tiles_w, tiles_h) for r in (0, 1))
+            assert a % n_tiles_n == b % n_tiles_n                                   # same N block
+            assert (a // n_tiles_n) % sp == (b // n_tiles_n) % sp                    # same patch (row and column tile)
+            assert (b // n_tiles_n) // sp == (a // n_tiles_n) // sp + 1              # neighbouring image groups
+            for x in (a, b):
+                if (x // n_tiles_n) // sp >= img_tiles:
+                    phantom += 1                                                    # decodes to an image index past the batch: TMA zero-fills / clips it
+                else:
+                    owned.append(x)
+        assert sorted(owned) == list(range(num_tiles))
+        assert phantom == (sp * n_tiles_n if img_tiles % 2 else 0)
